@@ -1,0 +1,207 @@
+/*
+ * miden_b200.h -- C ABI of the Blackwell (sm_100a) STARK proving backend for Miden VM.
+ *
+ * Drop-in boundary: everything beneath `miden_prover::prove_stark()` (reference
+ * prover/src/lib.rs:317-355), i.e. `ProverInstance::new(config, statement, None)?.prove(challenger)`
+ * (crates/lifted-stark/src/prover/mod.rs:139,157,230-578).  The Rust host keeps trace generation,
+ * the AIR (lowered once to an op-list, see mdn_air.program), the LogUp aux-trace builder
+ * (a callback) and wincode serialisation of the returned streams.  INTEGRATION.md shows the
+ * Rust `extern "C"` binding.
+ *
+ * Conventions
+ *   - every field element is a canonical Goldilocks u64 (< 2^64 - 2^32 + 1); quadratic-extension
+ *     elements are two consecutive u64 (c0, c1), u^2 = 7 -- the layout of the reference's
+ *     `Felt` / `QuadFelt` (crates/field/src/native/mod.rs:58, flatten_to_base order).
+ *   - matrices are row-major exactly like p3 `RowMajorMatrix<Felt>`; the library transposes on
+ *     the device.
+ *   - functions return 0 on success and a negative mdn_status otherwise; the message is
+ *     available through mdn_last_error().  Errors mirror `ProverError` / `ExecutionError::
+ *     ProvingError(String)` (prover/mod.rs:582-596, prover/src/lib.rs:336-345).
+ *   - a session is bound to one CUDA device and is not thread-safe; sessions are independent.
+ *   - there is NO CPU fallback: if no CUDA device is usable, mdn_session_create fails.
+ */
+#ifndef MIDEN_B200_H
+#define MIDEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mdn_session mdn_session;
+
+typedef enum {
+    MDN_OK = 0,
+    MDN_ERR_INVALID_ARG = -1,      /* malformed statement / trace shape (InstanceError) */
+    MDN_ERR_DOMAIN = -2,           /* DomainError: LDE order too large, degree > blowup */
+    MDN_ERR_CUDA = -3,             /* device error (message carries the CUDA string) */
+    MDN_ERR_UNSUPPORTED = -4,      /* e.g. folding arity other than 4, preprocessed columns */
+    MDN_ERR_AUX_BUILDER = -5,      /* aux-trace callback failed */
+    MDN_ERR_NO_DEVICE = -6,
+} mdn_status;
+
+/* PcsParams::new(log_blowup, log_folding_arity, log_final_degree, folding_pow_bits,
+ * deep_pow_bits, num_queries, query_pow_bits) -- crates/lifted-stark/src/pcs/params.rs:53-99.
+ * Miden production values: air/src/config.rs:55-67 = {3, 2, 7, 4, 12, 27, 16}. */
+typedef struct {
+    uint32_t log_blowup;
+    uint32_t log_folding_arity;
+    uint32_t log_final_degree;
+    uint32_t folding_pow_bits;
+    uint32_t deep_pow_bits;
+    uint32_t num_queries;
+    uint32_t query_pow_bits;
+} mdn_pcs_params;
+
+/* p3 `DuplexChallenger<Felt, Poseidon2, 12, 8>` state (public fields used at
+ * air/src/config.rs:264-271): sponge_state, input_buffer, output_buffer.  output_len counts the
+ * unread rate elements; the next sample returns sponge_state[output_len - 1]. */
+typedef struct {
+    uint64_t sponge_state[12];
+    uint64_t input_buffer[8];
+    uint32_t input_len;
+    uint32_t output_len;
+} mdn_challenger;
+
+/* One AIR of the MultiAir (crates/lifted-air/src/air.rs:47-202 `LiftedAir`): shape + constraint
+ * program.  `program` is the op-list lowering of `air.eval()`:
+ *   words[0..5) = { 0x5249414D ("MAIR"), 1, n_nodes, n_constraints, n_consts }
+ *   nodes: 3 words each { op, a, b }; constraints: node ids in emission order;
+ *   consts: (lo, hi) word pairs.
+ * Ops (leaf vocabulary of crates/ace-codegen/src/dag/lower.rs:109-210):
+ *   0 MAIN(a=row offset 0|1, b=col)  1 AUX(a=offset, b=EF col)  2 PUBLIC(a)  3 CHALLENGE(a)
+ *   4 AUX_VALUE(a)  5 IS_FIRST_ROW  6 IS_LAST_ROW  7 IS_TRANSITION  8 CONST(a)  9 EXT_CONST(a)
+ *   10 ADD(a,b)  11 SUB(a,b)  12 MUL(a,b)  13 NEG(a)
+ * Constraints are folded as acc <- acc*alpha + C_k in emission order
+ * (crates/lifted-stark/src/verifier/constraints.rs:83,108). */
+typedef struct {
+    uint32_t width;                 /* BaseAir::width -- main trace columns */
+    uint32_t aux_width;             /* LiftedAir::aux_width -- EF columns */
+    uint32_t num_aux_values;        /* LiftedAir::num_aux_values */
+    uint32_t num_randomness;        /* LiftedAir::num_randomness */
+    uint32_t log_quotient_degree;   /* domain.rs:585-598 (symbolic degree analysis stays host-side) */
+    uint32_t program_words;
+    const uint32_t* program;
+} mdn_air;
+
+/* p3 RowMajorMatrix<Felt>: `values` has (1 << log_height) * width entries.  With
+ * MDN_FLAG_DEVICE_TRACES `values` is a device pointer on the session's device. */
+typedef struct {
+    const uint64_t* values;
+    uint32_t log_height;
+    uint32_t width;
+} mdn_matrix;
+
+/* crates/lifted-air/src/statement.rs `Statement`: AIRs in instance order, shared air_inputs, and
+ * the exact felts `Statement::observe` absorbs (AIR-specific, e.g. air/src/lib.rs:817-847). */
+typedef struct {
+    const mdn_air* airs;
+    uint32_t n_airs;
+    const uint64_t* public_values;
+    uint32_t n_public_values;
+    const uint64_t* observe_felts;
+    uint32_t n_observe_felts;
+} mdn_statement;
+
+/* `LiftedAir::build_aux_trace(main, air_inputs, aux_inputs, challenges)` (prover/mod.rs:357-381),
+ * called once per AIR in instance order after the main root is observed.
+ *   randomness : 2 * num_randomness u64
+ *   aux_out    : (1 << log_height) x (2 * aux_width) row-major, EF flattened to base
+ *   aux_values : 2 * num_aux_values u64
+ * Return 0 on success.  A NULL builder means all-zero aux traces and values
+ * (crates/lifted-stark/src/testing/airs/miden.rs:84-94). */
+typedef int (*mdn_aux_builder)(void* ctx, uint32_t instance, const mdn_matrix* main,
+                               const uint64_t* randomness, uint64_t* aux_out, uint64_t* aux_values);
+
+/* `StarkProofData { log_trace_heights, transcript: TranscriptData { fields, commitments } }`
+ * (crates/lifted-stark/src/proof.rs:57-63, crates/stark-transcript/src/data.rs:11-15).
+ * Memory is owned by the session and valid until the next prove on it or its destruction. */
+typedef struct {
+    const uint8_t* log_trace_heights;
+    size_t n_heights;
+    const uint64_t* fields;
+    size_t n_fields;
+    const uint64_t* commitments;    /* 4 u64 per commitment */
+    size_t n_commitments;
+} mdn_proof;
+
+enum {
+    MDN_FLAG_DEVICE_TRACES = 1u,    /* trace matrices already resident in device memory */
+};
+
+/* ---- session ------------------------------------------------------------------------------ */
+int mdn_session_create(const mdn_pcs_params* params, int cuda_device, mdn_session** out);
+void mdn_session_destroy(mdn_session* s);
+const char* mdn_last_error(const mdn_session* s);   /* s may be NULL: last create error */
+
+/* ---- the drop-in: ProverInstance::prove (prover/mod.rs:230-578) ------------------------------
+ * `challenger` is the caller's pre-bound challenger (protocol params observed,
+ * prover/src/lib.rs:329-330); the statement felts and instance shape are observed inside, as the
+ * reference does (mod.rs:290-291). */
+int mdn_prove(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces /* instance order */,
+              const mdn_challenger* challenger, mdn_aux_builder build_aux, void* aux_ctx,
+              uint32_t flags, mdn_proof* out);
+
+/* ---- the same path, staged (for hosts that prefer to drive the aux build themselves) -------- */
+int mdn_prove_begin(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces,
+                    const mdn_challenger* challenger, uint32_t flags,
+                    uint64_t main_root[4], uint64_t* randomness_out /* 2*max num_randomness */);
+int mdn_prove_commit_aux(mdn_session* s, const mdn_matrix* aux /* instance order, base-flattened */,
+                         const uint64_t* const* aux_values /* per instance, 2*num_aux_values */,
+                         uint64_t aux_root[4]);
+int mdn_prove_finish(mdn_session* s, mdn_proof* out);
+
+/* wincode/bincode-default layout of StarkProofData (prover/src/lib.rs:347-354): u64-LE length +
+ * height bytes; u64-LE length + u64-LE felts; u64-LE length + 32-byte commitments.  Returns the
+ * number of bytes needed; writes only if cap is large enough.  (Layout unpinned in-tree.) */
+size_t mdn_proof_serialize(const mdn_proof* p, uint8_t* out, size_t cap);
+
+/* ---- the two trait seams of StarkConfig (crates/lifted-stark/src/config.rs:26-45) ----------- */
+/* Dft::coset_lde_batch(mat, added_bits, shift) as used at prover/commit.rs:173.  `out` receives
+ * the (1 << (log_height+added_bits)) x width result, row-major, rows in bit-reversed order. */
+int mdn_coset_lde_batch(mdn_session* s, const mdn_matrix* mat, uint32_t added_bits, uint64_t shift,
+                        uint64_t* out);
+/* Lmcs::build_aligned_tree(ldes).root() (lmcs/config.rs:125-139) for matrices given in domain
+ * (natural) order, ascending heights.  */
+int mdn_lmcs_commit(mdn_session* s, const mdn_matrix* mats_domain_order, uint32_t n_mats,
+                    uint64_t root[4]);
+/* Poseidon2 permutation on `n` independent 12-element states (crates/crypto/src/hash/
+ * algebraic_sponge/poseidon2/mod.rs:31-37), device-computed. */
+int mdn_poseidon2_permute(mdn_session* s, uint64_t* states /* n x 12 */, size_t n);
+
+/* ---- host-side transcript helpers -----------------------------------------------------------
+ * `CanObserve::observe` / `CanSample::sample` of the duplex challenger for hosts without p3
+ * (tests, bench); sequential sponge steps on the CPU, exactly what the reference's host does.
+ * Semantics: crates/lib/core/asm/stark/random_coin.masm:103-115,128-135,181-210,272-296. */
+void mdn_challenger_observe(mdn_challenger* c, const uint64_t* felts, size_t n);
+uint64_t mdn_challenger_sample(mdn_challenger* c);
+
+/* ---- introspection for stage-level parity tests and the benchmark ---------------------------- */
+typedef enum {
+    MDN_INFO_MAIN_ROOT = 0,        /* 4 u64 */
+    MDN_INFO_AUX_ROOT = 1,         /* 4 u64 */
+    MDN_INFO_QUOTIENT_ROOT = 2,    /* 4 u64 */
+    MDN_INFO_OOD_POINT = 3,        /* 2 u64 */
+    MDN_INFO_QUOTIENT_ACC = 4,     /* N_max*D EF values, natural order on gJ */
+    MDN_INFO_DEEP_EVALS = 5,       /* L EF values, bit-reversed order */
+    MDN_INFO_FRI_ROOTS = 6,        /* 4 u64 per round */
+    MDN_INFO_QUERY_INDICES = 7,    /* num_queries u64 */
+} mdn_info;
+/* Copies at most cap u64 into out; returns the number of u64 available (or <0). */
+long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap);
+
+/* Per-phase device timings of the last prove, in milliseconds (CUDA events on the session's
+ * stream).  Names follow the reference's tracing spans (prover/mod.rs:339,412,445,542,561). */
+typedef struct {
+    float h2d_transpose, commit_main, commit_aux, evaluate_constraints, commit_quotient, open, total;
+    float lde_main, hash_main;          /* inside commit_main */
+    unsigned long long kernel_launches; /* kernels launched by the last prove */
+} mdn_timings;
+int mdn_get_timings(mdn_session* s, mdn_timings* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIDEN_B200_H */

@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE ONLY (see field.hpp header).
+// AIR constraint programs: a flat op-list evaluated at one point of the quotient domain.
+//
+// The reference evaluates `air.eval(builder)` (generic Rust) at every point
+// (crates/lifted-stark/src/prover/constraints/mod.rs:83-278).  A C-ABI backend cannot call Rust
+// generics, so the host shim lowers `eval` once to a DAG with the leaf/op vocabulary the reference
+// already enumerates in crates/ace-codegen/src/dag/lower.rs:109-210, and ships it as the op-list
+// below (format shared with include/miden_b200.h).  Constraints are folded in emission order
+// with the verifier's orientation acc <- acc*alpha + C_k
+// (crates/lifted-stark/src/verifier/constraints.rs:83,108).
+#pragma once
+#include "field.hpp"
+#include <stdexcept>
+#include <string>
+
+namespace orc {
+
+enum AirOp : uint32_t {
+    OP_MAIN = 0,        // a = row offset (0 local, 1 next), b = column          -> F
+    OP_AUX = 1,         // a = row offset, b = EF column (base cols 2b, 2b+1)     -> EF
+    OP_PUBLIC = 2,      // a = public value index                                  -> F
+    OP_CHALLENGE = 3,   // a = randomness index                                    -> EF
+    OP_AUX_VALUE = 4,   // a = aux (permutation) value index                       -> EF
+    OP_IS_FIRST = 5,    //                                                          -> F
+    OP_IS_LAST = 6,     //                                                          -> F
+    OP_IS_TRANSITION = 7,  //                                                       -> F
+    OP_CONST = 8,       // a = constant-pool index                                 -> F
+    OP_EXT_CONST = 9,   // a = constant-pool index of (c0, c1)                     -> EF
+    OP_ADD = 10, OP_SUB = 11, OP_MUL = 12,  // a, b = node ids; EF if either is EF
+    OP_NEG = 13,        // a = node id
+};
+
+struct AirNode { uint32_t op, a, b; };
+
+struct AirProgram {
+    std::vector<AirNode> nodes;
+    std::vector<uint32_t> constraints;   // node ids, emission order
+    std::vector<u64> consts;
+    std::vector<uint8_t> is_ext;         // derived per node
+
+    static constexpr uint32_t MAGIC = 0x5249414Du;  // "MAIR"
+
+    // Serialized form: u32 words [MAGIC, version=1, n_nodes, n_constraints, n_consts,
+    //   nodes (3 words each), constraints, consts (lo, hi words each)].
+    static AirProgram parse(const uint32_t* w, size_t n_words) {
+        if (n_words < 5 || w[0] != MAGIC || w[1] != 1) throw std::runtime_error("air program: bad header");
+        size_t nn = w[2], nc = w[3], nk = w[4];
+        if (n_words != 5 + 3 * nn + nc + 2 * nk) throw std::runtime_error("air program: bad length");
+        AirProgram p;
+        const uint32_t* q = w + 5;
+        for (size_t i = 0; i < nn; i++, q += 3) p.nodes.push_back({q[0], q[1], q[2]});
+        for (size_t i = 0; i < nc; i++) p.constraints.push_back(*q++);
+        for (size_t i = 0; i < nk; i++, q += 2) p.consts.push_back((u64)q[0] | ((u64)q[1] << 32));
+        p.is_ext.resize(nn);
+        for (size_t i = 0; i < nn; i++) {
+            const AirNode& nd = p.nodes[i];
+            switch (nd.op) {
+                case OP_AUX: case OP_CHALLENGE: case OP_AUX_VALUE: case OP_EXT_CONST: p.is_ext[i] = 1; break;
+                case OP_ADD: case OP_SUB: case OP_MUL:
+                    if (nd.a >= i || nd.b >= i) throw std::runtime_error("air program: forward reference");
+                    p.is_ext[i] = p.is_ext[nd.a] | p.is_ext[nd.b]; break;
+                case OP_NEG:
+                    if (nd.a >= i) throw std::runtime_error("air program: forward reference");
+                    p.is_ext[i] = p.is_ext[nd.a]; break;
+                default:
+                    if (nd.op > OP_NEG) throw std::runtime_error("air program: unknown op");
+                    p.is_ext[i] = 0;
+            }
+        }
+        for (uint32_t c : p.constraints) if (c >= nn) throw std::runtime_error("air program: bad constraint id");
+        return p;
+    }
+};
+
+// Everything a program can read at one evaluation point.
+struct AirPoint {
+    const Fp* main_local; const Fp* main_next;
+    const Fp* aux_local; const Fp* aux_next;   // base-field layout: EF column c = (aux[2c], aux[2c+1])
+    const Fp* publics; const Ef* challenges; const Ef* aux_values;
+    Ef is_first, is_last, is_transition;       // EF so the same evaluator serves the OOD check
+    // For the OOD check main/aux cells are EF; then these are used instead of the Fp pointers.
+    const Ef* main_local_ef = nullptr; const Ef* main_next_ef = nullptr;
+    const Ef* aux_local_ef = nullptr; const Ef* aux_next_ef = nullptr;
+};
+
+// Evaluate all nodes; returns the alpha-folded constraint sum.
+inline Ef air_eval_folded(const AirProgram& p, const AirPoint& pt, Ef alpha, std::vector<Ef>& scratch) {
+    scratch.resize(p.nodes.size());
+    for (size_t i = 0; i < p.nodes.size(); i++) {
+        const AirNode& nd = p.nodes[i];
+        Ef v;
+        switch (nd.op) {
+            case OP_MAIN:
+                if (pt.main_local_ef) v = (nd.a ? pt.main_next_ef : pt.main_local_ef)[nd.b];
+                else v = Ef((nd.a ? pt.main_next : pt.main_local)[nd.b]);
+                break;
+            case OP_AUX:
+                if (pt.aux_local_ef) v = (nd.a ? pt.aux_next_ef : pt.aux_local_ef)[nd.b];
+                else { const Fp* r = nd.a ? pt.aux_next : pt.aux_local; v = Ef(r[2 * nd.b], r[2 * nd.b + 1]); }
+                break;
+            case OP_PUBLIC: v = Ef(pt.publics[nd.a]); break;
+            case OP_CHALLENGE: v = pt.challenges[nd.a]; break;
+            case OP_AUX_VALUE: v = pt.aux_values[nd.a]; break;
+            case OP_IS_FIRST: v = pt.is_first; break;
+            case OP_IS_LAST: v = pt.is_last; break;
+            case OP_IS_TRANSITION: v = pt.is_transition; break;
+            case OP_CONST: v = Ef(Fp(p.consts[nd.a])); break;
+            case OP_EXT_CONST: v = Ef(Fp(p.consts[nd.a]), Fp(p.consts[nd.a + 1])); break;
+            case OP_ADD: v = scratch[nd.a] + scratch[nd.b]; break;
+            case OP_SUB: v = scratch[nd.a] - scratch[nd.b]; break;
+            case OP_MUL: v = scratch[nd.a] * scratch[nd.b]; break;
+            case OP_NEG: v = -scratch[nd.a]; break;
+        }
+        scratch[i] = v;
+    }
+    Ef acc;
+    for (uint32_t c : p.constraints) acc = acc * alpha + scratch[c];
+    return acc;
+}
+
+}  // namespace orc

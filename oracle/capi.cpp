@@ -1,0 +1,205 @@
+// TEST INFRASTRUCTURE ONLY (see field.hpp header).
+// C entry points of the CPU oracle, loaded with ctypes by tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs.  The struct layouts deliberately equal the
+// ones in include/miden_b200.h so a test can hand the same buffers to both sides; the two
+// libraries share no code.
+#include "stark.hpp"
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace orc;
+
+extern "C" {
+
+struct orc_pcs_params { uint32_t log_blowup, log_folding_arity, log_final_degree, folding_pow_bits, deep_pow_bits, num_queries, query_pow_bits; };
+struct orc_challenger { uint64_t sponge_state[12]; uint64_t input_buffer[8]; uint32_t input_len, output_len; };
+struct orc_air { uint32_t width, aux_width, num_aux_values, num_randomness, log_quotient_degree, program_words; const uint32_t* program; };
+struct orc_matrix { const uint64_t* values; uint32_t log_height, width; };
+struct orc_statement { const orc_air* airs; uint32_t n_airs; const uint64_t* public_values; uint32_t n_public_values; const uint64_t* observe_felts; uint32_t n_observe_felts; };
+typedef int (*orc_aux_builder)(void* ctx, uint32_t instance, const orc_matrix* main, const uint64_t* randomness, uint64_t* aux_out, uint64_t* aux_values);
+struct orc_proof { const uint8_t* log_trace_heights; size_t n_heights; const uint64_t* fields; size_t n_fields; const uint64_t* commitments; size_t n_commitments; };
+
+static thread_local std::string g_err;
+const char* orc_last_error() { return g_err.c_str(); }
+
+void orc_poseidon2_permute(uint64_t* st, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        State s; for (int k = 0; k < 12; k++) s[k] = Fp(st[12 * i + k]);
+        poseidon2_permute(s);
+        for (int k = 0; k < 12; k++) st[12 * i + k] = s[k].v;
+    }
+}
+
+uint64_t orc_fp_mul(uint64_t a, uint64_t b) { return (Fp(a) * Fp(b)).v; }
+uint64_t orc_fp_inv(uint64_t a) { return fp_inv(Fp(a)).v; }
+uint64_t orc_two_adic_generator(uint32_t bits) { return two_adic_generator(bits).v; }
+uint64_t orc_lde_shift(uint32_t log_lde) { return lde_shift(log_lde).v; }
+
+static Matrix to_matrix(const orc_matrix& m) {
+    Matrix r(size_t(1) << m.log_height, m.width);
+    for (size_t i = 0; i < r.v.size(); i++) r.v[i] = Fp(m.values[i]);
+    return r;
+}
+
+// Naive O(n^2) DFT of one column (natural -> natural), the anchor for the fast transforms.
+void orc_naive_dft(const uint64_t* in, uint32_t log_n, uint64_t* out) {
+    size_t n = size_t(1) << log_n;
+    Fp w = two_adic_generator(log_n);
+    for (size_t k = 0; k < n; k++) {
+        Fp wk = fp_pow(w, k), x = Fp::raw(1), acc;
+        for (size_t j = 0; j < n; j++) { acc = acc + Fp(in[j]) * x; x = x * wk; }
+        out[k] = acc.v;
+    }
+}
+void orc_dft(const uint64_t* in, uint32_t log_n, uint32_t width, int inverse, uint64_t* out) {
+    orc_matrix om{in, log_n, width};
+    Matrix m = to_matrix(om);
+    if (inverse) idft_rows(m); else dft_rows(m);
+    for (size_t i = 0; i < m.v.size(); i++) out[i] = m.v[i].v;
+}
+
+// coset_lde_batch: bit-reversed rows, row-major.
+void orc_coset_lde_batch(const orc_matrix* mat, uint32_t added_bits, uint64_t shift, uint64_t* out) {
+    Matrix r = coset_lde_bitrev(to_matrix(*mat), added_bits, Fp(shift));
+    for (size_t i = 0; i < r.v.size(); i++) out[i] = r.v[i].v;
+}
+
+// build_aligned_tree over matrices given in DOMAIN order (ascending heights); returns the root and,
+// if layers_out != NULL, all digest layers top-down (2^(depth+1) - 1 digests).
+void orc_lmcs_commit(const orc_matrix* mats, uint32_t n, uint64_t root[4], uint64_t* layers_out) {
+    std::vector<Matrix> ms;
+    for (uint32_t i = 0; i < n; i++) { Matrix m = to_matrix(mats[i]); bit_reverse_rows(m); ms.push_back(std::move(m)); }
+    LmcsTree t = LmcsTree::build(std::move(ms), 8);
+    for (int i = 0; i < 4; i++) root[i] = t.root()[i].v;
+    if (layers_out) {
+        size_t o = 0;
+        for (auto& layer : t.layers) for (auto& d : layer) for (int i = 0; i < 4; i++) layers_out[o++] = d[i].v;
+    }
+}
+
+// Challenger scripting for transcript parity tests: ops[i] = 0 observe(arg) / 1 sample / 2 sample_bits(arg)
+// / 3 grind(arg).  out[i] receives the sampled value / witness (0 for observe).
+void orc_challenger_script(orc_challenger* c, const uint32_t* ops, const uint64_t* args, size_t n, uint64_t* out) {
+    Challenger ch;
+    for (int i = 0; i < 12; i++) ch.st[i] = Fp(c->sponge_state[i]);
+    for (uint32_t i = 0; i < c->input_len; i++) ch.in_buf[i] = Fp(c->input_buffer[i]);
+    ch.in_len = c->input_len; ch.out_len = c->output_len;
+    for (size_t i = 0; i < n; i++) {
+        switch (ops[i]) {
+            case 0: ch.observe(Fp(args[i])); out[i] = 0; break;
+            case 1: out[i] = ch.sample().v; break;
+            case 2: out[i] = ch.sample_bits((unsigned)args[i]); break;
+            case 3: out[i] = ch.grind((unsigned)args[i]).v; break;
+        }
+    }
+    for (int i = 0; i < 12; i++) c->sponge_state[i] = ch.st[i].v;
+    for (int i = 0; i < 8; i++) c->input_buffer[i] = i < ch.in_len ? ch.in_buf[i].v : 0;
+    c->input_len = ch.in_len; c->output_len = ch.out_len;
+}
+
+struct orc_prove_result {
+    Proof proof;
+    ProveDebug dbg;
+    std::vector<uint64_t> fields, commitments;
+};
+
+static Statement to_statement(const orc_statement* st) {
+    Statement s;
+    for (uint32_t i = 0; i < st->n_airs; i++) {
+        const orc_air& a = st->airs[i];
+        AirDesc d;
+        d.width = a.width; d.aux_width = a.aux_width; d.num_aux_values = a.num_aux_values;
+        d.num_randomness = a.num_randomness; d.log_quotient_degree = a.log_quotient_degree;
+        d.program = AirProgram::parse(a.program, a.program_words);
+        s.airs.push_back(std::move(d));
+    }
+    for (uint32_t i = 0; i < st->n_public_values; i++) s.public_values.push_back(Fp(st->public_values[i]));
+    for (uint32_t i = 0; i < st->n_observe_felts; i++) s.observe_felts.push_back(Fp(st->observe_felts[i]));
+    return s;
+}
+static Challenger to_challenger(const orc_challenger* c) {
+    Challenger ch;
+    for (int i = 0; i < 12; i++) ch.st[i] = Fp(c->sponge_state[i]);
+    for (uint32_t i = 0; i < c->input_len; i++) ch.in_buf[i] = Fp(c->input_buffer[i]);
+    ch.in_len = c->input_len; ch.out_len = c->output_len;
+    return ch;
+}
+static PcsParams to_params(const orc_pcs_params* p) {
+    PcsParams q;
+    q.log_blowup = p->log_blowup; q.log_folding_arity = p->log_folding_arity; q.log_final_degree = p->log_final_degree;
+    q.folding_pow_bits = p->folding_pow_bits; q.deep_pow_bits = p->deep_pow_bits; q.num_queries = p->num_queries;
+    q.query_pow_bits = p->query_pow_bits;
+    return q;
+}
+
+// Full prove.  Returns an opaque handle (NULL on error); `out` points into it.
+void* orc_prove(const orc_pcs_params* params, const orc_statement* st, const orc_matrix* traces,
+                const orc_challenger* challenger, orc_aux_builder cb, void* ctx, orc_proof* out) {
+    try {
+        Statement s = to_statement(st);
+        std::vector<Matrix> tr;
+        for (uint32_t i = 0; i < st->n_airs; i++) tr.push_back(to_matrix(traces[i]));
+        AuxBuilder ab;
+        if (cb) ab = [&](size_t inst, const Matrix& main, const std::vector<Ef>& r, Matrix& aux, std::vector<Ef>& av) {
+            std::vector<uint64_t> rr; for (auto& e : r) { rr.push_back(e.a.v); rr.push_back(e.b.v); }
+            std::vector<uint64_t> ao(aux.v.size()), avo(2 * av.size());
+            std::vector<uint64_t> mv(main.v.size()); for (size_t i = 0; i < mv.size(); i++) mv[i] = main.v[i].v;
+            orc_matrix mm{mv.data(), log2_strict(main.height), (uint32_t)main.width};
+            if (cb(ctx, (uint32_t)inst, &mm, rr.data(), ao.data(), avo.data()) != 0) throw std::runtime_error("aux builder failed");
+            for (size_t i = 0; i < ao.size(); i++) aux.v[i] = Fp(ao[i]);
+            for (size_t i = 0; i < av.size(); i++) av[i] = Ef(Fp(avo[2 * i]), Fp(avo[2 * i + 1]));
+        };
+        auto* res = new orc_prove_result();
+        res->proof = stark_prove(to_params(params), s, tr, to_challenger(challenger), ab, &res->dbg);
+        for (auto& f : res->proof.fields) res->fields.push_back(f.v);
+        for (auto& d : res->proof.commitments) for (int i = 0; i < 4; i++) res->commitments.push_back(d[i].v);
+        out->log_trace_heights = res->proof.log_trace_heights.data(); out->n_heights = res->proof.log_trace_heights.size();
+        out->fields = res->fields.data(); out->n_fields = res->fields.size();
+        out->commitments = res->commitments.data(); out->n_commitments = res->proof.commitments.size();
+        return res;
+    } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void orc_prove_free(void* h) { delete (orc_prove_result*)h; }
+
+// what: same numbering as mdn_info in include/miden_b200.h.
+long long orc_prove_info(void* h, int what, uint64_t* out, size_t cap) {
+    auto* r = (orc_prove_result*)h;
+    std::vector<uint64_t> v;
+    auto push_d = [&](const Digest& d) { for (int i = 0; i < 4; i++) v.push_back(d[i].v); };
+    auto push_e = [&](const Ef& e) { v.push_back(e.a.v); v.push_back(e.b.v); };
+    switch (what) {
+        case 0: push_d(r->dbg.main_root); break;
+        case 1: push_d(r->dbg.aux_root); break;
+        case 2: push_d(r->dbg.quotient_root); break;
+        case 3: push_e(r->dbg.z); break;
+        case 4: for (auto& e : r->dbg.quotient_acc) push_e(e); break;
+        case 5: for (auto& e : r->dbg.open.deep_evals) push_e(e); break;
+        case 6: for (auto& d : r->dbg.open.fri_roots) push_d(d); break;
+        case 7: for (auto q : r->dbg.open.query_indices) v.push_back(q); break;
+        default: return -1;
+    }
+    for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+    return (long long)v.size();
+}
+
+// Verify a proof given as raw streams.  0 = accepted; -1 = rejected (orc_last_error has the reason).
+int orc_verify(const orc_pcs_params* params, const orc_statement* st, const orc_proof* pf, const orc_challenger* challenger) {
+    try {
+        Statement s = to_statement(st);
+        Proof p;
+        p.log_trace_heights.assign(pf->log_trace_heights, pf->log_trace_heights + pf->n_heights);
+        for (size_t i = 0; i < pf->n_fields; i++) {
+            if (pf->fields[i] >= P) throw std::runtime_error("non-canonical field element");
+            p.fields.push_back(Fp::raw(pf->fields[i]));
+        }
+        for (size_t i = 0; i < pf->n_commitments; i++) {
+            Digest d; for (int k = 0; k < 4; k++) d[k] = Fp(pf->commitments[4 * i + k]);
+            p.commitments.push_back(d);
+        }
+        stark_verify(to_params(params), s, p, to_challenger(challenger));
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// TEST INFRASTRUCTURE ONLY (see field.hpp header).
+// Radix-2 NTTs over Goldilocks on row-major matrices, and the coset low-degree extension used by
+// the reference through p3-dft 0.6.2 `Radix2DitParallel` (un-vendored).  Every function here is
+// defined by exact field arithmetic, so any correct algorithm yields identical canonical values;
+// correctness is pinned against a naive O(n^2) DFT in tests/test_oracle_ntt.py (mirroring the
+// reference's NaiveDft differentials, e.g. crates/lifted-stark/src/prover/quotient.rs:254-265).
+#pragma once
+#include "field.hpp"
+#include <cstring>
+
+namespace orc {
+
+// Row-major matrix of base-field values.
+struct Matrix {
+    size_t height = 0, width = 0;
+    std::vector<Fp> v;
+    Matrix() {}
+    Matrix(size_t h, size_t w) : height(h), width(w), v(h * w) {}
+    Fp* row(size_t r) { return v.data() + r * width; }
+    const Fp* row(size_t r) const { return v.data() + r * width; }
+};
+
+inline void bit_reverse_rows(Matrix& m) {
+    unsigned lg = log2_strict(m.height);
+    std::vector<Fp> tmp(m.width);
+    for (size_t i = 0; i < m.height; i++) {
+        size_t j = reverse_bits64(i, lg);
+        if (i < j) {
+            memcpy(tmp.data(), m.row(i), m.width * sizeof(Fp));
+            memcpy(m.row(i), m.row(j), m.width * sizeof(Fp));
+            memcpy(m.row(j), tmp.data(), m.width * sizeof(Fp));
+        }
+    }
+}
+
+// In-place decimation-in-frequency transform on rows: natural-order input, BIT-REVERSED output.
+// out[bitrev(k)] = sum_j in[j] * root^(j k), root a primitive height-th root of unity.
+inline void dif_rows(Matrix& m, Fp root) {
+    size_t n = m.height, w = m.width;
+    if (n <= 1) return;
+    unsigned lg = log2_strict(n);
+    std::vector<Fp> tw(n / 2);
+    tw[0] = Fp::raw(1);
+    for (size_t i = 1; i < n / 2; i++) tw[i] = tw[i - 1] * root;
+    for (unsigned s = 0; s < lg; s++) {
+        size_t half = n >> (s + 1);           // butterfly span
+        size_t nblocks = size_t(1) << s;
+#pragma omp parallel for schedule(static) if (n * w > (1u << 16))
+        for (size_t bj = 0; bj < nblocks * half; bj++) {
+            size_t b = bj / half, j = bj % half;
+            Fp t = tw[j << s];
+            Fp* x = m.row(b * 2 * half + j);
+            Fp* y = m.row(b * 2 * half + j + half);
+            for (size_t c = 0; c < w; c++) {
+                Fp a = x[c], d = y[c];
+                x[c] = a + d;
+                y[c] = (a - d) * t;
+            }
+        }
+    }
+}
+
+// Forward DFT, natural in -> natural out:  out[k] = sum_j in[j] * omega_n^(j k).
+inline void dft_rows(Matrix& m) {
+    dif_rows(m, two_adic_generator(log2_strict(m.height)));
+    bit_reverse_rows(m);
+}
+// Inverse DFT, natural in -> natural out.
+inline void idft_rows(Matrix& m) {
+    unsigned lg = log2_strict(m.height);
+    dif_rows(m, fp_inv(two_adic_generator(lg)));
+    bit_reverse_rows(m);
+    Fp ninv = fp_inv(Fp::raw((u64)m.height));
+#pragma omp parallel for schedule(static) if (m.v.size() > (1u << 16))
+    for (size_t i = 0; i < m.v.size(); i++) m.v[i] = m.v[i] * ninv;
+}
+
+// p3 `coset_lde_batch(mat, added_bits, shift)` as called at
+// crates/lifted-stark/src/prover/commit.rs:173: interpret each column as evaluations over the
+// subgroup H (natural order), interpolate, and evaluate on the coset shift*K, |K| = |H| << added_bits.
+// Output: row-major, rows in BIT-REVERSED order of the coset index (commit.rs:118-119).
+inline Matrix coset_lde_bitrev(const Matrix& evals, unsigned added_bits, Fp shift) {
+    Matrix c = evals;
+    idft_rows(c);
+    size_t n = c.height, w = c.width, big = n << added_bits;
+    Matrix out(big, w);
+    Fp sp = Fp::raw(1);
+    for (size_t k = 0; k < n; k++) {
+        for (size_t j = 0; j < w; j++) out.row(k)[j] = c.row(k)[j] * sp;
+        sp = sp * shift;
+    }
+    dif_rows(out, two_adic_generator(log2_strict(big)));   // leaves rows bit-reversed
+    return out;
+}
+
+// Naive O(n^2) evaluation of a coefficient column at point x (test helper).
+inline Fp horner_eval(const std::vector<Fp>& coeffs, Fp x) {
+    Fp acc;
+    for (size_t i = coeffs.size(); i-- > 0;) acc = acc * x + coeffs[i];
+    return acc;
+}
+
+}  // namespace orc

@@ -1,0 +1,88 @@
+// TEST INFRASTRUCTURE ONLY (see field.hpp header).
+// Poseidon2 permutation over Goldilocks, width 12, and the three constructions the proving path
+// builds from it.  Round structure restated from the reference's own round-by-round helpers:
+//   crates/crypto/src/hash/algebraic_sponge/poseidon2/mod.rs:226-319 (M_E, M_I, add_rc, x^7)
+//   precompiles-prover/src/transcript/poseidon2/trace.rs:380-500 (order of the 1+4+22+4 steps)
+// Pinned by the known-answer test poseidon2/test.rs:7-39 (tests/test_oracle_kat.py).
+#pragma once
+#include "field.hpp"
+#include <array>
+
+namespace orc {
+
+#include "poseidon2_constants.inc"
+
+using State = std::array<Fp, 12>;
+
+inline Fp sbox7(Fp x) { Fp x2 = x * x; Fp x3 = x2 * x; Fp x4 = x2 * x2; return x4 * x3; }
+
+// External linear layer: block-circulant of M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]
+// (mod.rs:234-276): apply M4 to each 4-chunk, then add the column sums to every chunk.
+inline void p2_external(State& s) {
+    for (int c = 0; c < 3; c++) {
+        Fp x0 = s[4 * c], x1 = s[4 * c + 1], x2 = s[4 * c + 2], x3 = s[4 * c + 3];
+        Fp two = Fp::raw(2), three = Fp::raw(3);
+        s[4 * c + 0] = two * x0 + three * x1 + x2 + x3;
+        s[4 * c + 1] = x0 + two * x1 + three * x2 + x3;
+        s[4 * c + 2] = x0 + x1 + two * x2 + three * x3;
+        s[4 * c + 3] = three * x0 + x1 + x2 + two * x3;
+    }
+    Fp col[4];
+    for (int l = 0; l < 4; l++) col[l] = s[l] + s[4 + l] + s[8 + l];
+    for (int i = 0; i < 12; i++) s[i] = s[i] + col[i % 4];
+}
+
+// Internal linear layer: s_i * diag_i + sum(s)  (mod.rs:283-292).
+inline void p2_internal(State& s) {
+    Fp sum;
+    for (int i = 0; i < 12; i++) sum += s[i];
+    for (int i = 0; i < 12; i++) s[i] = s[i] * Fp::raw(P2_INTERNAL_DIAG[i]) + sum;
+}
+
+inline void poseidon2_permute(State& s) {
+    p2_external(s);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox7(s[i] + Fp::raw(P2_RC_EXT_INITIAL[12 * r + i]));
+        p2_external(s);
+    }
+    for (int r = 0; r < 22; r++) {
+        s[0] = sbox7(s[0] + Fp::raw(P2_RC_INTERNAL[r]));
+        p2_internal(s);
+    }
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox7(s[i] + Fp::raw(P2_RC_EXT_TERMINAL[12 * r + i]));
+        p2_external(s);
+    }
+}
+
+using Digest = std::array<Fp, 4>;
+
+// Overwrite-mode sponge absorb, WIDTH 12 / RATE 8 (crates/stateful-hasher/src/field_sponge.rs:41-59):
+// each full chunk of 8 overwrites state[0..8] then permutes; a trailing partial chunk is
+// zero-filled to the rate boundary and permuted; an empty input leaves the state untouched.
+inline void sponge_absorb(State& st, const Fp* in, size_t n) {
+    size_t i = 0;
+    while (i + 8 <= n) {
+        for (int k = 0; k < 8; k++) st[k] = in[i + k];
+        poseidon2_permute(st);
+        i += 8;
+    }
+    if (i < n) {
+        size_t rem = n - i;
+        for (size_t k = 0; k < rem; k++) st[k] = in[i + k];
+        for (size_t k = rem; k < 8; k++) st[k] = Fp();
+        poseidon2_permute(st);
+    }
+}
+inline Digest sponge_squeeze(const State& st) { return Digest{st[0], st[1], st[2], st[3]}; }
+
+// 2-to-1 compression = p3 TruncatedPermutation<_, 2, 4, 12>: perm([l | r | 0000])[0..4]
+// (air/src/config.rs:217; equality with Poseidon2::merge shown by poseidon2/test.rs:208-230).
+inline Digest compress2(const Digest& l, const Digest& r) {
+    State s;
+    for (int i = 0; i < 4; i++) { s[i] = l[i]; s[4 + i] = r[i]; s[8 + i] = Fp(); }
+    poseidon2_permute(s);
+    return Digest{s[0], s[1], s[2], s[3]};
+}
+
+}  // namespace orc

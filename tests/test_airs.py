@@ -1,0 +1,84 @@
+"""Small hand-written AIRs (as op-lists) that exercise everything DummyMidenAir does not:
+next-row access, the three row selectors, public values, EF aux columns, randomness, aux values,
+mixed base/ext constraints, and a quotient degree below the blowup (upsampling)."""
+import ctypes as C
+
+import numpy as np
+
+import pkgload
+
+pkg = pkgload.load_pkg()
+W = pkg.workload
+AP = pkg.air_program
+P = W.P
+
+
+def ef_mul(x, y):
+    return ((x[0] * y[0] + 7 * x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+
+
+def fib_product_program() -> np.ndarray:
+    """main: (a, b, c) with a' = b, b' = a + b, c free; aux: p running product of
+    (ch0 + a + ch1*b).  Constraint degree 3 -> log_quotient_degree = 1."""
+    b = AP.ProgramBuilder()
+    a0, b0 = b.main(0, 0), b.main(0, 1)
+    a1, b1 = b.main(1, 0), b.main(1, 1)
+    tr, first, last = b.is_transition(), b.is_first_row(), b.is_last_row()
+    b.assert_zero(first * (a0 - b.public(0)))
+    b.assert_zero(first * (b0 - b.public(1)))
+    b.assert_zero(tr * (a1 - b0))
+    b.assert_zero(tr * (b1 - (a0 + b0)))
+    p0, p1 = b.aux(0, 0), b.aux(1, 0)
+    factor = b.challenge(0) + a0 + b.challenge(1) * b0
+    b.assert_zero_ext(first * (p0 - b.const(1)))
+    b.assert_zero_ext(tr * (p1 - p0 * factor))
+    b.assert_zero(last * (b0 - b.public(2)))
+    b.assert_zero_ext(last * (p0 * factor - b.aux_value(0)))
+    b.assert_zero_ext((b.main(0, 2) - b.main(0, 2)) * b.ext_const(3, 5))   # ext constant path, trivially zero
+    return b.serialize()
+
+
+def fib_trace(log_h: int, a=1, b=1) -> np.ndarray:
+    n = 1 << log_h
+    t = np.zeros((n, 3), dtype=np.uint64)
+    for r in range(n):
+        t[r] = (a, b, (r * 77 + 5) % P)
+        a, b = b, (a + b) % P
+    return t
+
+
+def fib_product_workload(log_heights, with_dummy=False):
+    """All instances use the fib/product AIR (each with its own height); public values are those of
+    the FIRST instance, so only the first instance's boundary constraints hold unless heights match --
+    therefore every instance gets the same height-dependent publics via separate workloads in tests.
+    Here: instance i starts from (1, 1) and publics = (1, 1, b_last of instance 0), so only use
+    equal heights or a single fib instance plus dummy instances."""
+    progs, traces, widths, aux_w, lqd = [], [], [], [], []
+    fib_logs = log_heights[:1]
+    t0 = fib_trace(fib_logs[0])
+    publics = (1, 1, int(t0[-1, 1]))
+    progs.append(fib_product_program()); traces.append(t0); widths.append(3); aux_w.append(1); lqd.append(1)
+    for i, lh in enumerate(log_heights[1:], start=1):
+        progs.append(AP.dummy_miden_air()); traces.append(W.synthetic_trace(i, lh, 9)); widths.append(9); aux_w.append(1); lqd.append(3)
+    wl = W.Workload(log_heights, widths=widths, aux_widths=aux_w, programs=progs, traces=traces,
+                    public_values=publics, log_quotient_degrees=lqd, num_aux_values=[1] * len(log_heights))
+
+    def build_aux(ctx, instance, main, randomness, aux_out, aux_values):
+        n = 1 << main.contents.log_height
+        if instance != 0:
+            for i in range(2 * n):
+                aux_out[i] = 0
+            aux_values[0] = 0; aux_values[1] = 0
+            return 0
+        w = main.contents.width
+        ch0 = (randomness[0], randomness[1]); ch1 = (randomness[2], randomness[3])
+        p = (1, 0)
+        for r in range(n):
+            aux_out[2 * r], aux_out[2 * r + 1] = p
+            a, b_ = main.contents.values[r * w], main.contents.values[r * w + 1]
+            f = ((ch0[0] + a + ch1[0] * b_) % P, (ch0[1] + ch1[1] * b_) % P)
+            p = ef_mul(p, f)
+        aux_values[0], aux_values[1] = p
+        return 0
+
+    return wl, build_aux
