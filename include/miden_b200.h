@@ -189,6 +189,8 @@ typedef enum {
     MDN_INFO_FRI_ROOTS = 6,        /* 4 u64 per round */
     MDN_INFO_QUERY_INDICES = 7,    /* num_queries u64 */
 } mdn_info;
+/* QUOTIENT_ACC / DEEP_EVALS are only recorded (extra device->host copies) after mdn_set_debug(s, 1). */
+int mdn_set_debug(mdn_session* s, int enable);
 /* Copies at most cap u64 into out; returns the number of u64 available (or <0). */
 long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap);
 

@@ -60,7 +60,7 @@ EXPORTS = [
     "mdn_session_create", "mdn_session_destroy", "mdn_last_error", "mdn_prove", "mdn_prove_begin",
     "mdn_prove_commit_aux", "mdn_prove_finish", "mdn_proof_serialize", "mdn_coset_lde_batch",
     "mdn_lmcs_commit", "mdn_poseidon2_permute", "mdn_get_info", "mdn_get_timings",
-    "mdn_challenger_observe", "mdn_challenger_sample",
+    "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug",
 ]
 
 _lib = None
@@ -94,6 +94,7 @@ def lib():
         L.mdn_poseidon2_permute.argtypes = [C.c_void_p, u64p, C.c_size_t]
         L.mdn_get_info.restype = C.c_longlong
         L.mdn_get_info.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t]
+        L.mdn_set_debug.argtypes = [C.c_void_p, C.c_int]
         L.mdn_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.mdn_challenger_observe.argtypes = [C.POINTER(Challenger), u64p, C.c_size_t]
         L.mdn_challenger_sample.restype = C.c_uint64

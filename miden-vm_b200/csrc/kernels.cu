@@ -1,0 +1,602 @@
+// sm_100a kernels of the Miden STARK proving path.  See kernels.cuh for the data layout and
+// DESIGN.md for the roofline of each kernel.  All arithmetic is 64-bit modular integer work
+// (Goldilocks); the hot loops are (a) NTT butterflies through shared memory, (b) Poseidon2
+// permutations held entirely in registers, (c) streaming reductions over LDE columns.
+#include "kernels.cuh"
+#include "poseidon2.cuh"
+#include <cstdio>
+
+namespace mk {
+
+static unsigned long long g_launches = 0;
+unsigned long long launch_count() { return g_launches; }
+void reset_launch_count() { g_launches = 0; }
+#define COUNT_LAUNCH() (++g_launches)
+
+void upload_constants() {
+    cudaMemcpyToSymbol(p2::D_RC_EXT_INITIAL, p2::P2_RC_EXT_INITIAL, sizeof(u64) * 48);
+    cudaMemcpyToSymbol(p2::D_RC_INTERNAL, p2::P2_RC_INTERNAL, sizeof(u64) * 22);
+    cudaMemcpyToSymbol(p2::D_RC_EXT_TERMINAL, p2::P2_RC_EXT_TERMINAL, sizeof(u64) * 48);
+}
+
+// =============================================================================================
+// transpose: row-major (n_rows x width) -> column-major
+// =============================================================================================
+__global__ void k_transpose(const u64* __restrict__ src, u64* __restrict__ dst, u32 n_rows, u32 width) {
+    __shared__ u64 tile[32][33];
+    u32 r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (u32 i = threadIdx.y; i < 32; i += 8) {
+        u32 r = r0 + i, c = c0 + threadIdx.x;
+        if (r < n_rows && c < width) tile[i][threadIdx.x] = src[(size_t)r * width + c];
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.y; i < 32; i += 8) {
+        u32 c = c0 + i, r = r0 + threadIdx.x;
+        if (r < n_rows && c < width) dst[(size_t)c * n_rows + r] = tile[threadIdx.x][i];
+    }
+}
+void launch_transpose_rm_to_cm(const u64* src, u64* dst, u32 n_rows, u32 width, cudaStream_t st) {
+    dim3 grid((n_rows + 31) / 32, (width + 31) / 32), block(32, 8);
+    k_transpose<<<grid, block, 0, st>>>(src, dst, n_rows, width);
+    COUNT_LAUNCH();
+}
+
+// =============================================================================================
+// NTT.  N = N1 * N2.  Index conventions (see DESIGN.md "NTT"):
+//   inverse (DIF): natural j = j1*N2 + j2  ->  slot p = bitrev(k1)*N2 + bitrev(k2), k = k1 + N1*k2
+//   forward (DIT): slot p = p_hi*N2 + p_lo holds c[j], j = bitrev(p_lo)*N1 + bitrev(p_hi)
+//                  ->  natural k = k1*N2 + k2
+// =============================================================================================
+static constexpr int NTT_THREADS = 256;
+
+__device__ __forceinline__ u64 w_pow(const u64* __restrict__ hi, const u64* __restrict__ lo, u32 lo_bits, u64 e) {
+    return gl::mul(hi[e >> lo_bits], lo[e & ((1ull << lo_bits) - 1)]);
+}
+
+// DIF over `m` stages on x[(idx)*stride_elems + off] for idx < 2^m; `cols` interleaved columns.
+__device__ __forceinline__ void smem_dif(u64* x, const u64* tw, u32 m, u32 cols) {
+    u32 M = 1u << m;
+    for (u32 s = 0; s < m; s++) {
+        u32 half = M >> (s + 1);
+        for (u32 b = threadIdx.x; b < (M >> 1) * cols; b += blockDim.x) {
+            u32 cc = b % cols, bb = b / cols;
+            u32 blk = bb / half, j = bb % half;
+            u32 i0 = (blk * 2 * half + j) * cols + cc, i1 = i0 + half * cols;
+            u64 a = x[i0], c = x[i1];
+            x[i0] = gl::add(a, c);
+            x[i1] = gl::mul(gl::sub(a, c), tw[j << s]);
+        }
+        __syncthreads();
+    }
+}
+// DIT: bit-reversed input -> natural output.
+__device__ __forceinline__ void smem_dit(u64* x, const u64* tw, u32 m, u32 cols) {
+    u32 M = 1u << m;
+    for (u32 s = m; s-- > 0;) {
+        u32 half = M >> (s + 1);
+        for (u32 b = threadIdx.x; b < (M >> 1) * cols; b += blockDim.x) {
+            u32 cc = b % cols, bb = b / cols;
+            u32 blk = bb / half, j = bb % half;
+            u32 i0 = (blk * 2 * half + j) * cols + cc, i1 = i0 + half * cols;
+            u64 a = x[i0], c = gl::mul(x[i1], tw[j << s]);
+            x[i0] = gl::add(a, c);
+            x[i1] = gl::sub(a, c);
+        }
+        __syncthreads();
+    }
+}
+
+// inverse step 1: strided tile [N1][C]
+__global__ void __launch_bounds__(NTT_THREADS) k_intt_strided(u64* cols, size_t col_stride, NttTables T, u32 C) {
+    extern __shared__ u64 sm[];
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+    u64* x = sm; u64* tw = sm + (size_t)N1 * C;
+    u64* col = cols + blockIdx.y * col_stride;
+    u32 j2_0 = blockIdx.x * C;
+    for (u32 i = threadIdx.x; i < N1 / 2; i += blockDim.x) tw[i] = T.twi_n1[i];
+    for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
+        u32 j1 = idx / C, cc = idx % C;
+        x[idx] = col[(size_t)j1 * N2 + j2_0 + cc];
+    }
+    __syncthreads();
+    smem_dif(x, tw, T.n1, C);
+    for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
+        u32 slot = idx / C, cc = idx % C;
+        u32 k1 = gl::bitrev32(slot, T.n1);
+        u32 j2 = j2_0 + cc;
+        u64 f = w_pow(T.wi_hi, T.wi_lo, T.lo_bits, (u64)j2 * k1);
+        col[(size_t)slot * N2 + j2] = gl::mul(x[idx], f);
+    }
+}
+// inverse step 3 (or the whole transform when n1 == 0): contiguous chunk of N2
+__global__ void __launch_bounds__(NTT_THREADS) k_intt_contig(u64* cols, size_t col_stride, NttTables T) {
+    extern __shared__ u64 sm[];
+    u32 N2 = 1u << T.n2;
+    u64* x = sm; u64* tw = sm + N2;
+    u64* chunk = cols + blockIdx.y * col_stride + (size_t)blockIdx.x * N2;
+    for (u32 i = threadIdx.x; i < N2 / 2; i += blockDim.x) tw[i] = T.twi_n2[i];
+    for (u32 i = threadIdx.x; i < N2; i += blockDim.x) x[i] = chunk[i];
+    __syncthreads();
+    smem_dif(x, tw, T.n2, 1);
+    for (u32 i = threadIdx.x; i < N2; i += blockDim.x) chunk[i] = x[i];
+}
+void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, cudaStream_t st) {
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+    if (T.n1 > 0) {
+        u32 C = 8192 / N1; if (C > N2) C = N2; if (C < 1) C = 1;
+        size_t smem = ((size_t)N1 * C + N1 / 2) * sizeof(u64);
+        cudaFuncSetAttribute(k_intt_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_intt_strided<<<dim3(N2 / C, n_cols), NTT_THREADS, smem, st>>>(cols, col_stride, T, C);
+        COUNT_LAUNCH();
+    }
+    size_t smem = ((size_t)N2 + N2 / 2 + 1) * sizeof(u64);
+    k_intt_contig<<<dim3(N1, n_cols), NTT_THREADS, smem, st>>>(cols, col_stride, T);
+    COUNT_LAUNCH();
+}
+
+// forward step 1: contiguous chunk, premultiplied by base^j / N
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_contig(const FwdItem* __restrict__ items, NttTables T, PremulTables Pm) {
+    extern __shared__ u64 sm[];
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+    u64* x = sm; u64* tw = sm + N2;
+    FwdItem it = items[blockIdx.y];
+    u32 p_hi = blockIdx.x;
+    u32 j1 = gl::bitrev32(p_hi, T.n1);
+    const u64* src = it.src + (size_t)p_hi * N2;
+    u64* dst = it.dst + (size_t)p_hi * N2;
+    u64 fb = Pm.tab_b[(size_t)it.base * N1 + j1];
+    const u64* ta = Pm.tab_a + (size_t)it.base * N2;
+    for (u32 i = threadIdx.x; i < N2 / 2; i += blockDim.x) tw[i] = T.tw_n2[i];
+    for (u32 i = threadIdx.x; i < N2; i += blockDim.x) {
+        u32 j2 = gl::bitrev32(i, T.n2);
+        x[i] = gl::mul(src[i], gl::mul(ta[j2], fb));
+    }
+    __syncthreads();
+    smem_dit(x, tw, T.n2, 1);
+    if (T.n1 > 0) {
+        for (u32 k2 = threadIdx.x; k2 < N2; k2 += blockDim.x)
+            dst[k2] = gl::mul(x[k2], w_pow(T.w_hi, T.w_lo, T.lo_bits, (u64)j1 * k2));
+    } else {
+        for (u32 k2 = threadIdx.x; k2 < N2; k2 += blockDim.x) dst[k2] = x[k2];
+    }
+}
+// forward step 3: strided tile [N1][C], DIT along p_hi, in place
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_strided(const FwdItem* __restrict__ items, NttTables T, u32 C) {
+    extern __shared__ u64 sm[];
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+    u64* x = sm; u64* tw = sm + (size_t)N1 * C;
+    u64* col = items[blockIdx.y].dst;
+    u32 k2_0 = blockIdx.x * C;
+    for (u32 i = threadIdx.x; i < N1 / 2; i += blockDim.x) tw[i] = T.tw_n1[i];
+    for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
+        u32 p_hi = idx / C, cc = idx % C;
+        x[idx] = col[(size_t)p_hi * N2 + k2_0 + cc];
+    }
+    __syncthreads();
+    smem_dit(x, tw, T.n1, C);
+    for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
+        u32 k1 = idx / C, cc = idx % C;
+        col[(size_t)k1 * N2 + k2_0 + cc] = x[idx];
+    }
+}
+void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, const PremulTables& Pm, cudaStream_t st) {
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+    size_t smem = ((size_t)N2 + N2 / 2 + 1) * sizeof(u64);
+    k_fwd_contig<<<dim3(N1, n_items), NTT_THREADS, smem, st>>>(d_items, T, Pm);
+    COUNT_LAUNCH();
+    if (T.n1 > 0) {
+        u32 C = 8192 / N1; if (C > N2) C = N2; if (C < 1) C = 1;
+        size_t smem2 = ((size_t)N1 * C + N1 / 2) * sizeof(u64);
+        cudaFuncSetAttribute(k_fwd_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        k_fwd_strided<<<dim3(N2 / C, n_items), NTT_THREADS, smem2, st>>>(d_items, T, C);
+        COUNT_LAUNCH();
+    }
+}
+
+// =============================================================================================
+// Poseidon2 hashing
+// =============================================================================================
+static constexpr int HASH_THREADS = 128;
+
+__global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev,
+                                                            u32 prev_log_n, u64* __restrict__ states_out,
+                                                            u64* __restrict__ dig) {
+    size_t L = (size_t)1 << (log_n + log_b);
+    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= L) return;
+    u32 t = (u32)(pos >> log_n);
+    u32 r = (u32)(pos & (((size_t)1 << log_n) - 1));
+    u64 s[12];
+    if (prev) {
+        size_t Lp = (size_t)1 << (prev_log_n + log_b);
+        size_t pp = ((size_t)t << prev_log_n) + (r & ((1u << prev_log_n) - 1));
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = prev[k * Lp + pp];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = 0;
+    }
+    for (int m = 0; m < a.n_mats; m++) {
+        const u64* base = a.m[m].base + pos;
+        u32 w = a.m[m].width;
+        for (u32 c0 = 0; c0 < w; c0 += 8) {
+#pragma unroll
+            for (u32 k = 0; k < 8; k++) s[k] = (c0 + k < w) ? base[(size_t)(c0 + k) * L] : 0ull;
+            p2::permute(s);
+        }
+    }
+    if (states_out) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) states_out[k * L + pos] = s[k];
+    }
+    if (dig) {
+        size_t i = ((size_t)r << log_b) | t;
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(dig + i * 4);
+        d[0] = make_ulonglong2(s[0], s[1]);
+        d[1] = make_ulonglong2(s[2], s[3]);
+    }
+}
+void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                      u64* states_out, u64* digests_out, cudaStream_t st) {
+    size_t L = (size_t)1 << (log_n + log_blowup);
+    unsigned blocks = (unsigned)((L + HASH_THREADS - 1) / HASH_THREADS);
+    k_leaf_hash<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, digests_out);
+    COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(HASH_THREADS) k_compress(const u64* __restrict__ ch, u64* __restrict__ par, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ulonglong2* c = reinterpret_cast<const ulonglong2*>(ch + i * 8);
+    ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2], b1 = c[3];
+    u64 s[12] = {a0.x, a0.y, a1.x, a1.y, b0.x, b0.y, b1.x, b1.y, 0, 0, 0, 0};
+    p2::permute(s);
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(par + i * 4);
+    d[0] = make_ulonglong2(s[0], s[1]);
+    d[1] = make_ulonglong2(s[2], s[3]);
+}
+void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st) {
+    unsigned blocks = (unsigned)((n_parents + HASH_THREADS - 1) / HASH_THREADS);
+    k_compress<<<blocks, HASH_THREADS, 0, st>>>(children, parents, n_parents);
+    COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict__ ev, size_t q, u64* __restrict__ dig) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
+    ulonglong2 y0 = e[i], y2 = e[i + 2 * q], y1 = e[i + q], y3 = e[i + 3 * q];
+    u64 s[12] = {y0.x, y0.y, y2.x, y2.y, y1.x, y1.y, y3.x, y3.y, 0, 0, 0, 0};
+    p2::permute(s);
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(dig + i * 4);
+    d[0] = make_ulonglong2(s[0], s[1]);
+    d[1] = make_ulonglong2(s[2], s[3]);
+}
+void launch_fri_leaf_hash(const u64* evals, size_t quarter, u64* digests, cudaStream_t st) {
+    unsigned blocks = (unsigned)((quarter + HASH_THREADS - 1) / HASH_THREADS);
+    k_fri_leaf<<<blocks, HASH_THREADS, 0, st>>>(evals, quarter, digests);
+    COUNT_LAUNCH();
+}
+
+__global__ void k_p2_batch(u64* st, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = st[i * 12 + k];
+    p2::permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) st[i * 12 + k] = s[k];
+}
+void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st) {
+    k_p2_batch<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(states, n);
+    COUNT_LAUNCH();
+}
+
+// =============================================================================================
+// Constraint evaluation (op-list interpreter) + quotient accumulation
+// =============================================================================================
+struct ConstraintKArgs {
+    const u64* main_lde; const u64* aux_lde;
+    u32 log_n, log_b;
+    AirDev air;
+    const u64* publics; const u64* challenges; const u64* aux_values;
+    E2 alpha, beta;
+    const u64* acc_in; u32 acc_in_log_n;
+    u64* acc_out;
+    const u64* w_hi; const u64* w_lo; u32 lo_bits;   // w_N powers
+    u64 shift, w_l, w_h_inv;                          // LDE shift, w_L, w_H^-1
+    u64 zh[16], inv_zh[16];                           // per coset t
+};
+
+template <int MAXN>
+__global__ void __launch_bounds__(128) k_constraints(ConstraintKArgs a) {
+    size_t L = (size_t)1 << (a.log_n + a.log_b);
+    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= L) return;
+    u32 N = 1u << a.log_n;
+    u32 t = (u32)(pos >> a.log_n), r = (u32)(pos & (N - 1));
+    size_t pos_next = ((size_t)t << a.log_n) + ((r + 1) & (N - 1));
+    E2 is_first = gl::e2(0, 0), is_last = is_first, is_trans = is_first;
+    if (a.air.uses_selectors) {
+        u64 x = gl::mul(gl::mul(a.shift, gl::pow(a.w_l, t)), w_pow(a.w_hi, a.w_lo, a.lo_bits, r));
+        u64 d_first = gl::sub(x, 1), d_last = gl::sub(x, a.w_h_inv);
+        u64 inv = gl::inv(gl::mul(d_first, d_last));    // x is never in H on the LDE coset
+        is_first.a = gl::mul(a.zh[t], gl::mul(inv, d_last));
+        is_last.a = gl::mul(a.zh[t], gl::mul(inv, d_first));
+        is_trans.a = d_last;
+    }
+    E2 vals[MAXN];
+    const u32* nd = a.air.nodes;
+    for (u32 i = 0; i < a.air.n_nodes; i++, nd += 3) {
+        u32 op = nd[0], x = nd[1], y = nd[2];
+        E2 v;
+        switch (op) {
+            case 0: v = gl::e2(a.main_lde[(size_t)y * L + (x ? pos_next : pos)], 0); break;
+            case 1: { size_t p = x ? pos_next : pos; v = gl::e2(a.aux_lde[(size_t)(2 * y) * L + p], a.aux_lde[(size_t)(2 * y + 1) * L + p]); break; }
+            case 2: v = gl::e2(a.publics[x], 0); break;
+            case 3: v = gl::e2(a.challenges[2 * x], a.challenges[2 * x + 1]); break;
+            case 4: v = gl::e2(a.aux_values[2 * x], a.aux_values[2 * x + 1]); break;
+            case 5: v = is_first; break;
+            case 6: v = is_last; break;
+            case 7: v = is_trans; break;
+            case 8: v = gl::e2(a.air.consts[x], 0); break;
+            case 9: v = gl::e2(a.air.consts[x], a.air.consts[x + 1]); break;
+            case 10: v = gl::e2_add(vals[x], vals[y]); break;
+            case 11: v = gl::e2_sub(vals[x], vals[y]); break;
+            case 12: v = gl::e2_mul(vals[x], vals[y]); break;
+            default: v = gl::e2_neg(vals[x]); break;
+        }
+        vals[i] = v;
+    }
+    E2 acc = gl::e2(0, 0);
+    for (u32 k = 0; k < a.air.n_constraints; k++) acc = gl::e2_add(gl::e2_mul(acc, a.alpha), vals[a.air.constraints[k]]);
+    E2 q = gl::e2_mulf(acc, a.inv_zh[t]);
+    if (a.acc_in) {
+        size_t Lin = (size_t)1 << (a.acc_in_log_n + a.log_b);
+        size_t pa = ((size_t)t << a.acc_in_log_n) + (r & ((1u << a.acc_in_log_n) - 1));
+        E2 prev = gl::e2(a.acc_in[pa], a.acc_in[Lin + pa]);
+        q = gl::e2_add(gl::e2_mul(prev, a.beta), q);
+    }
+    a.acc_out[pos] = q.a;
+    a.acc_out[L + pos] = q.b;
+}
+
+int launch_constraints(const ConstraintArgs& a, cudaStream_t st) {
+    ConstraintKArgs k;
+    k.main_lde = a.main_lde; k.aux_lde = a.aux_lde; k.log_n = a.log_n; k.log_b = a.log_blowup; k.air = a.air;
+    k.publics = a.publics; k.challenges = a.challenges; k.aux_values = a.aux_values;
+    k.alpha = a.alpha; k.beta = a.beta; k.acc_in = a.acc_in; k.acc_in_log_n = a.acc_in_log_n; k.acc_out = a.acc_out;
+    k.w_hi = a.T->w_hi; k.w_lo = a.T->w_lo; k.lo_bits = a.T->lo_bits;
+    u32 log_lde = a.log_n + a.log_blowup;
+    k.shift = gl::lde_shift(log_lde);
+    k.w_l = gl::two_adic_generator(log_lde);
+    k.w_h_inv = gl::inv(gl::two_adic_generator(a.log_n));
+    u32 B = 1u << a.log_blowup;
+    if (B > 16) return -1;
+    // Z_H(x) on coset t: s^N * w_B^t - 1   (domain.rs:742-749)
+    u64 s_pow_n = gl::exp_pow2(k.shift, a.log_n), w_b = gl::two_adic_generator(a.log_blowup), x = 1;
+    for (u32 t = 0; t < B; t++) { k.zh[t] = gl::sub(gl::mul(s_pow_n, x), 1); k.inv_zh[t] = gl::inv(k.zh[t]); x = gl::mul(x, w_b); }
+    size_t L = (size_t)1 << log_lde;
+    unsigned blocks = (unsigned)((L + 127) / 128);
+    if (a.air.n_nodes <= 32) k_constraints<32><<<blocks, 128, 0, st>>>(k);
+    else if (a.air.n_nodes <= 256) k_constraints<256><<<blocks, 128, 0, st>>>(k);
+    else return -1;
+    COUNT_LAUNCH();
+    return 0;
+}
+
+// =============================================================================================
+// OOD evaluation: dot products of coefficient columns with y^(bitrev(p))
+// =============================================================================================
+__global__ void k_pow_bitrev(E2 y, u32 n, u64* __restrict__ wvec) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ((size_t)1 << n)) return;
+    u32 e = gl::bitrev32((u32)p, n);
+    E2 w = gl::e2_pow(y, e);
+    reinterpret_cast<ulonglong2*>(wvec)[p] = make_ulonglong2(w.a, w.b);
+}
+void launch_pow_bitrev(E2 y, u32 n, u64* wvec, cudaStream_t st) {
+    size_t N = (size_t)1 << n;
+    k_pow_bitrev<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(y, n, wvec);
+    COUNT_LAUNCH();
+}
+
+static constexpr int OOD_COLS = 8;
+__global__ void __launch_bounds__(256) k_ood_dot(const u64* __restrict__ coef, size_t col_stride, u32 n_cols, u32 n,
+                                                 const u64* __restrict__ w0, const u64* __restrict__ w1,
+                                                 u64* __restrict__ partial, u32 n_chunks) {
+    __shared__ u64 red[8][OOD_COLS * 4];
+    size_t N = (size_t)1 << n;
+    size_t chunk = N / n_chunks;
+    size_t p0 = (size_t)blockIdx.x * chunk;
+    u32 c0 = blockIdx.y * OOD_COLS;
+    u64 acc[OOD_COLS * 4];
+#pragma unroll
+    for (int i = 0; i < OOD_COLS * 4; i++) acc[i] = 0;
+    const ulonglong2* W0 = reinterpret_cast<const ulonglong2*>(w0);
+    const ulonglong2* W1 = reinterpret_cast<const ulonglong2*>(w1);
+    for (size_t p = p0 + threadIdx.x; p < p0 + chunk; p += blockDim.x) {
+        ulonglong2 a = W0[p], b = W1[p];
+#pragma unroll
+        for (int c = 0; c < OOD_COLS; c++) {
+            if (c0 + c < n_cols) {
+                u64 v = coef[(size_t)(c0 + c) * col_stride + p];
+                acc[4 * c + 0] = gl::add(acc[4 * c + 0], gl::mul(a.x, v));
+                acc[4 * c + 1] = gl::add(acc[4 * c + 1], gl::mul(a.y, v));
+                acc[4 * c + 2] = gl::add(acc[4 * c + 2], gl::mul(b.x, v));
+                acc[4 * c + 3] = gl::add(acc[4 * c + 3], gl::mul(b.y, v));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < OOD_COLS * 4; i++) {
+        u64 v = acc[i];
+        for (int off = 16; off > 0; off >>= 1) v = gl::add(v, (u64)__shfl_down_sync(0xffffffffu, (unsigned long long)v, off));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < OOD_COLS * 4) {
+        u64 v = 0;
+        for (int w = 0; w < 8; w++) v = gl::add(v, red[w][threadIdx.x]);
+        u32 c = c0 + threadIdx.x / 4;
+        if (c < n_cols) partial[((size_t)c * n_chunks + blockIdx.x) * 4 + (threadIdx.x & 3)] = v;
+    }
+}
+void launch_ood_dot(const u64* coef, size_t col_stride, u32 n_cols, u32 n, const u64* w0, const u64* w1, u64* partial,
+                    u32 n_chunks, cudaStream_t st) {
+    dim3 grid(n_chunks, (n_cols + OOD_COLS - 1) / OOD_COLS);
+    k_ood_dot<<<grid, 256, 0, st>>>(coef, col_stride, n_cols, n, w0, w1, partial, n_chunks);
+    COUNT_LAUNCH();
+}
+__global__ void k_ood_reduce(const u64* __restrict__ partial, u32 n_cols, u32 n_chunks, u64* __restrict__ out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cols * 4) return;
+    u32 c = i / 4, k = i & 3;
+    u64 v = 0;
+    for (u32 ch = 0; ch < n_chunks; ch++) v = gl::add(v, partial[((size_t)c * n_chunks + ch) * 4 + k]);
+    out[i] = v;
+}
+void launch_ood_reduce(const u64* partial, u32 n_cols, u32 n_chunks, u64* out, cudaStream_t st) {
+    k_ood_reduce<<<(n_cols * 4 + 127) / 128, 128, 0, st>>>(partial, n_cols, n_chunks, out);
+    COUNT_LAUNCH();
+}
+
+// =============================================================================================
+// DEEP quotient
+// =============================================================================================
+struct DeepKArgs {
+    DeepMat m[12]; int n_mats;
+    u32 log_n, log_b;
+    const u64* apow; u32 total_w;
+    E2 z0, z1, fz0, fz1, beta;
+    u64* out;
+    const u64* w_hi; const u64* w_lo; u32 lo_bits;
+    u64 shift, w_l;
+};
+__global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
+    extern __shared__ u64 sm_apow[];
+    for (u32 i = threadIdx.x; i < 2 * a.total_w; i += blockDim.x) sm_apow[i] = a.apow[i];
+    __syncthreads();
+    size_t L = (size_t)1 << (a.log_n + a.log_b);
+    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= L) return;
+    u32 t = (u32)(pos >> a.log_n), r = (u32)(pos & (((size_t)1 << a.log_n) - 1));
+    E2 fr = gl::e2(0, 0);
+    for (int m = 0; m < a.n_mats; m++) {
+        const DeepMat& M = a.m[m];
+        size_t Lm = (size_t)1 << (M.log_n + a.log_b);
+        size_t pm = ((size_t)t << M.log_n) + (r & ((1u << M.log_n) - 1));
+        const u64* base = M.base + pm;
+        const u64* ap = sm_apow + 2 * M.alpha_off;
+        for (u32 c = 0; c < M.width; c++) {
+            u64 v = base[(size_t)c * Lm];
+            fr.a = gl::add(fr.a, gl::mul(ap[2 * c], v));
+            fr.b = gl::add(fr.b, gl::mul(ap[2 * c + 1], v));
+        }
+    }
+    u64 x = gl::mul(gl::mul(a.shift, gl::pow(a.w_l, t)), w_pow(a.w_hi, a.w_lo, a.lo_bits, r));
+    E2 d0 = gl::e2(gl::sub(a.z0.a, x), a.z0.b), d1 = gl::e2(gl::sub(a.z1.a, x), a.z1.b);
+    E2 inv = gl::e2_inv(gl::e2_mul(d0, d1));
+    E2 i0 = gl::e2_mul(inv, d1), i1 = gl::e2_mul(inv, d0);
+    E2 q = gl::e2_add(gl::e2_mul(i0, gl::e2_sub(a.fz0, fr)),
+                      gl::e2_mul(a.beta, gl::e2_mul(i1, gl::e2_sub(a.fz1, fr))));
+    size_t i = ((size_t)r << a.log_b) | t;
+    reinterpret_cast<ulonglong2*>(a.out)[i] = make_ulonglong2(q.a, q.b);
+}
+void launch_deep(const DeepArgs& a, cudaStream_t st) {
+    DeepKArgs k;
+    for (int i = 0; i < a.n_mats; i++) k.m[i] = a.m[i];
+    k.n_mats = a.n_mats; k.log_n = a.log_n_max; k.log_b = a.log_blowup; k.apow = a.apow; k.total_w = a.total_w;
+    k.z0 = a.z0; k.z1 = a.z1; k.fz0 = a.fz0; k.fz1 = a.fz1; k.beta = a.beta; k.out = a.out;
+    k.w_hi = a.T->w_hi; k.w_lo = a.T->w_lo; k.lo_bits = a.T->lo_bits;
+    u32 log_lde = a.log_n_max + a.log_blowup;
+    k.shift = gl::lde_shift(log_lde); k.w_l = gl::two_adic_generator(log_lde);
+    size_t L = (size_t)1 << log_lde;
+    k_deep<<<(unsigned)((L + 255) / 256), 256, 2 * a.total_w * sizeof(u64), st>>>(k);
+    COUNT_LAUNCH();
+}
+
+// =============================================================================================
+// FRI fold (arity 4), natural domain order
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_fri_fold(const u64* __restrict__ ev, u32 log_dom, E2 beta, u64 w_inv, u64 w4,
+                                                  u64 four_inv, u64* __restrict__ next) {
+    size_t q = (size_t)1 << (log_dom - 2);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
+    ulonglong2 v0 = e[i], v2 = e[i + 2 * q], v1 = e[i + q], v3 = e[i + 3 * q];
+    E2 y0 = gl::e2(v0.x, v0.y), y2 = gl::e2(v2.x, v2.y), y1 = gl::e2(v1.x, v1.y), y3 = gl::e2(v3.x, v3.y);
+    // size-4 inverse DFT of [y0,y1,y2,y3] (pcs/fri/fold/arity4.rs:86-121), then Horner at beta/s
+    E2 s02 = gl::e2_add(y0, y2), d02 = gl::e2_sub(y0, y2), s13 = gl::e2_add(y1, y3);
+    E2 d31 = gl::e2_mulf(gl::e2_sub(y3, y1), w4);
+    E2 c0 = gl::e2_add(s02, s13), c1 = gl::e2_add(d02, d31), c2 = gl::e2_sub(s02, s13), c3 = gl::e2_sub(d02, d31);
+    u64 s_inv = gl::pow(w_inv, (u64)i);
+    E2 x = gl::e2_mulf(beta, s_inv);
+    E2 acc = gl::e2_add(gl::e2_mul(c3, x), c2);
+    acc = gl::e2_add(gl::e2_mul(acc, x), c1);
+    acc = gl::e2_add(gl::e2_mul(acc, x), c0);
+    acc = gl::e2_mulf(acc, four_inv);
+    reinterpret_cast<ulonglong2*>(next)[i] = make_ulonglong2(acc.a, acc.b);
+}
+void launch_fri_fold(const u64* evals, u32 log_dom, E2 beta, u64* next, cudaStream_t st) {
+    size_t q = (size_t)1 << (log_dom - 2);
+    u64 w_inv = gl::inv(gl::two_adic_generator(log_dom));
+    k_fri_fold<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(evals, log_dom, beta, w_inv, gl::two_adic_generator(2),
+                                                            gl::inv(4), next);
+    COUNT_LAUNCH();
+}
+
+// =============================================================================================
+// Proof-of-work grinding
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_grind(const u64* __restrict__ st12, u32 in_len, u64 mask, u64 start, u64 count,
+                                               u64* result) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    u64 w = start + idx;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = st12[k];
+#pragma unroll
+    for (u32 k = 0; k < 8; k++) {
+        if (k == in_len) s[k] = w;
+        else if (k > in_len) s[k] = 0;
+    }
+    s[8] = gl::add(s[8], (u64)(in_len + 1));
+    p2::permute(s);
+    if ((s[7] & mask) == 0) atomicMin(reinterpret_cast<unsigned long long*>(result), (unsigned long long)w);
+}
+void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
+    u64 mask = (1ull << bits) - 1;
+    k_grind<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_state12, in_len, mask, start, count, d_result);
+    COUNT_LAUNCH();
+}
+
+__global__ void k_gather(const u64* const* __restrict__ ptrs, u64* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = *ptrs[i];
+}
+void launch_gather(const u64* const* d_ptrs, u64* d_out, size_t n, cudaStream_t st) {
+    if (!n) return;
+    k_gather<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ptrs, d_out, n);
+    COUNT_LAUNCH();
+}
+
+__global__ void k_export_lde(const u64* __restrict__ lde, u32 log_n, u32 log_b, u32 width, u64* __restrict__ out) {
+    size_t L = (size_t)1 << (log_n + log_b);
+    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= L) return;
+    u32 t = (u32)(pos >> log_n), r = (u32)(pos & (((size_t)1 << log_n) - 1));
+    u32 i = (r << log_b) | t;
+    size_t row = gl::bitrev32(i, log_n + log_b);
+    for (u32 c = 0; c < width; c++) out[row * width + c] = lde[(size_t)c * L + pos];
+}
+void launch_export_lde_bitrev_rm(const u64* lde, u32 log_n, u32 log_blowup, u32 width, u64* out_rm, cudaStream_t st) {
+    size_t L = (size_t)1 << (log_n + log_blowup);
+    k_export_lde<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(lde, log_n, log_blowup, width, out_rm);
+    COUNT_LAUNCH();
+}
+
+}  // namespace mk

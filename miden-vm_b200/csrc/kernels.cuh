@@ -1,0 +1,137 @@
+// Kernel launch wrappers of the proving path (definitions in kernels.cu).
+//
+// Device data layout (DESIGN.md "Data layout in HBM"):
+//   * every committed matrix is COLUMN-major; an LDE column of a height-N trace has L = B*N
+//     entries ordered coset-major: entry t*N + r is the evaluation at x = s * w_L^(r*B + t),
+//     i.e. domain (natural) index i = r*B + t.  Coset t is the H-coset s*w_L^t*H in natural order,
+//     so "next row" is r+1 and the FRI/Merkle domain index is recovered arithmetically; nothing is
+//     ever bit-reverse-permuted in memory (the reference stores bit-reversed rows,
+//     prover/commit.rs:118-119; both index the same Merkle leaves by domain index).
+//   * coefficient columns (after the inverse NTT) are stored bit-reversed: slot p holds c[bitrev(p)].
+//   * extension-field vectors are interleaved (c0, c1) pairs unless noted.
+#pragma once
+#include "gl.cuh"
+#include <cuda_runtime.h>
+
+namespace mk {
+using gl::u64;
+using gl::u32;
+using gl::E2;
+
+// ---------------------------------------------------------------------------------------------
+// NTT plan for one transform size N = 2^n = N1 * N2 (strided pass of size N1, contiguous pass N2)
+// ---------------------------------------------------------------------------------------------
+struct NttTables {
+    u32 n, n1, n2, lo_bits;
+    const u64* tw_n1;       // w_{N1}^i, i < N1/2       (forward)
+    const u64* tw_n2;       // w_{N2}^i, i < N2/2
+    const u64* twi_n1;      // inverse roots
+    const u64* twi_n2;
+    const u64* w_lo;        // w_N^i,               i < 2^lo_bits
+    const u64* w_hi;        // w_N^(i << lo_bits),  i < 2^(n - lo_bits)
+    const u64* wi_lo;       // inverse
+    const u64* wi_hi;
+};
+// Pre-multiplication tables for a coset base g: premul(j) = g^j / N with j = j2*N1 + j1:
+//   tab_a[j2] = (g^N1)^j2 (j2 < N2),  tab_b[j1] = g^j1 / N (j1 < N1).  One pair per base.
+struct PremulTables {
+    const u64* tab_a;   // n_bases x N2
+    const u64* tab_b;   // n_bases x N1
+};
+
+void launch_transpose_rm_to_cm(const u64* src_rm, u64* dst_cm, u32 n_rows, u32 width, cudaStream_t st);
+
+// In-place inverse NTT of `n_cols` columns (stride col_stride): natural evaluations over H ->
+// coefficients (unscaled by 1/N; the forward premul tables carry it), stored bit-reversed.
+void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, cudaStream_t st);
+
+// Forward coset NTTs.  Work item w (0 <= w < n_items): src column items[w].src (bit-reversed
+// coefficients, length N), destination items[w].dst (length N, natural order), base id items[w].base.
+struct FwdItem { const u64* src; u64* dst; u32 base; u32 pad; };
+void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, const PremulTables& Pm, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// Poseidon2 hashing
+// ---------------------------------------------------------------------------------------------
+struct LeafMat { const u64* base; u32 width; u32 pad; };   // LDE matrix of the group's height
+struct LeafArgs { LeafMat m[8]; int n_mats; };
+// Absorb one height-group of matrices into the per-leaf sponge states.
+//   log_n        : log trace height of this group (leaves handled: B << log_n)
+//   prev_states  : SoA [12][B << prev_log_n] states of the previous (shorter) group, or NULL
+//   states_out   : SoA [12][B << log_n] if more groups follow, else NULL
+//   digests_out  : tree leaf layer (4 u64 per leaf, indexed by DOMAIN index r*B + t), or NULL
+void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                      u64* states_out, u64* digests_out, cudaStream_t st);
+// parent[i] = perm(child[2i] | child[2i+1] | 0000)[0..4]
+void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
+// FRI round leaves: leaf i' (< quarter) = sponge([f[i'], f[i'+2q], f[i'+q], f[i'+3q]]) (8 felts, one block)
+void launch_fri_leaf_hash(const u64* evals /* EF interleaved, 4q */, size_t quarter, u64* digests, cudaStream_t st);
+void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// Constraints / quotient
+// ---------------------------------------------------------------------------------------------
+struct AirDev {
+    const u32* nodes;        // 3 words per node
+    const u32* constraints;
+    const u64* consts;
+    u32 n_nodes, n_constraints;
+    u32 uses_selectors;      // any IS_FIRST / IS_LAST / IS_TRANSITION
+};
+struct ConstraintArgs {
+    const u64* main_lde; u32 main_width;
+    const u64* aux_lde; u32 aux_width_base;
+    u32 log_n, log_blowup;
+    AirDev air;
+    const u64* publics;      // device
+    const u64* challenges;   // device, EF pairs
+    const u64* aux_values;   // device, EF pairs
+    E2 alpha, beta;
+    const u64* acc_in; u32 acc_in_log_n;   // previous accumulator planes [2][B << acc_in_log_n], or NULL
+    u64* acc_out;                          // planes [2][B << log_n]
+    const NttTables* T;                    // for w_H powers (selectors)
+};
+int launch_constraints(const ConstraintArgs& a, cudaStream_t st);   // returns 0 or -1 (program too large)
+
+// ---------------------------------------------------------------------------------------------
+// DEEP / FRI / misc
+// ---------------------------------------------------------------------------------------------
+// wvec[p] = y^(bitrev_n(p)) for p < 2^n  (EF interleaved)
+void launch_pow_bitrev(E2 y, u32 n, u64* wvec, cudaStream_t st);
+// partial dot products: out[(col * n_chunks + chunk) * 4 + {0,1}] (point 0), {2,3} (point 1)
+void launch_ood_dot(const u64* coef, size_t col_stride, u32 n_cols, u32 n, const u64* w0, const u64* w1,
+                    u64* partial, u32 n_chunks, cudaStream_t st);
+void launch_ood_reduce(const u64* partial, u32 n_cols, u32 n_chunks, u64* out /* n_cols x 4 */, cudaStream_t st);
+
+struct DeepMat { const u64* base; u32 width; u32 log_n; u32 alpha_off; u32 pad; };
+struct DeepArgs {
+    DeepMat m[12]; int n_mats;
+    u32 log_n_max, log_blowup;
+    const u64* apow;         // device: W EF pairs, alpha^(W-1-i)
+    u32 total_w;
+    E2 z0, z1, fz0, fz1, beta;
+    u64* out;                // EF interleaved, indexed by domain index
+    const NttTables* T;      // tables of the max height (w_H powers)
+};
+void launch_deep(const DeepArgs& a, cudaStream_t st);
+
+// next[i'] = fold4([f[i'], f[i'+2q], f[i'+q], f[i'+3q]], s_inv = w_dom^(-i'), beta)
+void launch_fri_fold(const u64* evals, u32 log_dom, E2 beta, u64* next, cudaStream_t st);
+
+// Proof-of-work: smallest w such that the duplexed state has (st[7] & mask) == 0.
+//   base_state: 12 u64 with the pending inputs already written at rate[0..in_len) and the rest of
+//   the rate holding whatever the sponge holds; the kernel writes w at rate[in_len], zero-fills
+//   rate[in_len+1..8), adds (in_len+1) to st[8] and permutes.
+void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result /* init ~0 */,
+                  cudaStream_t st);
+
+void launch_gather(const u64* const* d_ptrs, u64* d_out, size_t n, cudaStream_t st);
+
+// test/export helper: LDE (coset-major columns) -> row-major with bit-reversed rows
+void launch_export_lde_bitrev_rm(const u64* lde, u32 log_n, u32 log_blowup, u32 width, u64* out_rm, cudaStream_t st);
+
+void upload_constants();   // Poseidon2 round constants -> __constant__
+unsigned long long launch_count();
+void reset_launch_count();
+
+}  // namespace mk

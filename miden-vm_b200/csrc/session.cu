@@ -1,0 +1,1104 @@
+// Host orchestration of the proving path + the C ABI (include/miden_b200.h).
+//
+// This file mirrors `miden_lifted_stark::prover::prove` (reference
+// crates/lifted-stark/src/prover/mod.rs:230-578) phase by phase; each phase names the reference
+// lines it replaces.  Everything data-parallel runs in the kernels of kernels.cu; the host keeps
+// the Fiat-Shamir transcript (sequential) exactly like the reference's host does.
+#include "../../include/miden_b200.h"
+#include "host_transcript.hpp"
+#include "kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using gl::E2;
+using gl::u32;
+using gl::u64;
+using hostfs::Duplex;
+using hostfs::Indices;
+using hostfs::Transcript;
+
+namespace {
+
+struct MdnError : std::runtime_error {
+    int code;
+    MdnError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    throw MdnError(code, buf);
+}
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) fail(MDN_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+std::string g_create_error;
+
+// stream-ordered device buffer
+struct DevBuf {
+    u64* p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept { p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; return *this; }
+    void alloc(size_t count, cudaStream_t s) {
+        release(); st = s; n = count;
+        if (count) CUDA_OK(cudaMallocAsync((void**)&p, count * sizeof(u64), s));
+    }
+    void release() { if (p) { cudaFreeAsync(p, st); p = nullptr; n = 0; } }
+    ~DevBuf() { release(); }
+};
+
+struct NttPlan {
+    mk::NttTables T;
+    DevBuf store;
+};
+struct PremulPlan {
+    mk::PremulTables P;
+    DevBuf store;
+    u32 n_bases;
+};
+
+struct Tree {
+    DevBuf nodes;   // heap layout: layer d at ((1<<d)-1)*4, 4 u64 per digest
+    u32 depth = 0;
+    u64* layer(u32 d) { return nodes.p + (((size_t)1 << d) - 1) * 4; }
+    const u64* layer(u32 d) const { return nodes.p + (((size_t)1 << d) - 1) * 4; }
+};
+
+struct CommittedMat { u64* lde; u64* coef; u32 log_n, width; };
+struct Committed {
+    DevBuf lde_buf, coef_buf;
+    std::vector<CommittedMat> mats;   // proof order (ascending height)
+    Tree tree;
+    u64 root[4];
+};
+
+struct AirHost {
+    mdn_air desc;
+    DevBuf program;   // nodes | constraints | consts(lo,hi pairs as u64)
+    mk::AirDev dev;
+};
+
+}  // namespace
+
+struct mdn_session {
+    mdn_pcs_params params;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    std::map<u32, std::unique_ptr<NttPlan>> ntt_plans;
+    std::map<std::pair<u32, u32>, std::unique_ptr<PremulPlan>> premul_plans;   // (n, kind)
+
+    // ---- per-proof state ----
+    bool in_proof = false;
+    std::vector<AirHost> airs;              // instance order
+    std::vector<u32> log_heights;           // instance order
+    std::vector<u32> order;                 // proof position -> instance
+    std::vector<u64> publics;
+    u32 log_max_n = 0;
+    Transcript tr;
+    std::vector<E2> randomness;
+    Committed main_c, aux_c, quot_c;
+    std::vector<std::vector<u64>> aux_values_p;   // proof order, EF pairs
+    DevBuf d_publics, d_randomness, d_aux_values;
+    std::vector<size_t> aux_values_off;           // proof order offsets (in u64) into d_aux_values
+    // outputs
+    std::vector<uint8_t> out_heights;
+    std::vector<u64> out_fields, out_commitments;
+    // introspection
+    E2 ood_z{0, 0};
+    u64 dbg_roots[3][4] = {};
+    std::vector<u64> dbg_quot_acc, dbg_deep, dbg_fri_roots, dbg_queries;
+    bool keep_debug = false;
+    mdn_timings timings{};
+    cudaEvent_t ev[16];
+
+    NttPlan& ntt(u32 n);
+    PremulPlan& premul_trace(u32 n);
+    PremulPlan& premul_quotient(u32 n);
+    void build_tree(Committed& c, bool aligned_unused);
+    void lde_and_commit(Committed& c, float* t_lde, float* t_hash);
+    void upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm);
+    void prove_begin(const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* ch, u32 flags);
+    void commit_aux(const mdn_matrix* aux, const u64* const* aux_values, bool zero_aux);
+    void finish();
+    u64 grind(u32 bits);
+    void reset_proof();
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// table construction (host, tiny) -------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+void split_n(u32 n, u32& n1, u32& n2) {
+    if (n <= 11) { n1 = 0; n2 = n; }
+    else { n1 = n / 2; n2 = n - n1; }
+}
+
+std::vector<u64> powers(u64 base, size_t count) {
+    std::vector<u64> v(count);
+    u64 x = 1;
+    for (size_t i = 0; i < count; i++) { v[i] = x; x = gl::mul(x, base); }
+    return v;
+}
+
+}  // namespace
+
+NttPlan& mdn_session::ntt(u32 n) {
+    auto it = ntt_plans.find(n);
+    if (it != ntt_plans.end()) return *it->second;
+    if (n > 22) fail(MDN_ERR_UNSUPPORTED, "trace height 2^%u exceeds the supported 2^22", n);
+    auto plan = std::make_unique<NttPlan>();
+    u32 n1, n2; split_n(n, n1, n2);
+    u32 lo_bits = (n + 1) / 2;
+    u64 w = gl::two_adic_generator(n), wi = gl::inv(w);
+    std::vector<u64> host;
+    auto push = [&](const std::vector<u64>& v) { size_t off = host.size(); host.insert(host.end(), v.begin(), v.end()); return off; };
+    u64 w1 = gl::two_adic_generator(n1), w2 = gl::two_adic_generator(n2);
+    size_t o_tw1 = push(powers(w1, n1 ? (size_t)1 << (n1 - 1) : 1));
+    size_t o_tw2 = push(powers(w2, n2 ? (size_t)1 << (n2 - 1) : 1));
+    size_t o_twi1 = push(powers(gl::inv(w1), n1 ? (size_t)1 << (n1 - 1) : 1));
+    size_t o_twi2 = push(powers(gl::inv(w2), n2 ? (size_t)1 << (n2 - 1) : 1));
+    size_t o_lo = push(powers(w, (size_t)1 << lo_bits));
+    size_t o_hi = push(powers(gl::exp_pow2(w, lo_bits), (size_t)1 << (n - lo_bits)));
+    size_t o_ilo = push(powers(wi, (size_t)1 << lo_bits));
+    size_t o_ihi = push(powers(gl::exp_pow2(wi, lo_bits), (size_t)1 << (n - lo_bits)));
+    plan->store.alloc(host.size(), stream);
+    CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    u64* b = plan->store.p;
+    plan->T = mk::NttTables{n, n1, n2, lo_bits, b + o_tw1, b + o_tw2, b + o_twi1, b + o_twi2, b + o_lo, b + o_hi, b + o_ilo, b + o_ihi};
+    auto& ref = *plan;
+    ntt_plans[n] = std::move(plan);
+    return ref;
+}
+
+namespace {
+std::unique_ptr<PremulPlan> make_premul(const std::vector<u64>& bases, u32 n, cudaStream_t stream) {
+    u32 n1, n2; split_n(n, n1, n2);
+    size_t N1 = (size_t)1 << n1, N2 = (size_t)1 << n2;
+    u64 n_inv = gl::inv((u64)1 << n);
+    std::vector<u64> host(bases.size() * (N1 + N2));
+    for (size_t b = 0; b < bases.size(); b++) {
+        u64 g = bases[b], gN1 = gl::exp_pow2(g, n1);
+        u64 x = 1;
+        for (size_t j2 = 0; j2 < N2; j2++) { host[b * N2 + j2] = x; x = gl::mul(x, gN1); }
+        x = n_inv;
+        for (size_t j1 = 0; j1 < N1; j1++) { host[bases.size() * N2 + b * N1 + j1] = x; x = gl::mul(x, g); }
+    }
+    auto plan = std::make_unique<PremulPlan>();
+    plan->store.alloc(host.size(), stream);
+    CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    plan->P.tab_a = plan->store.p;
+    plan->P.tab_b = plan->store.p + bases.size() * N2;
+    plan->n_bases = (u32)bases.size();
+    return plan;
+}
+}  // namespace
+
+// bases g_t = shift * w_L^t: coset t of the LDE of a height-2^n trace (commit.rs:137-141, domain.rs:358-361)
+PremulPlan& mdn_session::premul_trace(u32 n) {
+    auto key = std::make_pair(n, 0u);
+    auto it = premul_plans.find(key);
+    if (it != premul_plans.end()) return *it->second;
+    u32 lb = params.log_blowup, B = 1u << lb;
+    u64 s = gl::lde_shift(n + lb), wl = gl::two_adic_generator(n + lb);
+    std::vector<u64> bases(B);
+    u64 x = s;
+    for (u32 t = 0; t < B; t++) { bases[t] = x; x = gl::mul(x, wl); }
+    auto plan = make_premul(bases, n, stream);
+    auto& ref = *plan;
+    premul_plans[key] = std::move(plan);
+    return ref;
+}
+// bases w_J^(-t) * w_L^(t'), id = t*B + t'  (quotient.rs:186-209: chunk t scaled by w_J^(-kt), then a
+// plain DFT over K evaluates on g*K because the iDFT over H left g^k baked into the coefficients)
+PremulPlan& mdn_session::premul_quotient(u32 n) {
+    auto key = std::make_pair(n, 1u);
+    auto it = premul_plans.find(key);
+    if (it != premul_plans.end()) return *it->second;
+    u32 lb = params.log_blowup, B = 1u << lb;
+    u64 wl = gl::two_adic_generator(n + lb), wji = gl::inv(wl);   // D == B  =>  J == K
+    std::vector<u64> bases(B * B);
+    for (u32 t = 0; t < B; t++)
+        for (u32 t2 = 0; t2 < B; t2++) bases[t * B + t2] = gl::mul(gl::pow(wji, t), gl::pow(wl, t2));
+    auto plan = make_premul(bases, n, stream);
+    auto& ref = *plan;
+    premul_plans[key] = std::move(plan);
+    return ref;
+}
+
+void mdn_session::reset_proof() {
+    in_proof = false;
+    airs.clear(); log_heights.clear(); order.clear(); publics.clear(); randomness.clear();
+    main_c = Committed(); aux_c = Committed(); quot_c = Committed();
+    aux_values_p.clear(); aux_values_off.clear();
+    tr = Transcript();
+}
+
+// row-major (host or device) -> column-major device
+void mdn_session::upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm) {
+    size_t N = (size_t)1 << m.log_height;
+    if (m.width == 0) return;
+    if (on_device) {
+        mk::launch_transpose_rm_to_cm(m.values, dst_cm, (u32)N, m.width, stream);
+        return;
+    }
+    DevBuf staging; staging.alloc(N * m.width, stream);
+    CUDA_OK(cudaMemcpyAsync(staging.p, m.values, N * m.width * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    mk::launch_transpose_rm_to_cm(staging.p, dst_cm, (u32)N, m.width, stream);
+}
+
+// a1 + a2 + a3: coset LDE of every matrix of `c` (coefficients already in c.coef as natural
+// evaluations over H), leaf hashing and tree compression.
+//   reference: commit_traces (prover/commit.rs:142-180) -> coset_lde_batch (:173) +
+//   build_aligned_tree (:178; lmcs/lifted_tree.rs:202-284)
+void mdn_session::lde_and_commit(Committed& c, float* t_lde, float* t_hash) {
+    u32 lb = params.log_blowup, B = 1u << lb;
+    cudaEvent_t e0 = ev[12], e1 = ev[13], e2 = ev[14];
+    CUDA_OK(cudaEventRecord(e0, stream));
+    for (auto& m : c.mats) {
+        if (!m.width) continue;
+        size_t N = (size_t)1 << m.log_n, L = N << lb;
+        NttPlan& plan = ntt(m.log_n);
+        PremulPlan& pm = premul_trace(m.log_n);
+        mk::launch_intt(m.coef, N, m.width, plan.T, stream);
+        // column groups sized so a group's LDE (the fwd passes' working set) stays L2-resident
+        size_t col_bytes = L * sizeof(u64);
+        u32 group = (u32)std::max<size_t>(1, (48u << 20) / col_bytes);
+        std::vector<mk::FwdItem> items;
+        for (u32 cc = 0; cc < m.width; cc++)
+            for (u32 t = 0; t < B; t++)
+                items.push_back(mk::FwdItem{m.coef + (size_t)cc * N, m.lde + (size_t)cc * L + (size_t)t * N, t, 0});
+        DevBuf d_items;
+        d_items.alloc(items.size() * sizeof(mk::FwdItem) / sizeof(u64), stream);
+        CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(mk::FwdItem), cudaMemcpyHostToDevice, stream));
+        for (u32 c0 = 0; c0 < m.width; c0 += group) {
+            u32 cn = std::min(group, m.width - c0);
+            mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)c0 * B, cn * B, plan.T, pm.P, stream);
+        }
+    }
+    CUDA_OK(cudaEventRecord(e1, stream));
+    build_tree(c, true);
+    CUDA_OK(cudaEventRecord(e2, stream));
+    CUDA_OK(cudaEventSynchronize(e2));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+    if (t_lde) *t_lde += a;
+    if (t_hash) *t_hash += b;
+}
+
+// leaf sponge states per height group (ascending), then the compression layers
+void mdn_session::build_tree(Committed& c, bool) {
+    u32 lb = params.log_blowup;
+    u32 log_n_max = 0;
+    for (auto& m : c.mats) log_n_max = std::max(log_n_max, m.log_n);
+    u32 depth = log_n_max + lb;
+    size_t L = (size_t)1 << depth;
+    c.tree.depth = depth;
+    c.tree.nodes.alloc((2 * L - 1) * 4, stream);
+    DevBuf states_a, states_b;
+    const u64* prev = nullptr; u32 prev_log = 0;
+    size_t i = 0;
+    while (i < c.mats.size()) {
+        size_t j = i;
+        mk::LeafArgs args; args.n_mats = 0;
+        while (j < c.mats.size() && c.mats[j].log_n == c.mats[i].log_n) {
+            if (c.mats[j].width) {
+                if (args.n_mats == 8) fail(MDN_ERR_UNSUPPORTED, "more than 8 matrices of one height in a tree");
+                args.m[args.n_mats++] = mk::LeafMat{c.mats[j].lde, c.mats[j].width, 0};
+            }
+            j++;
+        }
+        bool last = (j == c.mats.size());
+        u32 ln = c.mats[i].log_n;
+        DevBuf& out = (prev == states_a.p && prev) ? states_b : states_a;
+        if (!last) out.alloc((size_t)12 << (ln + lb), stream);
+        mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? c.tree.layer(depth) : nullptr, stream);
+        prev = out.p; prev_log = ln;
+        i = j;
+    }
+    for (u32 d = depth; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
+    CUDA_OK(cudaMemcpyAsync(c.root, c.tree.layer(0), 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+// GrindingChallenger::grind on the device: smallest witness (sequential p3 order), then the
+// challenger advances to the post-check state (random_coin.masm:929-966).
+u64 mdn_session::grind(u32 bits) {
+    if (bits == 0) { tr.fields.push_back(0); return 0; }
+    Duplex& ch = tr.ch;
+    if (ch.in_len >= 8) fail(MDN_ERR_INVALID_ARG, "challenger buffer overflow");
+    u64 base[12];
+    for (int i = 0; i < 12; i++) base[i] = ch.st[i];
+    for (u32 i = 0; i < ch.in_len; i++) base[i] = ch.in[i];
+    DevBuf d; d.alloc(13, stream);
+    u64 init[13];
+    memcpy(init, base, sizeof base); init[12] = ~0ull;
+    CUDA_OK(cudaMemcpyAsync(d.p, init, sizeof init, cudaMemcpyHostToDevice, stream));
+    u64 start = 0, found = ~0ull;
+    u64 batch = std::max<u64>(1ull << 14, std::min<u64>(1ull << 22, 4ull << bits));
+    while (found == ~0ull) {
+        if (start >= gl::P) fail(MDN_ERR_INVALID_ARG, "proof-of-work search exhausted");
+        mk::launch_grind(d.p, ch.in_len, bits, start, batch, d.p + 12, stream);
+        CUDA_OK(cudaMemcpyAsync(&found, d.p + 12, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        start += batch;
+    }
+    ch.observe(found);
+    u64 chk = ch.sample_bits(bits);
+    if (chk != 0) fail(MDN_ERR_CUDA, "device proof-of-work witness failed the host check");
+    tr.fields.push_back(found);
+    return found;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prove_begin: validation, statement/shape binding, main commit, randomness  (mod.rs:240-349)
+// ---------------------------------------------------------------------------------------------
+void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* chal, u32 flags) {
+    reset_proof();
+    memset(&timings, 0, sizeof timings);
+    mk::reset_launch_count();
+    if (!st || !traces || !chal) fail(MDN_ERR_INVALID_ARG, "null argument");
+    if (st->n_airs == 0 || st->n_airs > 256) fail(MDN_ERR_INVALID_ARG, "AIR count must be in 1..=256");
+    if (params.log_folding_arity != 2) fail(MDN_ERR_UNSUPPORTED, "only FRI folding arity 4 is implemented");
+    u32 lb = params.log_blowup;
+    if (lb == 0 || lb > 4) fail(MDN_ERR_UNSUPPORTED, "log_blowup must be in 1..=4");
+    bool on_device = (flags & MDN_FLAG_DEVICE_TRACES) != 0;
+    CUDA_OK(cudaEventRecord(ev[0], stream));
+
+    u32 k = st->n_airs;
+    airs.resize(k); log_heights.resize(k);
+    for (u32 i = 0; i < k; i++) {
+        const mdn_air& a = st->airs[i];
+        if (traces[i].width != a.width) fail(MDN_ERR_INVALID_ARG, "trace %u width %u does not match AIR width %u", i, traces[i].width, a.width);
+        if (a.log_quotient_degree > lb)
+            fail(MDN_ERR_DOMAIN, "log_quotient_degree %u > log_blowup %u", a.log_quotient_degree, lb);
+        if (a.log_quotient_degree != lb)
+            fail(MDN_ERR_UNSUPPORTED, "AIR %u: log_quotient_degree %u != log_blowup %u (upsampling path not implemented)", i, a.log_quotient_degree, lb);
+        if (traces[i].log_height + lb > 32) fail(MDN_ERR_DOMAIN, "LDE log order %u exceeds two-adicity 32", traces[i].log_height + lb);
+        if (a.width == 0) fail(MDN_ERR_INVALID_ARG, "AIR %u has zero width", i);
+        log_heights[i] = traces[i].log_height;
+        // parse + upload the constraint program
+        AirHost& h = airs[i];
+        h.desc = a;
+        const u32* w = a.program;
+        if (!w || a.program_words < 5 || w[0] != 0x5249414Du || w[1] != 1) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint program header", i);
+        u32 nn = w[2], nc = w[3], nk = w[4];
+        if ((size_t)a.program_words != 5 + 3 * (size_t)nn + nc + 2 * (size_t)nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint program length", i);
+        bool uses_sel = false;
+        for (u32 j = 0; j < nn; j++) {
+            u32 op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
+            if (op > 13) fail(MDN_ERR_INVALID_ARG, "AIR %u: unknown op %u", i, op);
+            if (op >= 5 && op <= 7) uses_sel = true;
+            if (op >= 10 && op <= 12 && (x >= j || y >= j)) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
+            if (op == 13 && x >= j) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
+            if (op == 0 && (x > 1 || y >= a.width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: main column out of range", i);
+            if (op == 1 && (x > 1 || y >= a.aux_width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: aux column out of range", i);
+            if (op == 2 && x >= st->n_public_values) fail(MDN_ERR_INVALID_ARG, "AIR %u: public value out of range", i);
+            if (op == 3 && x >= a.num_randomness) fail(MDN_ERR_INVALID_ARG, "AIR %u: challenge out of range", i);
+            if (op == 4 && x >= a.num_aux_values) fail(MDN_ERR_INVALID_ARG, "AIR %u: aux value out of range", i);
+            if (op == 8 && x >= nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: constant out of range", i);
+            if (op == 9 && x + 1 >= nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: constant out of range", i);
+        }
+        for (u32 j = 0; j < nc; j++) if (w[5 + 3 * nn + j] >= nn) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint id", i);
+        if (nn > 256) fail(MDN_ERR_UNSUPPORTED, "AIR %u: constraint program with %u nodes exceeds the interpreter's 256-node limit", i, nn);
+        size_t words32 = 3 * (size_t)nn + nc;
+        size_t n64 = (words32 + 1) / 2 + nk;
+        std::vector<u64> hostp(n64 + 1, 0);
+        memcpy(hostp.data(), w + 5, words32 * sizeof(u32));
+        for (u32 j = 0; j < nk; j++) {
+            u64 v = (u64)w[5 + words32 + 2 * j] | ((u64)w[5 + words32 + 2 * j + 1] << 32);
+            if (v >= gl::P) fail(MDN_ERR_INVALID_ARG, "AIR %u: non-canonical constant", i);
+            hostp[(words32 + 1) / 2 + j] = v;
+        }
+        h.program.alloc(hostp.size(), stream);
+        CUDA_OK(cudaMemcpyAsync(h.program.p, hostp.data(), hostp.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        h.dev.nodes = (const u32*)h.program.p;
+        h.dev.constraints = (const u32*)h.program.p + 3 * (size_t)nn;
+        h.dev.consts = h.program.p + (words32 + 1) / 2;
+        h.dev.n_nodes = nn; h.dev.n_constraints = nc; h.dev.uses_selectors = uses_sel;
+    }
+    publics.assign(st->public_values, st->public_values + st->n_public_values);
+    // TraceOrder: stable sort on (log_height, instance)  (order.rs)
+    order.resize(k);
+    for (u32 i = 0; i < k; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return log_heights[a] < log_heights[b]; });
+    log_max_n = log_heights[order.back()];
+    for (u32 i = 0; i < k; i++) ntt(log_heights[i]);   // validates the supported range early
+
+    // challenger: caller's pre-bound state, then Statement::observe + observe_shape (mod.rs:290-291)
+    Duplex& ch = tr.ch;
+    for (int i = 0; i < 12; i++) ch.st[i] = chal->sponge_state[i];
+    if (chal->input_len > 7 || chal->output_len > 8) fail(MDN_ERR_INVALID_ARG, "malformed challenger state");
+    for (u32 i = 0; i < chal->input_len; i++) ch.in[i] = chal->input_buffer[i];
+    ch.in_len = chal->input_len; ch.out_len = chal->output_len;
+    for (u32 i = 0; i < st->n_observe_felts; i++) ch.observe(st->observe_felts[i]);
+    ch.observe(k);
+    for (u32 i = 0; i < k; i++) ch.observe(log_heights[i]);
+
+    // 1. upload + transpose main traces (proof order), LDE, LMCS  (mod.rs:326-341)
+    size_t coef_total = 0, lde_total = 0;
+    for (u32 j = 0; j < k; j++) {
+        u32 inst = order[j];
+        size_t N = (size_t)1 << log_heights[inst];
+        coef_total += N * airs[inst].desc.width; lde_total += (N << lb) * airs[inst].desc.width;
+    }
+    main_c.coef_buf.alloc(coef_total, stream);
+    main_c.lde_buf.alloc(lde_total, stream);
+    size_t co = 0, lo = 0;
+    for (u32 j = 0; j < k; j++) {
+        u32 inst = order[j];
+        size_t N = (size_t)1 << log_heights[inst];
+        u32 w = airs[inst].desc.width;
+        main_c.mats.push_back(CommittedMat{main_c.lde_buf.p + lo, main_c.coef_buf.p + co, log_heights[inst], w});
+        upload_matrix(traces[inst], on_device, main_c.coef_buf.p + co);
+        co += N * w; lo += (N << lb) * w;
+    }
+    CUDA_OK(cudaEventRecord(ev[1], stream));
+    lde_and_commit(main_c, &timings.lde_main, &timings.hash_main);
+    CUDA_OK(cudaEventRecord(ev[2], stream));
+    tr.send_commitment(main_c.root);
+    memcpy(dbg_roots[0], main_c.root, 32);
+    // 2. randomness (mod.rs:344-349)
+    u32 max_rand = 0;
+    for (auto& a : airs) max_rand = std::max(max_rand, a.desc.num_randomness);
+    for (u32 i = 0; i < max_rand; i++) randomness.push_back(tr.ch.sample_ext());
+    in_proof = true;
+}
+
+// aux traces (instance order, EF flattened to base), aux values; commit + observe (mod.rs:397-422)
+void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values, bool zero_aux) {
+    if (!in_proof) fail(MDN_ERR_INVALID_ARG, "commit_aux called outside a proof");
+    u32 k = (u32)airs.size(), lb = params.log_blowup;
+    CUDA_OK(cudaEventRecord(ev[3], stream));
+    size_t coef_total = 0, lde_total = 0;
+    for (u32 j = 0; j < k; j++) {
+        u32 inst = order[j];
+        size_t N = (size_t)1 << log_heights[inst];
+        u32 w = 2 * airs[inst].desc.aux_width;
+        coef_total += N * w; lde_total += (N << lb) * w;
+    }
+    aux_c.coef_buf.alloc(coef_total, stream);
+    aux_c.lde_buf.alloc(lde_total, stream);
+    size_t co = 0, lo = 0;
+    std::vector<u64> flat_values;
+    aux_values_p.assign(k, {}); aux_values_off.assign(k, 0);
+    for (u32 j = 0; j < k; j++) {
+        u32 inst = order[j];
+        size_t N = (size_t)1 << log_heights[inst];
+        u32 w = 2 * airs[inst].desc.aux_width;
+        aux_c.mats.push_back(CommittedMat{aux_c.lde_buf.p + lo, aux_c.coef_buf.p + co, log_heights[inst], w});
+        if (w) {
+            if (zero_aux) CUDA_OK(cudaMemsetAsync(aux_c.coef_buf.p + co, 0, N * w * sizeof(u64), stream));
+            else {
+                if (aux[inst].width != w || aux[inst].log_height != log_heights[inst]) fail(MDN_ERR_INVALID_ARG, "aux trace %u has the wrong shape", inst);
+                upload_matrix(aux[inst], false, aux_c.coef_buf.p + co);
+            }
+        }
+        u32 nav = airs[inst].desc.num_aux_values;
+        aux_values_off[j] = flat_values.size();
+        for (u32 v = 0; v < 2 * nav; v++) {
+            u64 x = zero_aux ? 0 : aux_values[inst][v];
+            if (x >= gl::P) fail(MDN_ERR_INVALID_ARG, "non-canonical aux value");
+            aux_values_p[j].push_back(x); flat_values.push_back(x);
+        }
+        co += N * w; lo += (N << lb) * w;
+    }
+    lde_and_commit(aux_c, nullptr, nullptr);
+    tr.send_commitment(aux_c.root);
+    memcpy(dbg_roots[1], aux_c.root, 32);
+    for (auto& vs : aux_values_p) for (u64 v : vs) tr.send_field(v);
+    // device copies of the small per-proof vectors used by the constraint kernel
+    d_publics.alloc(std::max<size_t>(1, publics.size()), stream);
+    if (!publics.empty()) CUDA_OK(cudaMemcpyAsync(d_publics.p, publics.data(), publics.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    d_randomness.alloc(std::max<size_t>(1, 2 * randomness.size()), stream);
+    if (!randomness.empty()) CUDA_OK(cudaMemcpyAsync(d_randomness.p, randomness.data(), randomness.size() * sizeof(E2), cudaMemcpyHostToDevice, stream));
+    d_aux_values.alloc(std::max<size_t>(1, flat_values.size()), stream);
+    if (!flat_values.empty()) CUDA_OK(cudaMemcpyAsync(d_aux_values.p, flat_values.data(), flat_values.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaEventRecord(ev[4], stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// finish: constraints, quotient commit, OOD point, PCS opening  (mod.rs:424-577)
+// ---------------------------------------------------------------------------------------------
+void mdn_session::finish() {
+    if (!in_proof) fail(MDN_ERR_INVALID_ARG, "finish called outside a proof");
+    u32 k = (u32)airs.size(), lb = params.log_blowup, B = 1u << lb;
+    u32 log_lde = log_max_n + lb;
+    size_t Nmax = (size_t)1 << log_max_n, L = Nmax << lb;
+    // 3. alpha, beta (mod.rs:425-426)
+    E2 alpha = tr.ch.sample_ext(), beta = tr.ch.sample_ext();
+    // 4. constraint evaluation + beta accumulation, ascending height (mod.rs:445-537)
+    DevBuf acc_pp[2];
+    int acc_cur = -1;
+    u32 acc_prev_log = 0;
+    for (u32 j = 0; j < k; j++) {
+        u32 inst = order[j];
+        AirHost& air = airs[inst];
+        u32 ln = log_heights[inst];
+        int nxt = acc_cur < 0 ? 0 : 1 - acc_cur;
+        acc_pp[nxt].alloc((size_t)2 << (ln + lb), stream);
+        mk::ConstraintArgs ca;
+        ca.main_lde = main_c.mats[j].lde; ca.main_width = main_c.mats[j].width;
+        ca.aux_lde = aux_c.mats[j].lde; ca.aux_width_base = aux_c.mats[j].width;
+        ca.log_n = ln; ca.log_blowup = lb; ca.air = air.dev;
+        ca.publics = d_publics.p; ca.challenges = d_randomness.p; ca.aux_values = d_aux_values.p + aux_values_off[j];
+        ca.alpha = alpha; ca.beta = beta;
+        ca.acc_in = acc_cur < 0 ? nullptr : acc_pp[acc_cur].p; ca.acc_in_log_n = acc_prev_log; ca.acc_out = acc_pp[nxt].p;
+        ca.T = &ntt(ln).T;
+        if (mk::launch_constraints(ca, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "constraint program too large for the interpreter");
+        acc_cur = nxt; acc_prev_log = ln;
+    }
+    DevBuf acc = std::move(acc_pp[acc_cur]);
+    acc_pp[1 - acc_cur].release();
+    CUDA_OK(cudaEventRecord(ev[5], stream));
+    if (keep_debug) {
+        // natural order on gJ: index r*B + t  <- planes [coord][t*N + r]
+        std::vector<u64> planes(2 * L);
+        CUDA_OK(cudaMemcpyAsync(planes.data(), acc.p, 2 * L * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        dbg_quot_acc.assign(2 * L, 0);
+        for (size_t t = 0; t < B; t++)
+            for (size_t r = 0; r < Nmax; r++) {
+                dbg_quot_acc[2 * (r * B + t)] = planes[t * Nmax + r];
+                dbg_quot_acc[2 * (r * B + t) + 1] = planes[L + t * Nmax + r];
+            }
+    }
+    // 5. quotient commit (quotient.rs:143-217).  acc planes = 2*B columns of height N (column
+    // coord*B + t); the committed matrix has column 2t + coord.
+    {
+        NttPlan& plan = ntt(log_max_n);
+        PremulPlan& pm = premul_quotient(log_max_n);
+        mk::launch_intt(acc.p, Nmax, 2 * B, plan.T, stream);
+        quot_c.lde_buf.alloc(L * 2 * B, stream);
+        quot_c.coef_buf = std::move(acc);
+        quot_c.mats.push_back(CommittedMat{quot_c.lde_buf.p, quot_c.coef_buf.p, log_max_n, 2 * B});
+        std::vector<mk::FwdItem> items;
+        for (u32 t = 0; t < B; t++)
+            for (u32 coord = 0; coord < 2; coord++)
+                for (u32 t2 = 0; t2 < B; t2++)
+                    items.push_back(mk::FwdItem{quot_c.coef_buf.p + (size_t)(coord * B + t) * Nmax,
+                                                quot_c.lde_buf.p + (size_t)(2 * t + coord) * L + (size_t)t2 * Nmax, t * B + t2, 0});
+        DevBuf d_items; d_items.alloc(items.size() * sizeof(mk::FwdItem) / sizeof(u64), stream);
+        CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(mk::FwdItem), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        // column-pair groups keep the working set near L2 size
+        u32 per = 2 * B;   // items per chunk t
+        for (u32 t = 0; t < B; t++) mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)t * per, per, plan.T, pm.P, stream);
+        build_tree(quot_c, true);
+        tr.send_commitment(quot_c.root);
+        memcpy(dbg_roots[2], quot_c.root, 32);
+    }
+    CUDA_OK(cudaEventRecord(ev[6], stream));
+    // 6. OOD point: resample while z = 0, z in H, or z in gK  (domain.rs:539-552)
+    u64 shift = gl::lde_shift(log_lde), shift_inv = gl::inv(shift);
+    E2 z;
+    for (;;) {
+        z = tr.ch.sample_ext();
+        if (z.a == 0 && z.b == 0) continue;
+        if (gl::e2_eq(gl::e2_exp_pow2(z, log_max_n), gl::e2(1, 0))) continue;
+        if (gl::e2_eq(gl::e2_exp_pow2(gl::e2_mulf(z, shift_inv), log_lde), gl::e2(1, 0))) continue;
+        break;
+    }
+    ood_z = z;
+    u64 omega_h = gl::two_adic_generator(log_max_n);
+    E2 z_next = gl::e2_mulf(z, omega_h);
+
+    // 7. PCS opening (pcs/prover.rs:34-102)
+    // 7a. OOD evaluations of every committed column at z^(r_m), (z*w_H)^(r_m)
+    //     (deep/interpolate.rs:127-203; computed here from the coefficient columns)
+    Committed* groups[3] = {&main_c, &aux_c, &quot_c};
+    struct MatEval { std::vector<u64> v; };   // width x 4
+    std::vector<std::vector<MatEval>> evals(3);
+    {
+        std::map<u32, std::pair<DevBuf, DevBuf>> weights;   // per log height: (w0, w1)
+        auto get_w = [&](u32 ln, E2 y0, E2 y1, std::pair<DevBuf, DevBuf>& slot) {
+            slot.first.alloc((size_t)2 << ln, stream); slot.second.alloc((size_t)2 << ln, stream);
+            mk::launch_pow_bitrev(y0, ln, slot.first.p, stream);
+            mk::launch_pow_bitrev(y1, ln, slot.second.p, stream);
+        };
+        for (int g = 0; g < 3; g++) {
+            evals[g].resize(groups[g]->mats.size());
+            for (size_t m = 0; m < groups[g]->mats.size(); m++) {
+                CommittedMat& cm = groups[g]->mats[m];
+                evals[g][m].v.assign((size_t)cm.width * 4, 0);
+                if (!cm.width) continue;
+                u32 ln = cm.log_n, lr = log_max_n - ln;
+                size_t Nm = (size_t)1 << ln;
+                u32 n_chunks = (u32)std::min<size_t>(Nm, 64);
+                u64 n_inv = gl::inv((u64)Nm);   // launch_intt leaves coefficients scaled by N
+                if (g < 2) {
+                    auto it = weights.find(ln);
+                    if (it == weights.end()) {
+                        it = weights.emplace(ln, std::pair<DevBuf, DevBuf>()).first;
+                        get_w(ln, gl::e2_exp_pow2(z, lr), gl::e2_exp_pow2(z_next, lr), it->second);
+                    }
+                    DevBuf partial; partial.alloc((size_t)cm.width * n_chunks * 4, stream);
+                    DevBuf outv; outv.alloc((size_t)cm.width * 4, stream);
+                    mk::launch_ood_dot(cm.coef, Nm, cm.width, ln, it->second.first.p, it->second.second.p, partial.p, n_chunks, stream);
+                    mk::launch_ood_reduce(partial.p, cm.width, n_chunks, outv.p, stream);
+                    CUDA_OK(cudaMemcpyAsync(evals[g][m].v.data(), outv.p, (size_t)cm.width * 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+                    CUDA_OK(cudaStreamSynchronize(stream));
+                } else {
+                    // quotient chunk t: stored coefficients are a_k * (g*w_J^t)^k (columns t and B+t of
+                    // the coefficient buffer), so q_t(y) is their evaluation at y / (g * w_J^t).
+                    u64 wj_inv = gl::inv(gl::two_adic_generator(log_lde));
+                    for (u32 t = 0; t < B; t++) {
+                        u64 f = gl::mul(shift_inv, gl::pow(wj_inv, t));
+                        std::pair<DevBuf, DevBuf> wv;
+                        get_w(ln, gl::e2_mulf(z, f), gl::e2_mulf(z_next, f), wv);
+                        DevBuf partial; partial.alloc((size_t)2 * n_chunks * 4, stream);
+                        DevBuf outv; outv.alloc(8, stream);
+                        mk::launch_ood_dot(cm.coef + (size_t)t * Nm, (size_t)B * Nm, 2, ln, wv.first.p, wv.second.p, partial.p, n_chunks, stream);
+                        mk::launch_ood_reduce(partial.p, 2, n_chunks, outv.p, stream);
+                        u64 tmp[8];
+                        CUDA_OK(cudaMemcpyAsync(tmp, outv.p, sizeof tmp, cudaMemcpyDeviceToHost, stream));
+                        CUDA_OK(cudaStreamSynchronize(stream));
+                        for (u32 coord = 0; coord < 2; coord++)
+                            for (int q = 0; q < 4; q++) evals[g][m].v[4 * (2 * t + coord) + q] = tmp[4 * coord + q];
+                    }
+                }
+                for (u64& x : evals[g][m].v) x = gl::mul(x, n_inv);
+            }
+        }
+    }
+    // aligned flat evaluation lists per point (deep/prover.rs:150-154)
+    std::vector<E2> flat[2];
+    std::vector<u32> aligned_off;   // per (group, matrix): offset in the aligned index space
+    u32 W = 0;
+    for (int g = 0; g < 3; g++)
+        for (size_t m = 0; m < groups[g]->mats.size(); m++) {
+            u32 w = groups[g]->mats[m].width, aw = (w + 7) / 8 * 8;
+            aligned_off.push_back(W);
+            for (int p = 0; p < 2; p++) {
+                for (u32 c = 0; c < w; c++) {
+                    flat[p].push_back(gl::e2(evals[g][m].v[4 * c + 2 * p], evals[g][m].v[4 * c + 2 * p + 1]));
+                }
+                for (u32 c = w; c < aw; c++) flat[p].push_back(gl::e2(0, 0));
+            }
+            W += aw;
+        }
+    for (int p = 0; p < 2; p++) for (const E2& e : flat[p]) tr.send_ext(e);
+    // 7b. DEEP grind + challenges (deep/prover.rs:157-162)
+    grind(params.deep_pow_bits);
+    E2 dalpha = tr.ch.sample_ext(), dbeta = tr.ch.sample_ext();
+    E2 fz[2];
+    for (int p = 0; p < 2; p++) { E2 a = gl::e2(0, 0); for (const E2& e : flat[p]) a = gl::e2_add(gl::e2_mul(a, dalpha), e); fz[p] = a; }
+    std::vector<E2> apow(W);
+    { E2 a = gl::e2(1, 0); for (u32 i = W; i-- > 0;) { apow[i] = a; a = gl::e2_mul(a, dalpha); } }
+    // 7c. DEEP quotient over the LDE domain (deep/prover.rs:214-312)
+    DevBuf d_apow; d_apow.alloc(2 * (size_t)W, stream);
+    CUDA_OK(cudaMemcpyAsync(d_apow.p, apow.data(), W * sizeof(E2), cudaMemcpyHostToDevice, stream));
+    std::vector<DevBuf> fri_layers;   // EF interleaved, natural domain order
+    fri_layers.emplace_back(); fri_layers[0].alloc(2 * L, stream);
+    {
+        mk::DeepArgs da; da.n_mats = 0;
+        size_t mi = 0;
+        for (int g = 0; g < 3; g++)
+            for (size_t m = 0; m < groups[g]->mats.size(); m++, mi++) {
+                CommittedMat& cm = groups[g]->mats[m];
+                if (!cm.width) continue;
+                if (da.n_mats == 12) fail(MDN_ERR_UNSUPPORTED, "more than 12 committed matrices");
+                da.m[da.n_mats++] = mk::DeepMat{cm.lde, cm.width, cm.log_n, aligned_off[mi], 0};
+            }
+        // NB: the quotient matrix's device columns are already in committed order (2t + coord).
+        da.log_n_max = log_max_n; da.log_blowup = lb; da.apow = d_apow.p; da.total_w = W;
+        da.z0 = z; da.z1 = z_next; da.fz0 = fz[0]; da.fz1 = fz[1]; da.beta = dbeta;
+        da.out = fri_layers[0].p; da.T = &ntt(log_max_n).T;
+        mk::launch_deep(da, stream);
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+    if (keep_debug) {
+        // export in the reference's bit-reversed order
+        std::vector<u64> nat(2 * L);
+        CUDA_OK(cudaMemcpy(nat.data(), fri_layers[0].p, 2 * L * sizeof(u64), cudaMemcpyDeviceToHost));
+        dbg_deep.assign(2 * L, 0);
+        for (size_t i = 0; i < L; i++) {
+            size_t br = gl::bitrev32((u32)i, log_lde);
+            dbg_deep[2 * br] = nat[2 * i]; dbg_deep[2 * br + 1] = nat[2 * i + 1];
+        }
+    }
+    // 7d. FRI commit phase (fri/prover.rs:93-242)
+    u32 rounds; size_t final_deg;
+    {
+        u32 target = params.log_final_degree + lb;
+        u32 steps = log_lde > target ? log_lde - target : 0;
+        rounds = (steps + 1) / 2;
+        u32 lf = log_lde > 2 * rounds ? log_lde - 2 * rounds : 0;
+        final_deg = (size_t)1 << (lf > lb ? lf - lb : 0);
+    }
+    std::vector<Tree> fri_trees(rounds);
+    dbg_fri_roots.clear();
+    u32 log_dom = log_lde;
+    for (u32 r = 0; r < rounds; r++) {
+        if (log_dom < 2) fail(MDN_ERR_INVALID_ARG, "FRI domain too small for arity 4");
+        size_t q = (size_t)1 << (log_dom - 2);
+        Tree& t = fri_trees[r];
+        t.depth = log_dom - 2;
+        t.nodes.alloc((2 * q - 1) * 4, stream);
+        mk::launch_fri_leaf_hash(fri_layers[r].p, q, t.layer(t.depth), stream);
+        for (u32 d = t.depth; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
+        u64 root[4];
+        CUDA_OK(cudaMemcpyAsync(root, t.layer(0), sizeof root, cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        tr.send_commitment(root);
+        dbg_fri_roots.insert(dbg_fri_roots.end(), root, root + 4);
+        grind(params.folding_pow_bits);
+        E2 fb = tr.ch.sample_ext();
+        fri_layers.emplace_back(); fri_layers[r + 1].alloc(2 * q, stream);
+        mk::launch_fri_fold(fri_layers[r].p, log_dom, fb, fri_layers[r + 1].p, stream);
+        log_dom -= 2;
+    }
+    // final polynomial (fri/prover.rs:228-239): values on the size-final_deg subgroup are the
+    // final-layer entries at natural indices i*B; iDFT on the host, sent in descending order.
+    {
+        size_t dom = (size_t)1 << log_dom;
+        std::vector<u64> lay(2 * dom);
+        CUDA_OK(cudaMemcpyAsync(lay.data(), fri_layers[rounds].p, 2 * dom * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        size_t stride = dom / final_deg;
+        u32 lf = 0; while (((size_t)1 << lf) < final_deg) lf++;
+        u64 wi = gl::inv(gl::two_adic_generator(lf)), ninv = gl::inv((u64)final_deg);
+        std::vector<E2> coeff(final_deg);
+        for (size_t kk = 0; kk < final_deg; kk++) {
+            u64 wk = gl::pow(wi, kk), x = 1;
+            E2 a = gl::e2(0, 0);
+            for (size_t i = 0; i < final_deg; i++) {
+                E2 e = gl::e2(lay[2 * i * stride], lay[2 * i * stride + 1]);
+                a = gl::e2_add(a, gl::e2_mulf(e, x));
+                x = gl::mul(x, wk);
+            }
+            coeff[kk] = gl::e2_mulf(a, ninv);
+        }
+        for (size_t i = final_deg; i-- > 0;) tr.send_ext(coeff[i]);
+    }
+    // 7e. query grind + indices (pcs/prover.rs:73-84)
+    grind(params.query_pow_bits);
+    std::vector<size_t> qs;
+    for (u32 i = 0; i < params.num_queries; i++) qs.push_back((size_t)tr.ch.sample_bits(log_lde));
+    dbg_queries.assign(qs.begin(), qs.end());
+    Indices ti = Indices::make(qs, log_lde);
+    // 7f. openings: one pointer list, one gather (pcs/prover.rs:89-101; lifted_tree.rs:155-180)
+    std::vector<const u64*> ptrs;
+    struct Emit { int kind; size_t count; size_t pad; };   // kind 0: `count` fields then `pad` zero fields; 1: commitment (4)
+    std::vector<Emit> plan;
+    for (int g = 0; g < 3; g++) {
+        Committed& c = *groups[g];
+        Indices leafs = ti.folded(c.tree.depth);
+        for (size_t idx : leafs.idx)
+            for (auto& cm : c.mats) {
+                u32 ldm = cm.log_n + lb;
+                size_t im = idx & (((size_t)1 << ldm) - 1);
+                size_t t = im & (B - 1), rr = im >> lb;
+                size_t pos = (t << cm.log_n) + rr, Lm = (size_t)1 << ldm;
+                for (u32 col = 0; col < cm.width; col++) ptrs.push_back(cm.lde + (size_t)col * Lm + pos);
+                plan.push_back(Emit{0, cm.width, (size_t)((cm.width + 7) / 8 * 8 - cm.width)});
+            }
+        for (auto& ds : hostfs::missing_siblings(leafs)) {
+            for (int q = 0; q < 4; q++) ptrs.push_back(c.tree.layer(ds.first) + ds.second * 4 + q);
+            plan.push_back(Emit{1, 4, 0});
+        }
+    }
+    {
+        Indices fi = ti;
+        u32 ld = log_lde;
+        for (u32 r = 0; r < rounds; r++) {
+            fi = fi.folded(fi.depth > 2 ? fi.depth - 2 : 0);
+            size_t q = (size_t)1 << (ld - 2);
+            const u64* lay = fri_layers[r].p;
+            for (size_t idx : fi.idx) {
+                size_t src[4] = {idx, idx + 2 * q, idx + q, idx + 3 * q};
+                for (int e = 0; e < 4; e++) { ptrs.push_back(lay + 2 * src[e]); ptrs.push_back(lay + 2 * src[e] + 1); }
+                plan.push_back(Emit{0, 8, 0});
+            }
+            for (auto& ds : hostfs::missing_siblings(fi)) {
+                for (int qq = 0; qq < 4; qq++) ptrs.push_back(fri_trees[r].layer(ds.first) + ds.second * 4 + qq);
+                plan.push_back(Emit{1, 4, 0});
+            }
+            ld -= 2;
+        }
+    }
+    {
+        DevBuf d_ptrs, d_vals; d_ptrs.alloc(ptrs.size(), stream); d_vals.alloc(ptrs.size(), stream);
+        CUDA_OK(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+        mk::launch_gather((const u64* const*)d_ptrs.p, d_vals.p, ptrs.size(), stream);
+        std::vector<u64> vals(ptrs.size());
+        CUDA_OK(cudaMemcpyAsync(vals.data(), d_vals.p, vals.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        size_t o = 0;
+        for (auto& e : plan) {
+            if (e.kind == 0) { for (size_t i = 0; i < e.count; i++) tr.hint_field(vals[o++]); for (size_t i = 0; i < e.pad; i++) tr.hint_field(0); }
+            else { tr.hint_commitment(&vals[o]); o += 4; }
+        }
+    }
+    CUDA_OK(cudaEventRecord(ev[7], stream));
+    CUDA_OK(cudaEventSynchronize(ev[7]));
+    // 8. StarkProofData (mod.rs:572-577)
+    out_heights.clear();
+    for (u32 h : log_heights) out_heights.push_back((uint8_t)h);
+    out_fields = std::move(tr.fields);
+    out_commitments = std::move(tr.commitments);
+    cudaEventElapsedTime(&timings.h2d_transpose, ev[0], ev[1]);
+    cudaEventElapsedTime(&timings.commit_main, ev[1], ev[2]);
+    cudaEventElapsedTime(&timings.commit_aux, ev[3], ev[4]);
+    cudaEventElapsedTime(&timings.evaluate_constraints, ev[4], ev[5]);
+    cudaEventElapsedTime(&timings.commit_quotient, ev[5], ev[6]);
+    cudaEventElapsedTime(&timings.open, ev[6], ev[7]);
+    cudaEventElapsedTime(&timings.total, ev[0], ev[7]);
+    timings.kernel_launches = mk::launch_count();
+    // release per-proof device memory (returns to the stream-ordered pool)
+    main_c = Committed(); aux_c = Committed(); quot_c = Committed();
+    in_proof = false;
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+#define API_TRY(s) try {
+#define API_CATCH(s) } catch (const MdnError& e) { (s)->error = e.what(); (s)->reset_proof(); return e.code; } \
+    catch (const std::exception& e) { (s)->error = e.what(); (s)->reset_proof(); return MDN_ERR_INVALID_ARG; } return MDN_OK;
+
+extern "C" {
+
+int mdn_session_create(const mdn_pcs_params* params, int cuda_device, mdn_session** out) {
+    if (!params || !out) { g_create_error = "null argument"; return MDN_ERR_INVALID_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (this backend has no CPU fallback)";
+        return MDN_ERR_NO_DEVICE;
+    }
+    if (cuda_device < 0 || cuda_device >= count) { g_create_error = "CUDA device index out of range"; return MDN_ERR_NO_DEVICE; }
+    if (params->num_queries == 0 || params->log_blowup == 0) { g_create_error = "invalid PCS parameters"; return MDN_ERR_INVALID_ARG; }
+    auto* s = new mdn_session();
+    s->params = *params; s->device = cuda_device;
+    try {
+        CUDA_OK(cudaSetDevice(cuda_device));
+        CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        for (auto& evn : s->ev) CUDA_OK(cudaEventCreate(&evn));
+        cudaMemPool_t pool;
+        CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, cuda_device));
+        uint64_t thr = ~0ull;
+        CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        mk::upload_constants();
+        CUDA_OK(cudaDeviceSynchronize());
+    } catch (const std::exception& ex) { g_create_error = ex.what(); delete s; return MDN_ERR_CUDA; }
+    *out = s;
+    return MDN_OK;
+}
+
+void mdn_session_destroy(mdn_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    s->reset_proof();
+    s->ntt_plans.clear(); s->premul_plans.clear();
+    cudaStreamSynchronize(s->stream);
+    for (auto& evn : s->ev) cudaEventDestroy(evn);
+    cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+const char* mdn_last_error(const mdn_session* s) { return s ? s->error.c_str() : g_create_error.c_str(); }
+
+static void fill_proof(mdn_session* s, mdn_proof* out) {
+    out->log_trace_heights = s->out_heights.data(); out->n_heights = s->out_heights.size();
+    out->fields = s->out_fields.data(); out->n_fields = s->out_fields.size();
+    out->commitments = s->out_commitments.data(); out->n_commitments = s->out_commitments.size() / 4;
+}
+
+int mdn_prove_begin(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* challenger,
+                    uint32_t flags, uint64_t main_root[4], uint64_t* randomness_out) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    API_TRY(s)
+    CUDA_OK(cudaSetDevice(s->device));
+    s->prove_begin(st, traces, challenger, flags);
+    if (main_root) memcpy(main_root, s->main_c.root, 32);
+    if (randomness_out) for (size_t i = 0; i < s->randomness.size(); i++) { randomness_out[2 * i] = s->randomness[i].a; randomness_out[2 * i + 1] = s->randomness[i].b; }
+    API_CATCH(s)
+}
+
+int mdn_prove_commit_aux(mdn_session* s, const mdn_matrix* aux, const uint64_t* const* aux_values, uint64_t aux_root[4]) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    API_TRY(s)
+    CUDA_OK(cudaSetDevice(s->device));
+    s->commit_aux(aux, aux_values, aux == nullptr);
+    if (aux_root) memcpy(aux_root, s->aux_c.root, 32);
+    API_CATCH(s)
+}
+
+int mdn_prove_finish(mdn_session* s, mdn_proof* out) {
+    if (!s || !out) return MDN_ERR_INVALID_ARG;
+    API_TRY(s)
+    CUDA_OK(cudaSetDevice(s->device));
+    s->finish();
+    fill_proof(s, out);
+    API_CATCH(s)
+}
+
+int mdn_prove(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* challenger,
+              mdn_aux_builder build_aux, void* aux_ctx, uint32_t flags, mdn_proof* out) {
+    if (!s || !out) return MDN_ERR_INVALID_ARG;
+    API_TRY(s)
+    CUDA_OK(cudaSetDevice(s->device));
+    s->prove_begin(st, traces, challenger, flags);
+    if (!build_aux) {
+        s->commit_aux(nullptr, nullptr, true);
+    } else {
+        if (flags & MDN_FLAG_DEVICE_TRACES) fail(MDN_ERR_UNSUPPORTED, "an aux builder needs host-resident main traces");
+        u32 k = st->n_airs;
+        std::vector<std::vector<u64>> aux_bufs(k), val_bufs(k);
+        std::vector<mdn_matrix> aux_mats(k);
+        std::vector<const u64*> val_ptrs(k);
+        for (u32 i = 0; i < k; i++) {
+            const mdn_air& a = st->airs[i];
+            size_t N = (size_t)1 << traces[i].log_height;
+            aux_bufs[i].assign(N * 2 * a.aux_width, 0);
+            val_bufs[i].assign(2 * (size_t)a.num_aux_values + 1, 0);
+            std::vector<u64> r;
+            for (u32 q = 0; q < a.num_randomness; q++) { r.push_back(s->randomness[q].a); r.push_back(s->randomness[q].b); }
+            r.push_back(0);
+            if (build_aux(aux_ctx, i, &traces[i], r.data(), aux_bufs[i].data(), val_bufs[i].data()) != 0)
+                fail(MDN_ERR_AUX_BUILDER, "aux builder failed for instance %u", i);
+            for (u64 v : aux_bufs[i]) if (v >= gl::P) fail(MDN_ERR_INVALID_ARG, "non-canonical aux trace value");
+            aux_mats[i] = mdn_matrix{aux_bufs[i].data(), traces[i].log_height, 2 * a.aux_width};
+            val_ptrs[i] = val_bufs[i].data();
+        }
+        s->commit_aux(aux_mats.data(), val_ptrs.data(), false);
+    }
+    s->finish();
+    fill_proof(s, out);
+    API_CATCH(s)
+}
+
+size_t mdn_proof_serialize(const mdn_proof* p, uint8_t* out, size_t cap) {
+    size_t need = 8 + p->n_heights + 8 + 8 * p->n_fields + 8 + 32 * p->n_commitments;
+    if (!out || cap < need) return need;
+    auto put64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) *out++ = (uint8_t)(v >> (8 * i)); };
+    put64(p->n_heights); memcpy(out, p->log_trace_heights, p->n_heights); out += p->n_heights;
+    put64(p->n_fields); for (size_t i = 0; i < p->n_fields; i++) put64(p->fields[i]);
+    put64(p->n_commitments); for (size_t i = 0; i < 4 * p->n_commitments; i++) put64(p->commitments[i]);
+    return need;
+}
+
+int mdn_coset_lde_batch(mdn_session* s, const mdn_matrix* mat, uint32_t added_bits, uint64_t shift, uint64_t* out) {
+    if (!s || !mat || !out) return MDN_ERR_INVALID_ARG;
+    API_TRY(s)
+    CUDA_OK(cudaSetDevice(s->device));
+    if (added_bits != s->params.log_blowup) fail(MDN_ERR_UNSUPPORTED, "added_bits must equal the session's log_blowup");
+    if (shift != gl::lde_shift(mat->log_height + added_bits)) fail(MDN_ERR_UNSUPPORTED, "only the canonical LDE shift 7^(2^(32-log_lde)) is supported");
+    for (size_t i = 0; i < ((size_t)mat->width << mat->log_height); i++) if (mat->values[i] >= gl::P) fail(MDN_ERR_INVALID_ARG, "non-canonical input");
+    Committed c;
+    size_t N = (size_t)1 << mat->log_height, L = N << added_bits;
+    c.coef_buf.alloc(N * mat->width, s->stream); c.lde_buf.alloc(L * mat->width, s->stream);
+    c.mats.push_back(CommittedMat{c.lde_buf.p, c.coef_buf.p, mat->log_height, mat->width});
+    s->upload_matrix(*mat, false, c.coef_buf.p);
+    s->lde_and_commit(c, nullptr, nullptr);
+    DevBuf rm; rm.alloc(L * mat->width, s->stream);
+    mk::launch_export_lde_bitrev_rm(c.lde_buf.p, mat->log_height, added_bits, mat->width, rm.p, s->stream);
+    CUDA_OK(cudaMemcpyAsync(out, rm.p, L * mat->width * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    API_CATCH(s)
+}
+
+// The matrices are trace-domain evaluations (height N); the committed tree is the one
+// `commit_traces` builds: LDE by the session blowup then build_aligned_tree.
+int mdn_lmcs_commit(mdn_session* s, const mdn_matrix* mats, uint32_t n_mats, uint64_t root[4]) {
+    if (!s || !mats || !root || !n_mats) return MDN_ERR_INVALID_ARG;
+    API_TRY(s)
+    CUDA_OK(cudaSetDevice(s->device));
+    u32 lb = s->params.log_blowup;
+    Committed c;
+    size_t ct = 0, lt = 0;
+    for (u32 i = 0; i < n_mats; i++) {
+        if (i && mats[i].log_height < mats[i - 1].log_height) fail(MDN_ERR_INVALID_ARG, "matrices must be sorted by ascending height");
+        size_t N = (size_t)1 << mats[i].log_height; ct += N * mats[i].width; lt += (N << lb) * mats[i].width;
+    }
+    c.coef_buf.alloc(ct, s->stream); c.lde_buf.alloc(lt, s->stream);
+    size_t co = 0, lo = 0;
+    for (u32 i = 0; i < n_mats; i++) {
+        size_t N = (size_t)1 << mats[i].log_height;
+        c.mats.push_back(CommittedMat{c.lde_buf.p + lo, c.coef_buf.p + co, mats[i].log_height, mats[i].width});
+        s->upload_matrix(mats[i], false, c.coef_buf.p + co);
+        co += N * mats[i].width; lo += (N << lb) * mats[i].width;
+    }
+    s->lde_and_commit(c, nullptr, nullptr);
+    memcpy(root, c.root, 32);
+    API_CATCH(s)
+}
+
+int mdn_poseidon2_permute(mdn_session* s, uint64_t* states, size_t n) {
+    if (!s || !states) return MDN_ERR_INVALID_ARG;
+    API_TRY(s)
+    CUDA_OK(cudaSetDevice(s->device));
+    DevBuf d; d.alloc(12 * n, s->stream);
+    CUDA_OK(cudaMemcpyAsync(d.p, states, 12 * n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    mk::launch_poseidon2_batch(d.p, n, s->stream);
+    CUDA_OK(cudaMemcpyAsync(states, d.p, 12 * n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    API_CATCH(s)
+}
+
+void mdn_challenger_observe(mdn_challenger* c, const uint64_t* felts, size_t n) {
+    Duplex d;
+    memcpy(d.st, c->sponge_state, sizeof d.st);
+    memcpy(d.in, c->input_buffer, sizeof d.in);
+    d.in_len = c->input_len; d.out_len = c->output_len;
+    for (size_t i = 0; i < n; i++) d.observe(felts[i]);
+    memcpy(c->sponge_state, d.st, sizeof d.st);
+    for (u32 i = 0; i < 8; i++) c->input_buffer[i] = i < d.in_len ? d.in[i] : 0;
+    c->input_len = d.in_len; c->output_len = d.out_len;
+}
+uint64_t mdn_challenger_sample(mdn_challenger* c) {
+    Duplex d;
+    memcpy(d.st, c->sponge_state, sizeof d.st);
+    memcpy(d.in, c->input_buffer, sizeof d.in);
+    d.in_len = c->input_len; d.out_len = c->output_len;
+    u64 v = d.sample();
+    memcpy(c->sponge_state, d.st, sizeof d.st);
+    for (u32 i = 0; i < 8; i++) c->input_buffer[i] = i < d.in_len ? d.in[i] : 0;
+    c->input_len = d.in_len; c->output_len = d.out_len;
+    return v;
+}
+
+long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap) {
+    if (!s) return -1;
+    std::vector<u64> v;
+    switch (what) {
+        case MDN_INFO_MAIN_ROOT: v.assign(s->dbg_roots[0], s->dbg_roots[0] + 4); break;
+        case MDN_INFO_AUX_ROOT: v.assign(s->dbg_roots[1], s->dbg_roots[1] + 4); break;
+        case MDN_INFO_QUOTIENT_ROOT: v.assign(s->dbg_roots[2], s->dbg_roots[2] + 4); break;
+        case MDN_INFO_OOD_POINT: v = {s->ood_z.a, s->ood_z.b}; break;
+        case MDN_INFO_QUOTIENT_ACC: v = s->dbg_quot_acc; break;
+        case MDN_INFO_DEEP_EVALS: v = s->dbg_deep; break;
+        case MDN_INFO_FRI_ROOTS: v = s->dbg_fri_roots; break;
+        case MDN_INFO_QUERY_INDICES: v = s->dbg_queries; break;
+        default: return -1;
+    }
+    if (out) for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+    return (long long)v.size();
+}
+
+int mdn_set_debug(mdn_session* s, int enable) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    s->keep_debug = enable != 0;
+    return MDN_OK;
+}
+
+int mdn_get_timings(mdn_session* s, mdn_timings* out) {
+    if (!s || !out) return MDN_ERR_INVALID_ARG;
+    *out = s->timings;
+    return MDN_OK;
+}
+
+}  // extern "C"

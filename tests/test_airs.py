@@ -47,21 +47,21 @@ def fib_trace(log_h: int, a=1, b=1) -> np.ndarray:
     return t
 
 
-def fib_product_workload(log_heights, with_dummy=False):
+def fib_product_workload(log_heights, with_dummy=False, lqd=1):
     """All instances use the fib/product AIR (each with its own height); public values are those of
     the FIRST instance, so only the first instance's boundary constraints hold unless heights match --
     therefore every instance gets the same height-dependent publics via separate workloads in tests.
     Here: instance i starts from (1, 1) and publics = (1, 1, b_last of instance 0), so only use
     equal heights or a single fib instance plus dummy instances."""
-    progs, traces, widths, aux_w, lqd = [], [], [], [], []
+    progs, traces, widths, aux_w, lqds = [], [], [], [], []
     fib_logs = log_heights[:1]
     t0 = fib_trace(fib_logs[0])
     publics = (1, 1, int(t0[-1, 1]))
-    progs.append(fib_product_program()); traces.append(t0); widths.append(3); aux_w.append(1); lqd.append(1)
+    progs.append(fib_product_program()); traces.append(t0); widths.append(3); aux_w.append(1); lqds.append(lqd)
     for i, lh in enumerate(log_heights[1:], start=1):
-        progs.append(AP.dummy_miden_air()); traces.append(W.synthetic_trace(i, lh, 9)); widths.append(9); aux_w.append(1); lqd.append(3)
+        progs.append(AP.dummy_miden_air()); traces.append(W.synthetic_trace(i, lh, 9)); widths.append(9); aux_w.append(1); lqds.append(3)
     wl = W.Workload(log_heights, widths=widths, aux_widths=aux_w, programs=progs, traces=traces,
-                    public_values=publics, log_quotient_degrees=lqd, num_aux_values=[1] * len(log_heights))
+                    public_values=publics, log_quotient_degrees=lqds, num_aux_values=[1] * len(log_heights))
 
     def build_aux(ctx, instance, main, randomness, aux_out, aux_values):
         n = 1 << main.contents.log_height
