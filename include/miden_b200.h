@@ -199,7 +199,15 @@ long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap)
 typedef struct {
     float h2d_transpose, commit_main, commit_aux, evaluate_constraints, commit_quotient, open, total;
     float lde_main, hash_main;          /* inside commit_main */
+    /* per kernel class, summed over the last prove's launches (CUDA events on the session stream):
+     * 0 transpose, 1 NTT/LDE, 2 leaf sponge, 3 Merkle compress, 4 constraints, 5 OOD dot products,
+     * 6 DEEP quotient, 7 FRI (leaf+compress+fold), 8 PoW grind, 9 opening gather */
+    float kernel_ms[10];
+    unsigned kernel_regions[10];        /* timed regions per class */
     unsigned long long kernel_launches; /* kernels launched by the last prove */
+    unsigned long long permutations;    /* Poseidon2 permutations executed for commitments */
+    double leaf_hash_bytes;             /* algorithmic bytes of the leaf-sponge launches (LDE read + state/digest write) */
+    double ntt_bytes;                   /* algorithmic bytes of the LDE: (N + L) * width * 8 per matrix */
 } mdn_timings;
 int mdn_get_timings(mdn_session* s, mdn_timings* out);
 

@@ -49,7 +49,8 @@ class Proof(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_transpose", "commit_main", "commit_aux", "evaluate_constraints",
                                          "commit_quotient", "open", "total", "lde_main", "hash_main")] + \
-               [("kernel_launches", C.c_ulonglong)]
+               [("kernel_ms", C.c_float * 10), ("kernel_regions", C.c_uint * 10), ("kernel_launches", C.c_ulonglong),
+                ("permutations", C.c_ulonglong), ("leaf_hash_bytes", C.c_double), ("ntt_bytes", C.c_double)]
 
 
 AUX_BUILDER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Matrix), u64p, u64p, u64p)

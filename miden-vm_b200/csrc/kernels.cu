@@ -4,6 +4,7 @@
 // permutations held entirely in registers, (c) streaming reductions over LDE columns.
 #include "kernels.cuh"
 #include "poseidon2.cuh"
+#include "poseidon2_fast.cuh"
 #include <cstdio>
 
 namespace mk {
@@ -53,15 +54,19 @@ __device__ __forceinline__ u64 w_pow(const u64* __restrict__ hi, const u64* __re
     return gl::mul(hi[e >> lo_bits], lo[e & ((1ull << lo_bits) - 1)]);
 }
 
-// DIF over `m` stages on x[(idx)*stride_elems + off] for idx < 2^m; `cols` interleaved columns.
-__device__ __forceinline__ void smem_dif(u64* x, const u64* tw, u32 m, u32 cols) {
-    u32 M = 1u << m;
+// DIF over `m` stages on a tile x[idx * cols + cc] (idx < 2^m, cols = 2^log_cols interleaved columns).
+// All index arithmetic is shifts/masks (every size is a power of two).
+__device__ __forceinline__ void smem_dif(u64* x, const u64* tw, u32 m, u32 log_cols) {
+    if (m == 0) return;
+    u32 total = 1u << (m - 1 + log_cols);        // butterflies per stage
+    u32 cmask = (1u << log_cols) - 1;
     for (u32 s = 0; s < m; s++) {
-        u32 half = M >> (s + 1);
-        for (u32 b = threadIdx.x; b < (M >> 1) * cols; b += blockDim.x) {
-            u32 cc = b % cols, bb = b / cols;
-            u32 blk = bb / half, j = bb % half;
-            u32 i0 = (blk * 2 * half + j) * cols + cc, i1 = i0 + half * cols;
+        u32 lh = m - s - 1;                        // log2(half)
+        u32 hmask = (1u << lh) - 1;
+        for (u32 b = threadIdx.x; b < total; b += blockDim.x) {
+            u32 cc = b & cmask, bb = b >> log_cols;
+            u32 j = bb & hmask, blk = bb >> lh;
+            u32 i0 = (((blk << (lh + 1)) + j) << log_cols) + cc, i1 = i0 + (1u << (lh + log_cols));
             u64 a = x[i0], c = x[i1];
             x[i0] = gl::add(a, c);
             x[i1] = gl::mul(gl::sub(a, c), tw[j << s]);
@@ -70,14 +75,17 @@ __device__ __forceinline__ void smem_dif(u64* x, const u64* tw, u32 m, u32 cols)
     }
 }
 // DIT: bit-reversed input -> natural output.
-__device__ __forceinline__ void smem_dit(u64* x, const u64* tw, u32 m, u32 cols) {
-    u32 M = 1u << m;
+__device__ __forceinline__ void smem_dit(u64* x, const u64* tw, u32 m, u32 log_cols) {
+    if (m == 0) return;
+    u32 total = 1u << (m - 1 + log_cols);
+    u32 cmask = (1u << log_cols) - 1;
     for (u32 s = m; s-- > 0;) {
-        u32 half = M >> (s + 1);
-        for (u32 b = threadIdx.x; b < (M >> 1) * cols; b += blockDim.x) {
-            u32 cc = b % cols, bb = b / cols;
-            u32 blk = bb / half, j = bb % half;
-            u32 i0 = (blk * 2 * half + j) * cols + cc, i1 = i0 + half * cols;
+        u32 lh = m - s - 1;
+        u32 hmask = (1u << lh) - 1;
+        for (u32 b = threadIdx.x; b < total; b += blockDim.x) {
+            u32 cc = b & cmask, bb = b >> log_cols;
+            u32 j = bb & hmask, blk = bb >> lh;
+            u32 i0 = (((blk << (lh + 1)) + j) << log_cols) + cc, i1 = i0 + (1u << (lh + log_cols));
             u64 a = x[i0], c = gl::mul(x[i1], tw[j << s]);
             x[i0] = gl::add(a, c);
             x[i1] = gl::sub(a, c);
@@ -87,7 +95,8 @@ __device__ __forceinline__ void smem_dit(u64* x, const u64* tw, u32 m, u32 cols)
 }
 
 // inverse step 1: strided tile [N1][C]
-__global__ void __launch_bounds__(NTT_THREADS) k_intt_strided(u64* cols, size_t col_stride, NttTables T, u32 C) {
+__global__ void __launch_bounds__(NTT_THREADS) k_intt_strided(u64* cols, size_t col_stride, NttTables T, u32 log_c) {
+    u32 C = 1u << log_c;
     extern __shared__ u64 sm[];
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
     u64* x = sm; u64* tw = sm + (size_t)N1 * C;
@@ -95,13 +104,13 @@ __global__ void __launch_bounds__(NTT_THREADS) k_intt_strided(u64* cols, size_t 
     u32 j2_0 = blockIdx.x * C;
     for (u32 i = threadIdx.x; i < N1 / 2; i += blockDim.x) tw[i] = T.twi_n1[i];
     for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
-        u32 j1 = idx / C, cc = idx % C;
+        u32 j1 = idx >> log_c, cc = idx & (C - 1);
         x[idx] = col[(size_t)j1 * N2 + j2_0 + cc];
     }
     __syncthreads();
-    smem_dif(x, tw, T.n1, C);
+    smem_dif(x, tw, T.n1, log_c);
     for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
-        u32 slot = idx / C, cc = idx % C;
+        u32 slot = idx >> log_c, cc = idx & (C - 1);
         u32 k1 = gl::bitrev32(slot, T.n1);
         u32 j2 = j2_0 + cc;
         u64 f = w_pow(T.wi_hi, T.wi_lo, T.lo_bits, (u64)j2 * k1);
@@ -117,16 +126,17 @@ __global__ void __launch_bounds__(NTT_THREADS) k_intt_contig(u64* cols, size_t c
     for (u32 i = threadIdx.x; i < N2 / 2; i += blockDim.x) tw[i] = T.twi_n2[i];
     for (u32 i = threadIdx.x; i < N2; i += blockDim.x) x[i] = chunk[i];
     __syncthreads();
-    smem_dif(x, tw, T.n2, 1);
+    smem_dif(x, tw, T.n2, 0);
     for (u32 i = threadIdx.x; i < N2; i += blockDim.x) chunk[i] = x[i];
 }
 void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, cudaStream_t st) {
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
     if (T.n1 > 0) {
-        u32 C = 8192 / N1; if (C > N2) C = N2; if (C < 1) C = 1;
+        u32 log_c = 13 - T.n1; if (log_c > T.n2) log_c = T.n2;
+        u32 C = 1u << log_c;
         size_t smem = ((size_t)N1 * C + N1 / 2) * sizeof(u64);
         cudaFuncSetAttribute(k_intt_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_intt_strided<<<dim3(N2 / C, n_cols), NTT_THREADS, smem, st>>>(cols, col_stride, T, C);
+        k_intt_strided<<<dim3(N2 / C, n_cols), NTT_THREADS, smem, st>>>(cols, col_stride, T, log_c);
         COUNT_LAUNCH();
     }
     size_t smem = ((size_t)N2 + N2 / 2 + 1) * sizeof(u64);
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_contig(const FwdItem* __res
         x[i] = gl::mul(src[i], gl::mul(ta[j2], fb));
     }
     __syncthreads();
-    smem_dit(x, tw, T.n2, 1);
+    smem_dit(x, tw, T.n2, 0);
     if (T.n1 > 0) {
         for (u32 k2 = threadIdx.x; k2 < N2; k2 += blockDim.x)
             dst[k2] = gl::mul(x[k2], w_pow(T.w_hi, T.w_lo, T.lo_bits, (u64)j1 * k2));
@@ -161,7 +171,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_contig(const FwdItem* __res
     }
 }
 // forward step 3: strided tile [N1][C], DIT along p_hi, in place
-__global__ void __launch_bounds__(NTT_THREADS) k_fwd_strided(const FwdItem* __restrict__ items, NttTables T, u32 C) {
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_strided(const FwdItem* __restrict__ items, NttTables T, u32 log_c) {
+    u32 C = 1u << log_c;
     extern __shared__ u64 sm[];
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
     u64* x = sm; u64* tw = sm + (size_t)N1 * C;
@@ -169,13 +180,13 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_strided(const FwdItem* __re
     u32 k2_0 = blockIdx.x * C;
     for (u32 i = threadIdx.x; i < N1 / 2; i += blockDim.x) tw[i] = T.tw_n1[i];
     for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
-        u32 p_hi = idx / C, cc = idx % C;
+        u32 p_hi = idx >> log_c, cc = idx & (C - 1);
         x[idx] = col[(size_t)p_hi * N2 + k2_0 + cc];
     }
     __syncthreads();
-    smem_dit(x, tw, T.n1, C);
+    smem_dit(x, tw, T.n1, log_c);
     for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
-        u32 k1 = idx / C, cc = idx % C;
+        u32 k1 = idx >> log_c, cc = idx & (C - 1);
         col[(size_t)k1 * N2 + k2_0 + cc] = x[idx];
     }
 }
@@ -185,10 +196,11 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
     k_fwd_contig<<<dim3(N1, n_items), NTT_THREADS, smem, st>>>(d_items, T, Pm);
     COUNT_LAUNCH();
     if (T.n1 > 0) {
-        u32 C = 8192 / N1; if (C > N2) C = N2; if (C < 1) C = 1;
+        u32 log_c = 13 - T.n1; if (log_c > T.n2) log_c = T.n2;
+        u32 C = 1u << log_c;
         size_t smem2 = ((size_t)N1 * C + N1 / 2) * sizeof(u64);
         cudaFuncSetAttribute(k_fwd_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        k_fwd_strided<<<dim3(N2 / C, n_items), NTT_THREADS, smem2, st>>>(d_items, T, C);
+        k_fwd_strided<<<dim3(N2 / C, n_items), NTT_THREADS, smem2, st>>>(d_items, T, log_c);
         COUNT_LAUNCH();
     }
 }
@@ -222,18 +234,18 @@ __global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash(LeafArgs a, u32 log_
         for (u32 c0 = 0; c0 < w; c0 += 8) {
 #pragma unroll
             for (u32 k = 0; k < 8; k++) s[k] = (c0 + k < w) ? base[(size_t)(c0 + k) * L] : 0ull;
-            p2::permute(s);
+            p2f::permute(s);
         }
     }
     if (states_out) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) states_out[k * L + pos] = s[k];
+        for (int k = 0; k < 12; k++) states_out[k * L + pos] = glf::canon(s[k]);
     }
     if (dig) {
         size_t i = ((size_t)r << log_b) | t;
         ulonglong2* d = reinterpret_cast<ulonglong2*>(dig + i * 4);
-        d[0] = make_ulonglong2(s[0], s[1]);
-        d[1] = make_ulonglong2(s[2], s[3]);
+        d[0] = make_ulonglong2(glf::canon(s[0]), glf::canon(s[1]));
+        d[1] = make_ulonglong2(glf::canon(s[2]), glf::canon(s[3]));
     }
 }
 void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
@@ -250,10 +262,10 @@ __global__ void __launch_bounds__(HASH_THREADS) k_compress(const u64* __restrict
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(ch + i * 8);
     ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2], b1 = c[3];
     u64 s[12] = {a0.x, a0.y, a1.x, a1.y, b0.x, b0.y, b1.x, b1.y, 0, 0, 0, 0};
-    p2::permute(s);
+    p2f::permute(s);
     ulonglong2* d = reinterpret_cast<ulonglong2*>(par + i * 4);
-    d[0] = make_ulonglong2(s[0], s[1]);
-    d[1] = make_ulonglong2(s[2], s[3]);
+    d[0] = make_ulonglong2(glf::canon(s[0]), glf::canon(s[1]));
+    d[1] = make_ulonglong2(glf::canon(s[2]), glf::canon(s[3]));
 }
 void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st) {
     unsigned blocks = (unsigned)((n_parents + HASH_THREADS - 1) / HASH_THREADS);
@@ -267,10 +279,10 @@ __global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict
     const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
     ulonglong2 y0 = e[i], y2 = e[i + 2 * q], y1 = e[i + q], y3 = e[i + 3 * q];
     u64 s[12] = {y0.x, y0.y, y2.x, y2.y, y1.x, y1.y, y3.x, y3.y, 0, 0, 0, 0};
-    p2::permute(s);
+    p2f::permute(s);
     ulonglong2* d = reinterpret_cast<ulonglong2*>(dig + i * 4);
-    d[0] = make_ulonglong2(s[0], s[1]);
-    d[1] = make_ulonglong2(s[2], s[3]);
+    d[0] = make_ulonglong2(glf::canon(s[0]), glf::canon(s[1]));
+    d[1] = make_ulonglong2(glf::canon(s[2]), glf::canon(s[3]));
 }
 void launch_fri_leaf_hash(const u64* evals, size_t quarter, u64* digests, cudaStream_t st) {
     unsigned blocks = (unsigned)((quarter + HASH_THREADS - 1) / HASH_THREADS);
@@ -284,9 +296,9 @@ __global__ void k_p2_batch(u64* st, size_t n) {
     u64 s[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) s[k] = st[i * 12 + k];
-    p2::permute(s);
+    p2f::permute(s);
 #pragma unroll
-    for (int k = 0; k < 12; k++) st[i * 12 + k] = s[k];
+    for (int k = 0; k < 12; k++) st[i * 12 + k] = glf::canon(s[k]);
 }
 void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st) {
     k_p2_batch<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(states, n);
@@ -565,8 +577,8 @@ __global__ void __launch_bounds__(128) k_grind(const u64* __restrict__ st12, u32
         else if (k > in_len) s[k] = 0;
     }
     s[8] = gl::add(s[8], (u64)(in_len + 1));
-    p2::permute(s);
-    if ((s[7] & mask) == 0) atomicMin(reinterpret_cast<unsigned long long*>(result), (unsigned long long)w);
+    p2f::permute(s);
+    if ((glf::canon(s[7]) & mask) == 0) atomicMin(reinterpret_cast<unsigned long long*>(result), (unsigned long long)w);
 }
 void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
     u64 mask = (1ull << bits) - 1;

@@ -64,6 +64,25 @@ struct PremulPlan {
     u32 n_bases;
 };
 
+enum ProfCat { PC_TRANSPOSE = 0, PC_NTT, PC_LEAF, PC_COMPRESS, PC_CONSTRAINTS, PC_OOD, PC_DEEP, PC_FRI, PC_GRIND, PC_GATHER, PC_COUNT };
+struct Prof {
+    std::vector<cudaEvent_t> pool;
+    struct Region { int cat; size_t e0, e1; };
+    std::vector<Region> regions;
+    size_t used = 0;
+    cudaStream_t st = nullptr;
+    size_t ev() { if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); } return used++; }
+    size_t begin(int cat) { size_t a = ev(); cudaEventRecord(pool[a], st); regions.push_back({cat, a, a}); return regions.size() - 1; }
+    void end(size_t r) { size_t b = ev(); cudaEventRecord(pool[b], st); regions[r].e1 = b; }
+    void reset() { used = 0; regions.clear(); }
+    void resolve(float* ms, unsigned* counts) {
+        for (int i = 0; i < PC_COUNT; i++) { ms[i] = 0; counts[i] = 0; }
+        for (auto& r : regions) { float t = 0; cudaEventElapsedTime(&t, pool[r.e0], pool[r.e1]); ms[r.cat] += t; counts[r.cat]++; }
+    }
+    ~Prof() { for (auto e : pool) cudaEventDestroy(e); }
+};
+struct ProfScope { Prof& p; size_t r; ProfScope(Prof& p_, int cat) : p(p_), r(p_.begin(cat)) {} ~ProfScope() { p.end(r); } };
+
 struct Tree {
     DevBuf nodes;   // heap layout: layer d at ((1<<d)-1)*4, 4 u64 per digest
     u32 depth = 0;
@@ -118,6 +137,8 @@ struct mdn_session {
     bool keep_debug = false;
     mdn_timings timings{};
     cudaEvent_t ev[16];
+    Prof prof;
+    double leaf_bytes = 0, ntt_bytes = 0; unsigned long long perms = 0;
 
     NttPlan& ntt(u32 n);
     PremulPlan& premul_trace(u32 n);
@@ -249,11 +270,13 @@ void mdn_session::upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm
     size_t N = (size_t)1 << m.log_height;
     if (m.width == 0) return;
     if (on_device) {
+        ProfScope ps(prof, PC_TRANSPOSE);
         mk::launch_transpose_rm_to_cm(m.values, dst_cm, (u32)N, m.width, stream);
         return;
     }
     DevBuf staging; staging.alloc(N * m.width, stream);
     CUDA_OK(cudaMemcpyAsync(staging.p, m.values, N * m.width * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    ProfScope ps(prof, PC_TRANSPOSE);
     mk::launch_transpose_rm_to_cm(staging.p, dst_cm, (u32)N, m.width, stream);
 }
 
@@ -270,6 +293,8 @@ void mdn_session::lde_and_commit(Committed& c, float* t_lde, float* t_hash) {
         size_t N = (size_t)1 << m.log_n, L = N << lb;
         NttPlan& plan = ntt(m.log_n);
         PremulPlan& pm = premul_trace(m.log_n);
+        ProfScope ps(prof, PC_NTT);
+        ntt_bytes += (double)(N + L) * m.width * 8.0;   // read the trace column once, write the LDE once
         mk::launch_intt(m.coef, N, m.width, plan.T, stream);
         // column groups sized so a group's LDE (the fwd passes' working set) stays L2-resident
         size_t col_bytes = L * sizeof(u64);
@@ -322,11 +347,21 @@ void mdn_session::build_tree(Committed& c, bool) {
         u32 ln = c.mats[i].log_n;
         DevBuf& out = (prev == states_a.p && prev) ? states_b : states_a;
         if (!last) out.alloc((size_t)12 << (ln + lb), stream);
-        mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? c.tree.layer(depth) : nullptr, stream);
+        {
+            ProfScope ps(prof, PC_LEAF);
+            size_t Lg = (size_t)1 << (ln + lb);
+            for (int q = 0; q < args.n_mats; q++) { leaf_bytes += (double)Lg * args.m[q].width * 8.0; perms += Lg * ((args.m[q].width + 7) / 8); }
+            leaf_bytes += last ? (double)Lg * 32.0 : (double)Lg * 96.0;
+            mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? c.tree.layer(depth) : nullptr, stream);
+        }
         prev = out.p; prev_log = ln;
         i = j;
     }
-    for (u32 d = depth; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
+    {
+        ProfScope ps(prof, PC_COMPRESS);
+        perms += L - 1;
+        for (u32 d = depth; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
+    }
     CUDA_OK(cudaMemcpyAsync(c.root, c.tree.layer(0), 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
 }
@@ -346,6 +381,7 @@ u64 mdn_session::grind(u32 bits) {
     CUDA_OK(cudaMemcpyAsync(d.p, init, sizeof init, cudaMemcpyHostToDevice, stream));
     u64 start = 0, found = ~0ull;
     u64 batch = std::max<u64>(1ull << 14, std::min<u64>(1ull << 22, 4ull << bits));
+    ProfScope ps(prof, PC_GRIND);
     while (found == ~0ull) {
         if (start >= gl::P) fail(MDN_ERR_INVALID_ARG, "proof-of-work search exhausted");
         mk::launch_grind(d.p, ch.in_len, bits, start, batch, d.p + 12, stream);
@@ -367,6 +403,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     reset_proof();
     memset(&timings, 0, sizeof timings);
     mk::reset_launch_count();
+    prof.st = stream; prof.reset(); leaf_bytes = ntt_bytes = 0; perms = 0;
     if (!st || !traces || !chal) fail(MDN_ERR_INVALID_ARG, "null argument");
     if (st->n_airs == 0 || st->n_airs > 256) fail(MDN_ERR_INVALID_ARG, "AIR count must be in 1..=256");
     if (params.log_folding_arity != 2) fail(MDN_ERR_UNSUPPORTED, "only FRI folding arity 4 is implemented");
@@ -557,6 +594,7 @@ void mdn_session::finish() {
         ca.alpha = alpha; ca.beta = beta;
         ca.acc_in = acc_cur < 0 ? nullptr : acc_pp[acc_cur].p; ca.acc_in_log_n = acc_prev_log; ca.acc_out = acc_pp[nxt].p;
         ca.T = &ntt(ln).T;
+        ProfScope ps(prof, PC_CONSTRAINTS);
         if (mk::launch_constraints(ca, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "constraint program too large for the interpreter");
         acc_cur = nxt; acc_prev_log = ln;
     }
@@ -580,6 +618,8 @@ void mdn_session::finish() {
     {
         NttPlan& plan = ntt(log_max_n);
         PremulPlan& pm = premul_quotient(log_max_n);
+        size_t rq = prof.begin(PC_NTT);
+        ntt_bytes += (double)(Nmax + L) * 2 * B * 8.0;
         mk::launch_intt(acc.p, Nmax, 2 * B, plan.T, stream);
         quot_c.lde_buf.alloc(L * 2 * B, stream);
         quot_c.coef_buf = std::move(acc);
@@ -596,6 +636,7 @@ void mdn_session::finish() {
         // column-pair groups keep the working set near L2 size
         u32 per = 2 * B;   // items per chunk t
         for (u32 t = 0; t < B; t++) mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)t * per, per, plan.T, pm.P, stream);
+        prof.end(rq);
         build_tree(quot_c, true);
         tr.send_commitment(quot_c.root);
         memcpy(dbg_roots[2], quot_c.root, 32);
@@ -622,6 +663,7 @@ void mdn_session::finish() {
     struct MatEval { std::vector<u64> v; };   // width x 4
     std::vector<std::vector<MatEval>> evals(3);
     {
+        ProfScope ps_ood(prof, PC_OOD);
         std::map<u32, std::pair<DevBuf, DevBuf>> weights;   // per log height: (w0, w1)
         auto get_w = [&](u32 ln, E2 y0, E2 y1, std::pair<DevBuf, DevBuf>& slot) {
             slot.first.alloc((size_t)2 << ln, stream); slot.second.alloc((size_t)2 << ln, stream);
@@ -716,6 +758,7 @@ void mdn_session::finish() {
         da.log_n_max = log_max_n; da.log_blowup = lb; da.apow = d_apow.p; da.total_w = W;
         da.z0 = z; da.z1 = z_next; da.fz0 = fz[0]; da.fz1 = fz[1]; da.beta = dbeta;
         da.out = fri_layers[0].p; da.T = &ntt(log_max_n).T;
+        ProfScope ps(prof, PC_DEEP);
         mk::launch_deep(da, stream);
     }
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -747,8 +790,12 @@ void mdn_session::finish() {
         Tree& t = fri_trees[r];
         t.depth = log_dom - 2;
         t.nodes.alloc((2 * q - 1) * 4, stream);
-        mk::launch_fri_leaf_hash(fri_layers[r].p, q, t.layer(t.depth), stream);
-        for (u32 d = t.depth; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
+        {
+            ProfScope ps(prof, PC_FRI);
+            perms += 2 * q - 1;
+            mk::launch_fri_leaf_hash(fri_layers[r].p, q, t.layer(t.depth), stream);
+            for (u32 d = t.depth; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
+        }
         u64 root[4];
         CUDA_OK(cudaMemcpyAsync(root, t.layer(0), sizeof root, cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
@@ -757,7 +804,7 @@ void mdn_session::finish() {
         grind(params.folding_pow_bits);
         E2 fb = tr.ch.sample_ext();
         fri_layers.emplace_back(); fri_layers[r + 1].alloc(2 * q, stream);
-        mk::launch_fri_fold(fri_layers[r].p, log_dom, fb, fri_layers[r + 1].p, stream);
+        { ProfScope ps(prof, PC_FRI); mk::launch_fri_fold(fri_layers[r].p, log_dom, fb, fri_layers[r + 1].p, stream); }
         log_dom -= 2;
     }
     // final polynomial (fri/prover.rs:228-239): values on the size-final_deg subgroup are the
@@ -832,7 +879,7 @@ void mdn_session::finish() {
     {
         DevBuf d_ptrs, d_vals; d_ptrs.alloc(ptrs.size(), stream); d_vals.alloc(ptrs.size(), stream);
         CUDA_OK(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
-        mk::launch_gather((const u64* const*)d_ptrs.p, d_vals.p, ptrs.size(), stream);
+        { ProfScope ps(prof, PC_GATHER); mk::launch_gather((const u64* const*)d_ptrs.p, d_vals.p, ptrs.size(), stream); }
         std::vector<u64> vals(ptrs.size());
         CUDA_OK(cudaMemcpyAsync(vals.data(), d_vals.p, vals.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
@@ -857,6 +904,8 @@ void mdn_session::finish() {
     cudaEventElapsedTime(&timings.open, ev[6], ev[7]);
     cudaEventElapsedTime(&timings.total, ev[0], ev[7]);
     timings.kernel_launches = mk::launch_count();
+    prof.resolve(timings.kernel_ms, timings.kernel_regions);
+    timings.leaf_hash_bytes = leaf_bytes; timings.ntt_bytes = ntt_bytes; timings.permutations = perms;
     // release per-proof device memory (returns to the stream-ordered pool)
     main_c = Committed(); aux_c = Committed(); quot_c = Committed();
     in_proof = false;
