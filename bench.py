@@ -143,7 +143,7 @@ def main():
     lib = B.lib()   # raises BackendMissing if the CUDA library is absent: no fallback
     params = W.miden_pcs_params()
     lh = args.log_height
-    wl = W.Workload([lh] * 3, seed=W.SEED + rank)
+    wl = W.Workload([lh] * 3, seed=pkg.parallel.rank_seed(W.SEED, rank))
     sess = B.Session(params, local_rank)
 
     def observe(c, felts):
@@ -191,14 +191,8 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    total_v, total_e = max_over_ranks(total_v), max_over_ranks(total_e)
+    total_v = pkg.parallel.max_over_ranks(total_v, "cuda")
+    total_e = pkg.parallel.max_over_ranks(total_e, "cuda")
     cells = wl.cells
     value = world * cells * args.steps / total_v
     e2e = world * cells * args.steps / total_e

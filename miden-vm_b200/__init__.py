@@ -9,4 +9,4 @@ modules here are thin host-side helpers used by tests and bench.py:
   air_program  constructor for the AIR constraint op-list (`mdn_air.program`)
   workload     Miden production configuration + synthetic trace generator
 """
-from . import air_program, binding, workload  # noqa: F401
+from . import air_program, binding, parallel, workload  # noqa: F401
