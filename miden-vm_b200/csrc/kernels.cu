@@ -49,47 +49,107 @@ void launch_transpose_rm_to_cm(const u64* src, u64* dst, u32 n_rows, u32 width, 
 //                  ->  natural k = k1*N2 + k2
 // =============================================================================================
 static constexpr int NTT_THREADS = 256;
+// one radix-8 group per thread when possible
+static inline unsigned ntt_threads(u32 m, u32 log_cols) {
+    u32 g = (m + log_cols >= 3) ? (1u << (m + log_cols - 3)) : 1u;
+    if (g < 32) g = 32;
+    if (g > 256) g = 256;
+    return g;
+}
 
 __device__ __forceinline__ u64 w_pow(const u64* __restrict__ hi, const u64* __restrict__ lo, u32 lo_bits, u64 e) {
     return gl::mul(hi[e >> lo_bits], lo[e & ((1ull << lo_bits) - 1)]);
 }
 
-// DIF over `m` stages on a tile x[idx * cols + cc] (idx < 2^m, cols = 2^log_cols interleaved columns).
-// All index arithmetic is shifts/masks (every size is a power of two).
-__device__ __forceinline__ void smem_dif(u64* x, const u64* tw, u32 m, u32 log_cols) {
-    if (m == 0) return;
-    u32 total = 1u << (m - 1 + log_cols);        // butterflies per stage
-    u32 cmask = (1u << log_cols) - 1;
-    for (u32 s = 0; s < m; s++) {
-        u32 lh = m - s - 1;                        // log2(half)
-        u32 hmask = (1u << lh) - 1;
-        for (u32 b = threadIdx.x; b < total; b += blockDim.x) {
-            u32 cc = b & cmask, bb = b >> log_cols;
-            u32 j = bb & hmask, blk = bb >> lh;
-            u32 i0 = (((blk << (lh + 1)) + j) << log_cols) + cc, i1 = i0 + (1u << (lh + log_cols));
-            u64 a = x[i0], c = x[i1];
-            x[i0] = gl::add(a, c);
-            x[i1] = gl::mul(gl::sub(a, c), tw[j << s]);
+// ---------------------------------------------------------------------------------------------
+// Register-tiled radix-2 stages over a shared-memory tile.
+//   tile element (idx, cc), idx < 2^m, cc < 2^log_cols, lives at off(idx, cc); contiguous tiles
+//   (log_cols == 0) are padded by one word every 8 to keep the strided accesses conflict-free.
+//   Each thread takes groups of 2^LOGR elements idx = base + k * 2^b and runs LOGR stages on them in
+//   registers, so a size-2^m transform needs ceil(m / 3) shared-memory round trips instead of m.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 tile_off(u32 idx, u32 cc, u32 log_cols) {
+    u32 o = (idx << log_cols) + cc;
+    return log_cols ? o : o + (o >> 3);
+}
+__host__ __device__ __forceinline__ u32 tile_words(u32 m, u32 log_cols) {
+    u32 n = 1u << (m + log_cols);
+    return log_cols ? n : n + (n >> 3) + 1;
+}
+
+// DIT (bit-reversed -> natural) stages b .. b+LOGR-1 (butterfly spans 2^b .. 2^(b+LOGR-1)).
+template <int LOGR>
+__device__ __forceinline__ void dit_round(u64* x, const u64* tw, u32 m, u32 b, u32 log_cols) {
+    constexpr int R = 1 << LOGR;
+    u32 groups = 1u << (m - LOGR + log_cols);
+    for (u32 g = threadIdx.x; g < groups; g += blockDim.x) {
+        u32 cc = g & ((1u << log_cols) - 1), gg = g >> log_cols;
+        u32 lo = gg & ((1u << b) - 1), hi = gg >> b;
+        u32 base = (hi << (b + LOGR)) | lo;
+        u64 v[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) v[k] = x[tile_off(base + ((u32)k << b), cc, log_cols)];
+#pragma unroll
+        for (int st = 0; st < LOGR; st++) {
+            // span 2^(b+st): pairs (k, k + 2^st) with bit st of k clear; j = lo + (k mod 2^st) * 2^b
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & (1 << st)) continue;
+                u32 j = lo + ((u32)(k & ((1 << st) - 1)) << b);
+                u64 w = tw[j << (m - 1 - b - st)];
+                u64 a = v[k], c = glf::cmul(v[k + (1 << st)], w);
+                v[k] = glf::cadd(a, c);
+                v[k + (1 << st)] = glf::csub(a, c);
+            }
         }
+#pragma unroll
+        for (int k = 0; k < R; k++) x[tile_off(base + ((u32)k << b), cc, log_cols)] = v[k];
+    }
+}
+// DIF (natural -> bit-reversed) stages with spans 2^(b+LOGR-1) .. 2^b (descending).
+template <int LOGR>
+__device__ __forceinline__ void dif_round(u64* x, const u64* tw, u32 m, u32 b, u32 log_cols) {
+    constexpr int R = 1 << LOGR;
+    u32 groups = 1u << (m - LOGR + log_cols);
+    for (u32 g = threadIdx.x; g < groups; g += blockDim.x) {
+        u32 cc = g & ((1u << log_cols) - 1), gg = g >> log_cols;
+        u32 lo = gg & ((1u << b) - 1), hi = gg >> b;
+        u32 base = (hi << (b + LOGR)) | lo;
+        u64 v[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) v[k] = x[tile_off(base + ((u32)k << b), cc, log_cols)];
+#pragma unroll
+        for (int st = LOGR - 1; st >= 0; st--) {
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & (1 << st)) continue;
+                u32 j = lo + ((u32)(k & ((1 << st) - 1)) << b);
+                u64 w = tw[j << (m - 1 - b - st)];
+                u64 a = v[k], c = v[k + (1 << st)];
+                v[k] = glf::cadd(a, c);
+                v[k + (1 << st)] = glf::cmul(glf::csub(a, c), w);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) x[tile_off(base + ((u32)k << b), cc, log_cols)] = v[k];
+    }
+}
+__device__ __forceinline__ void smem_dit(u64* x, const u64* tw, u32 m, u32 log_cols) {
+    u32 b = 0;
+    while (b < m) {
+        u32 left = m - b;
+        if (left >= 3 && left != 4) { dit_round<3>(x, tw, m, b, log_cols); b += 3; }
+        else if (left == 4 || left == 2) { dit_round<2>(x, tw, m, b, log_cols); b += 2; }
+        else { dit_round<1>(x, tw, m, b, log_cols); b += 1; }
         __syncthreads();
     }
 }
-// DIT: bit-reversed input -> natural output.
-__device__ __forceinline__ void smem_dit(u64* x, const u64* tw, u32 m, u32 log_cols) {
-    if (m == 0) return;
-    u32 total = 1u << (m - 1 + log_cols);
-    u32 cmask = (1u << log_cols) - 1;
-    for (u32 s = m; s-- > 0;) {
-        u32 lh = m - s - 1;
-        u32 hmask = (1u << lh) - 1;
-        for (u32 b = threadIdx.x; b < total; b += blockDim.x) {
-            u32 cc = b & cmask, bb = b >> log_cols;
-            u32 j = bb & hmask, blk = bb >> lh;
-            u32 i0 = (((blk << (lh + 1)) + j) << log_cols) + cc, i1 = i0 + (1u << (lh + log_cols));
-            u64 a = x[i0], c = gl::mul(x[i1], tw[j << s]);
-            x[i0] = gl::add(a, c);
-            x[i1] = gl::sub(a, c);
-        }
+__device__ __forceinline__ void smem_dif(u64* x, const u64* tw, u32 m, u32 log_cols) {
+    u32 top = m;   // stages with spans below 2^top remain
+    while (top > 0) {
+        if (top >= 3 && top != 4) { dif_round<3>(x, tw, m, top - 3, log_cols); top -= 3; }
+        else if (top == 4 || top == 2) { dif_round<2>(x, tw, m, top - 2, log_cols); top -= 2; }
+        else { dif_round<1>(x, tw, m, top - 1, log_cols); top -= 1; }
         __syncthreads();
     }
 }
@@ -99,13 +159,13 @@ __global__ void __launch_bounds__(NTT_THREADS) k_intt_strided(u64* cols, size_t 
     u32 C = 1u << log_c;
     extern __shared__ u64 sm[];
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + (size_t)N1 * C;
+    u64* x = sm; u64* tw = sm + tile_words(T.n1, log_c);
     u64* col = cols + blockIdx.y * col_stride;
     u32 j2_0 = blockIdx.x * C;
     for (u32 i = threadIdx.x; i < N1 / 2; i += blockDim.x) tw[i] = T.twi_n1[i];
     for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
         u32 j1 = idx >> log_c, cc = idx & (C - 1);
-        x[idx] = col[(size_t)j1 * N2 + j2_0 + cc];
+        x[tile_off(j1, cc, log_c)] = col[(size_t)j1 * N2 + j2_0 + cc];
     }
     __syncthreads();
     smem_dif(x, tw, T.n1, log_c);
@@ -114,33 +174,33 @@ __global__ void __launch_bounds__(NTT_THREADS) k_intt_strided(u64* cols, size_t 
         u32 k1 = gl::bitrev32(slot, T.n1);
         u32 j2 = j2_0 + cc;
         u64 f = w_pow(T.wi_hi, T.wi_lo, T.lo_bits, (u64)j2 * k1);
-        col[(size_t)slot * N2 + j2] = gl::mul(x[idx], f);
+        col[(size_t)slot * N2 + j2] = glf::cmul(x[tile_off(slot, cc, log_c)], f);
     }
 }
 // inverse step 3 (or the whole transform when n1 == 0): contiguous chunk of N2
 __global__ void __launch_bounds__(NTT_THREADS) k_intt_contig(u64* cols, size_t col_stride, NttTables T) {
     extern __shared__ u64 sm[];
     u32 N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + N2;
+    u64* x = sm; u64* tw = sm + tile_words(T.n2, 0);
     u64* chunk = cols + blockIdx.y * col_stride + (size_t)blockIdx.x * N2;
     for (u32 i = threadIdx.x; i < N2 / 2; i += blockDim.x) tw[i] = T.twi_n2[i];
-    for (u32 i = threadIdx.x; i < N2; i += blockDim.x) x[i] = chunk[i];
+    for (u32 i = threadIdx.x; i < N2; i += blockDim.x) x[tile_off(i, 0, 0)] = chunk[i];
     __syncthreads();
     smem_dif(x, tw, T.n2, 0);
-    for (u32 i = threadIdx.x; i < N2; i += blockDim.x) chunk[i] = x[i];
+    for (u32 i = threadIdx.x; i < N2; i += blockDim.x) chunk[i] = x[tile_off(i, 0, 0)];
 }
 void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, cudaStream_t st) {
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
     if (T.n1 > 0) {
-        u32 log_c = 13 - T.n1; if (log_c > T.n2) log_c = T.n2;
+        u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
         u32 C = 1u << log_c;
-        size_t smem = ((size_t)N1 * C + N1 / 2) * sizeof(u64);
+        size_t smem = ((size_t)tile_words(T.n1, log_c) + N1 / 2) * sizeof(u64);
         cudaFuncSetAttribute(k_intt_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_intt_strided<<<dim3(N2 / C, n_cols), NTT_THREADS, smem, st>>>(cols, col_stride, T, log_c);
+        k_intt_strided<<<dim3(N2 / C, n_cols), ntt_threads(T.n1, log_c), smem, st>>>(cols, col_stride, T, log_c);
         COUNT_LAUNCH();
     }
-    size_t smem = ((size_t)N2 + N2 / 2 + 1) * sizeof(u64);
-    k_intt_contig<<<dim3(N1, n_cols), NTT_THREADS, smem, st>>>(cols, col_stride, T);
+    size_t smem = ((size_t)tile_words(T.n2, 0) + N2 / 2 + 1) * sizeof(u64);
+    k_intt_contig<<<dim3(N1, n_cols), ntt_threads(T.n2, 0), smem, st>>>(cols, col_stride, T);
     COUNT_LAUNCH();
 }
 
@@ -148,7 +208,7 @@ void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, c
 __global__ void __launch_bounds__(NTT_THREADS) k_fwd_contig(const FwdItem* __restrict__ items, NttTables T, PremulTables Pm) {
     extern __shared__ u64 sm[];
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + N2;
+    u64* x = sm; u64* tw = sm + tile_words(T.n2, 0);
     FwdItem it = items[blockIdx.y];
     u32 p_hi = blockIdx.x;
     u32 j1 = gl::bitrev32(p_hi, T.n1);
@@ -159,15 +219,15 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_contig(const FwdItem* __res
     for (u32 i = threadIdx.x; i < N2 / 2; i += blockDim.x) tw[i] = T.tw_n2[i];
     for (u32 i = threadIdx.x; i < N2; i += blockDim.x) {
         u32 j2 = gl::bitrev32(i, T.n2);
-        x[i] = gl::mul(src[i], gl::mul(ta[j2], fb));
+        x[tile_off(i, 0, 0)] = glf::cmul(src[i], glf::mul(ta[j2], fb));
     }
     __syncthreads();
     smem_dit(x, tw, T.n2, 0);
     if (T.n1 > 0) {
         for (u32 k2 = threadIdx.x; k2 < N2; k2 += blockDim.x)
-            dst[k2] = gl::mul(x[k2], w_pow(T.w_hi, T.w_lo, T.lo_bits, (u64)j1 * k2));
+            dst[k2] = glf::cmul(x[tile_off(k2, 0, 0)], glf::mul(T.w_hi[((u64)j1 * k2) >> T.lo_bits], T.w_lo[((u64)j1 * k2) & ((1ull << T.lo_bits) - 1)]));
     } else {
-        for (u32 k2 = threadIdx.x; k2 < N2; k2 += blockDim.x) dst[k2] = x[k2];
+        for (u32 k2 = threadIdx.x; k2 < N2; k2 += blockDim.x) dst[k2] = x[tile_off(k2, 0, 0)];
     }
 }
 // forward step 3: strided tile [N1][C], DIT along p_hi, in place
@@ -175,32 +235,32 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_strided(const FwdItem* __re
     u32 C = 1u << log_c;
     extern __shared__ u64 sm[];
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + (size_t)N1 * C;
+    u64* x = sm; u64* tw = sm + tile_words(T.n1, log_c);
     u64* col = items[blockIdx.y].dst;
     u32 k2_0 = blockIdx.x * C;
     for (u32 i = threadIdx.x; i < N1 / 2; i += blockDim.x) tw[i] = T.tw_n1[i];
     for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
         u32 p_hi = idx >> log_c, cc = idx & (C - 1);
-        x[idx] = col[(size_t)p_hi * N2 + k2_0 + cc];
+        x[tile_off(p_hi, cc, log_c)] = col[(size_t)p_hi * N2 + k2_0 + cc];
     }
     __syncthreads();
     smem_dit(x, tw, T.n1, log_c);
     for (u32 idx = threadIdx.x; idx < N1 * C; idx += blockDim.x) {
         u32 k1 = idx >> log_c, cc = idx & (C - 1);
-        col[(size_t)k1 * N2 + k2_0 + cc] = x[idx];
+        col[(size_t)k1 * N2 + k2_0 + cc] = x[tile_off(k1, cc, log_c)];
     }
 }
 void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, const PremulTables& Pm, cudaStream_t st) {
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
-    size_t smem = ((size_t)N2 + N2 / 2 + 1) * sizeof(u64);
-    k_fwd_contig<<<dim3(N1, n_items), NTT_THREADS, smem, st>>>(d_items, T, Pm);
+    size_t smem = ((size_t)tile_words(T.n2, 0) + N2 / 2 + 1) * sizeof(u64);
+    k_fwd_contig<<<dim3(N1, n_items), ntt_threads(T.n2, 0), smem, st>>>(d_items, T, Pm);
     COUNT_LAUNCH();
     if (T.n1 > 0) {
-        u32 log_c = 13 - T.n1; if (log_c > T.n2) log_c = T.n2;
+        u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
         u32 C = 1u << log_c;
-        size_t smem2 = ((size_t)N1 * C + N1 / 2) * sizeof(u64);
+        size_t smem2 = ((size_t)tile_words(T.n1, log_c) + N1 / 2) * sizeof(u64);
         cudaFuncSetAttribute(k_fwd_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        k_fwd_strided<<<dim3(N2 / C, n_items), NTT_THREADS, smem2, st>>>(d_items, T, log_c);
+        k_fwd_strided<<<dim3(N2 / C, n_items), ntt_threads(T.n1, log_c), smem2, st>>>(d_items, T, log_c);
         COUNT_LAUNCH();
     }
 }

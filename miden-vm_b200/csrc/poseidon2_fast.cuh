@@ -64,6 +64,20 @@ __device__ __forceinline__ u64 wred(W w) {
     asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(w.lo), "l"(m));
     return r + (u64)(0u - c);
 }
+// ---- canonical (< p) arithmetic built on the carry flag, for the NTT butterflies ----------------
+__device__ __forceinline__ u64 canon_cc(u64 r) {      // r in [0, 2^64) -> r mod p
+    u64 t; u32 m;
+    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(t), "=r"(m) : "l"(r), "l"(0xFFFFFFFF00000001ull));
+    return t - (u64)m;                                 // borrowed (r < p): add p back == subtract 2^32 - 1
+}
+__device__ __forceinline__ u64 csub(u64 a, u64 b) {   // a, b < p
+    u64 d; u32 m;
+    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(d), "=r"(m) : "l"(a), "l"(b));
+    return d - (u64)m;
+}
+__device__ __forceinline__ u64 cadd(u64 a, u64 b) { return csub(a, 0xFFFFFFFF00000001ull - b); }   // a - (p - b)
+__device__ __forceinline__ u64 cmul(u64 a, u64 b) { return canon_cc(mul(a, b)); }
+
 // x / 2 for any representative: result < 2^64.
 __device__ __forceinline__ u64 half(u64 x) { return (x >> 1) + ((x & 1) ? 0x7FFFFFFF80000001ull : 0ull); }
 
