@@ -73,7 +73,7 @@ typedef struct {
  * Ops (leaf vocabulary of crates/ace-codegen/src/dag/lower.rs:109-210):
  *   0 MAIN(a=row offset 0|1, b=col)  1 AUX(a=offset, b=EF col)  2 PUBLIC(a)  3 CHALLENGE(a)
  *   4 AUX_VALUE(a)  5 IS_FIRST_ROW  6 IS_LAST_ROW  7 IS_TRANSITION  8 CONST(a)  9 EXT_CONST(a)
- *   10 ADD(a,b)  11 SUB(a,b)  12 MUL(a,b)  13 NEG(a)
+ *   10 ADD(a,b)  11 SUB(a,b)  12 MUL(a,b)  13 NEG(a)  14 PERIODIC(a=periodic column)
  * Constraints are folded as acc <- acc*alpha + C_k in emission order
  * (crates/lifted-stark/src/verifier/constraints.rs:83,108). */
 typedef struct {
@@ -84,6 +84,12 @@ typedef struct {
     uint32_t log_quotient_degree;   /* domain.rs:585-598 (symbolic degree analysis stays host-side) */
     uint32_t program_words;
     const uint32_t* program;
+    /* `BaseAir::periodic_columns_matrix()` (crates/lifted-stark/src/prover/periodic.rs:49-98): row-major
+     * (1 << log_max_period) x num_periodic_columns, every column repeated to the maximum period.
+     * NULL / 0 when the AIR has no periodic columns. */
+    const uint64_t* periodic_values;
+    uint32_t num_periodic_columns;
+    uint32_t log_max_period;
 } mdn_air;
 
 /* p3 RowMajorMatrix<Felt>: `values` has (1 << log_height) * width entries.  With

@@ -381,7 +381,7 @@ struct ConstraintKArgs {
     u64 zh[16], inv_zh[16];                           // per coset t
 };
 
-template <int MAXN>
+template <int MAXS>
 __global__ void __launch_bounds__(128) k_constraints(ConstraintKArgs a) {
     size_t L = (size_t)1 << (a.log_n + a.log_b);
     size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,10 +398,14 @@ __global__ void __launch_bounds__(128) k_constraints(ConstraintKArgs a) {
         is_last.a = gl::mul(a.zh[t], gl::mul(inv, d_first));
         is_trans.a = d_last;
     }
-    E2 vals[MAXN];
-    const u32* nd = a.air.nodes;
-    for (u32 i = 0; i < a.air.n_nodes; i++, nd += 3) {
-        u32 op = nd[0], x = nd[1], y = nd[2];
+    size_t per_idx = ((size_t)(r & ((1u << a.air.log_max_period) - 1)) << a.log_b) | t;
+    size_t per_stride = (size_t)1 << (a.air.log_max_period + a.log_b);
+    E2 slot[MAXS];
+    E2 acc = gl::e2(0, 0);
+    const uint4* code = reinterpret_cast<const uint4*>(a.air.code);
+    for (u32 i = 0; i < a.air.n_instr; i++) {
+        uint4 ins = code[i];
+        u32 op = ins.x & 0xff, ext = ins.x >> 8, x = ins.z, y = ins.w;
         E2 v;
         switch (op) {
             case 0: v = gl::e2(a.main_lde[(size_t)y * L + (x ? pos_next : pos)], 0); break;
@@ -414,15 +418,15 @@ __global__ void __launch_bounds__(128) k_constraints(ConstraintKArgs a) {
             case 7: v = is_trans; break;
             case 8: v = gl::e2(a.air.consts[x], 0); break;
             case 9: v = gl::e2(a.air.consts[x], a.air.consts[x + 1]); break;
-            case 10: v = gl::e2_add(vals[x], vals[y]); break;
-            case 11: v = gl::e2_sub(vals[x], vals[y]); break;
-            case 12: v = gl::e2_mul(vals[x], vals[y]); break;
-            default: v = gl::e2_neg(vals[x]); break;
+            case 10: v = ext ? gl::e2_add(slot[x], slot[y]) : gl::e2(gl::add(slot[x].a, slot[y].a), 0); break;
+            case 11: v = ext ? gl::e2_sub(slot[x], slot[y]) : gl::e2(gl::sub(slot[x].a, slot[y].a), 0); break;
+            case 12: v = ext ? gl::e2_mul(slot[x], slot[y]) : gl::e2(gl::mul(slot[x].a, slot[y].a), 0); break;
+            case 13: v = ext ? gl::e2_neg(slot[x]) : gl::e2(gl::neg(slot[x].a), 0); break;
+            case 14: v = gl::e2(a.air.periodic[x * per_stride + per_idx], 0); break;
+            default: acc = gl::e2_add(gl::e2_mul(acc, a.alpha), slot[x]); continue;
         }
-        vals[i] = v;
+        slot[ins.y] = v;
     }
-    E2 acc = gl::e2(0, 0);
-    for (u32 k = 0; k < a.air.n_constraints; k++) acc = gl::e2_add(gl::e2_mul(acc, a.alpha), vals[a.air.constraints[k]]);
     E2 q = gl::e2_mulf(acc, a.inv_zh[t]);
     if (a.acc_in) {
         size_t Lin = (size_t)1 << (a.acc_in_log_n + a.log_b);
@@ -451,8 +455,10 @@ int launch_constraints(const ConstraintArgs& a, cudaStream_t st) {
     for (u32 t = 0; t < B; t++) { k.zh[t] = gl::sub(gl::mul(s_pow_n, x), 1); k.inv_zh[t] = gl::inv(k.zh[t]); x = gl::mul(x, w_b); }
     size_t L = (size_t)1 << log_lde;
     unsigned blocks = (unsigned)((L + 127) / 128);
-    if (a.air.n_nodes <= 32) k_constraints<32><<<blocks, 128, 0, st>>>(k);
-    else if (a.air.n_nodes <= 256) k_constraints<256><<<blocks, 128, 0, st>>>(k);
+    if (a.air.n_slots <= 16) k_constraints<16><<<blocks, 128, 0, st>>>(k);
+    else if (a.air.n_slots <= 64) k_constraints<64><<<blocks, 128, 0, st>>>(k);
+    else if (a.air.n_slots <= 256) k_constraints<256><<<blocks, 128, 0, st>>>(k);
+    else if (a.air.n_slots <= 1024) k_constraints<1024><<<blocks, 128, 0, st>>>(k);
     else return -1;
     COUNT_LAUNCH();
     return 0;
@@ -461,16 +467,28 @@ int launch_constraints(const ConstraintArgs& a, cudaStream_t st) {
 // =============================================================================================
 // OOD evaluation: dot products of coefficient columns with y^(bitrev(p))
 // =============================================================================================
-__global__ void k_pow_bitrev(E2 y, u32 n, u64* __restrict__ wvec) {
+struct PowTable { E2 sq[24]; };   // sq[i] = y^(2^i)
+__global__ void k_pow_bitrev(PowTable tab, u32 n, u64* __restrict__ wvec) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= ((size_t)1 << n)) return;
-    u32 e = gl::bitrev32((u32)p, n);
-    E2 w = gl::e2_pow(y, e);
+    // exponent bitrev_n(p): bit (n-1-i) of the exponent is bit i of p
+    E2 w = gl::e2(1, 0);
+    bool first = true;
+    for (u32 i = 0; i < n; i++) {
+        if ((p >> i) & 1) {
+            E2 f = tab.sq[n - 1 - i];
+            w = first ? f : gl::e2_mul(w, f);
+            first = false;
+        }
+    }
     reinterpret_cast<ulonglong2*>(wvec)[p] = make_ulonglong2(w.a, w.b);
 }
 void launch_pow_bitrev(E2 y, u32 n, u64* wvec, cudaStream_t st) {
     size_t N = (size_t)1 << n;
-    k_pow_bitrev<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(y, n, wvec);
+    PowTable tab;
+    E2 x = y;
+    for (u32 i = 0; i < 24; i++) { tab.sq[i] = x; x = gl::e2_sqr(x); }
+    k_pow_bitrev<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(tab, n, wvec);
     COUNT_LAUNCH();
 }
 
@@ -561,7 +579,18 @@ __global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
         size_t pm = ((size_t)t << M.log_n) + (r & ((1u << M.log_n) - 1));
         const u64* base = M.base + pm;
         const u64* ap = sm_apow + 2 * M.alpha_off;
-        for (u32 c = 0; c < M.width; c++) {
+        u32 c = 0;
+        for (; c + 4 <= M.width; c += 4) {
+            u64 v0 = base[(size_t)c * Lm], v1 = base[(size_t)(c + 1) * Lm];
+            u64 v2 = base[(size_t)(c + 2) * Lm], v3 = base[(size_t)(c + 3) * Lm];
+            glf::W wa = glf::wide(glf::mul(ap[2 * c], v0)), wb = glf::wide(glf::mul(ap[2 * c + 1], v0));
+            glf::wadd(wa, glf::mul(ap[2 * c + 2], v1)); glf::wadd(wb, glf::mul(ap[2 * c + 3], v1));
+            glf::wadd(wa, glf::mul(ap[2 * c + 4], v2)); glf::wadd(wb, glf::mul(ap[2 * c + 5], v2));
+            glf::wadd(wa, glf::mul(ap[2 * c + 6], v3)); glf::wadd(wb, glf::mul(ap[2 * c + 7], v3));
+            glf::wadd(wa, fr.a); glf::wadd(wb, fr.b);
+            fr.a = glf::canon_cc(glf::wred(wa)); fr.b = glf::canon_cc(glf::wred(wb));
+        }
+        for (; c < M.width; c++) {
             u64 v = base[(size_t)c * Lm];
             fr.a = gl::add(fr.a, gl::mul(ap[2 * c], v));
             fr.b = gl::add(fr.b, gl::mul(ap[2 * c + 1], v));

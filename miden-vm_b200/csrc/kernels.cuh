@@ -71,12 +71,18 @@ void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
 // ---------------------------------------------------------------------------------------------
 // Constraints / quotient
 // ---------------------------------------------------------------------------------------------
+// Compiled constraint program: 4 words per instruction {op | ext << 8, dst slot, a, b}.  Ops 0..14 as in
+// include/miden_b200.h (operands of ADD/SUB/MUL/NEG are SLOTS), 15 = FOLD slot a into the accumulator
+// (acc <- acc * alpha + slot).  `ext` = 1 selects extension-field arithmetic for ADD/SUB/MUL/NEG.
+// Slots are assigned by liveness on the host, so the interpreter's register file is the program's
+// maximum number of simultaneously live values, not its node count.
 struct AirDev {
-    const u32* nodes;        // 3 words per node
-    const u32* constraints;
+    const u32* code;         // 4 words per instruction
     const u64* consts;
-    u32 n_nodes, n_constraints;
-    u32 uses_selectors;      // any IS_FIRST / IS_LAST / IS_TRANSITION
+    const u64* periodic;     // [col][(r mod max_period) * B + t], or NULL
+    u32 n_instr, n_slots;
+    u32 uses_selectors;
+    u32 log_max_period, n_periodic;
 };
 struct ConstraintArgs {
     const u64* main_lde; u32 main_width;

@@ -434,7 +434,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         bool uses_sel = false;
         for (u32 j = 0; j < nn; j++) {
             u32 op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
-            if (op > 13) fail(MDN_ERR_INVALID_ARG, "AIR %u: unknown op %u", i, op);
+            if (op > 14) fail(MDN_ERR_INVALID_ARG, "AIR %u: unknown op %u", i, op);
             if (op >= 5 && op <= 7) uses_sel = true;
             if (op >= 10 && op <= 12 && (x >= j || y >= j)) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
             if (op == 13 && x >= j) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
@@ -447,23 +447,99 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
             if (op == 9 && x + 1 >= nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: constant out of range", i);
         }
         for (u32 j = 0; j < nc; j++) if (w[5 + 3 * nn + j] >= nn) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint id", i);
-        if (nn > 256) fail(MDN_ERR_UNSUPPORTED, "AIR %u: constraint program with %u nodes exceeds the interpreter's 256-node limit", i, nn);
+        // ---- compile: event stream (node definitions + constraint folds in emission order), liveness,
+        //      slot assignment ----
+        struct Ev { u32 fold; u32 node; };
+        std::vector<Ev> evs; evs.reserve(nn + nc);
+        { u32 kk = 0;
+          for (u32 j = 0; j < nn; j++) {
+              evs.push_back({0, j});
+              while (kk < nc && w[5 + 3 * nn + kk] <= j) { evs.push_back({1, w[5 + 3 * nn + kk]}); kk++; }
+          } }
+        std::vector<u32> last_use(nn, 0);
+        std::vector<uint8_t> is_ext(nn, 0);
+        for (u32 e = 0; e < evs.size(); e++) {
+            if (evs[e].fold) { last_use[evs[e].node] = e; continue; }
+            u32 j = evs[e].node, op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
+            last_use[j] = std::max(last_use[j], e);
+            if (op >= 10 && op <= 12) { last_use[x] = e; last_use[y] = e; is_ext[j] = is_ext[x] | is_ext[y]; }
+            else if (op == 13) { last_use[x] = e; is_ext[j] = is_ext[x]; }
+            else is_ext[j] = (op == 1 || op == 3 || op == 4 || op == 9);
+            if (op == 14 && x >= a.num_periodic_columns) fail(MDN_ERR_INVALID_ARG, "AIR %u: periodic column out of range", i);
+        }
+        std::vector<u32> slot_of(nn, 0), free_slots;
+        u32 n_slots = 0;
+        std::vector<u32> code; code.reserve(4 * evs.size());
+        auto release = [&](u32 node, u32 e) { if (last_use[node] == e) free_slots.push_back(slot_of[node]); };
+        for (u32 e = 0; e < evs.size(); e++) {
+            if (evs[e].fold) {
+                code.insert(code.end(), {15u | ((u32)is_ext[evs[e].node] << 8), 0u, slot_of[evs[e].node], 0u});
+                release(evs[e].node, e);
+                continue;
+            }
+            u32 j = evs[e].node, op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
+            u32 ox = x, oy = y;
+            if (op >= 10 && op <= 13) {
+                ox = slot_of[x]; oy = (op == 13) ? 0 : slot_of[y];
+                release(x, e);
+                if (op != 13 && y != x) release(y, e);
+            }
+            u32 dst;
+            if (!free_slots.empty()) { dst = free_slots.back(); free_slots.pop_back(); }
+            else dst = n_slots++;
+            slot_of[j] = dst;
+            code.insert(code.end(), {op | ((u32)is_ext[j] << 8), dst, ox, oy});
+            if (last_use[j] == e) free_slots.push_back(dst);   // dead value
+        }
+        if (n_slots > 1024) fail(MDN_ERR_UNSUPPORTED, "AIR %u: constraint program needs %u live values (interpreter limit 1024)", i, n_slots);
+        std::vector<u64> hostp((code.size() + 1) / 2 + nk + 2, 0);
+        memcpy(hostp.data(), code.data(), code.size() * sizeof(u32));
+        size_t const_off = (code.size() + 1) / 2;
         size_t words32 = 3 * (size_t)nn + nc;
-        size_t n64 = (words32 + 1) / 2 + nk;
-        std::vector<u64> hostp(n64 + 1, 0);
-        memcpy(hostp.data(), w + 5, words32 * sizeof(u32));
         for (u32 j = 0; j < nk; j++) {
             u64 v = (u64)w[5 + words32 + 2 * j] | ((u64)w[5 + words32 + 2 * j + 1] << 32);
             if (v >= gl::P) fail(MDN_ERR_INVALID_ARG, "AIR %u: non-canonical constant", i);
-            hostp[(words32 + 1) / 2 + j] = v;
+            hostp[const_off + j] = v;
+        }
+        // periodic columns: table[col][m] = P_col(s^(n/maxp) * w_{maxp*B}^m), m < maxp*B
+        // (prover/periodic.rs:49-98; the column is interpolated over the size-maxp subgroup)
+        size_t per_off = hostp.size();
+        if (a.num_periodic_columns) {
+            if (!a.periodic_values) fail(MDN_ERR_INVALID_ARG, "AIR %u: periodic_values is NULL", i);
+            if (a.log_max_period > traces[i].log_height) fail(MDN_ERR_INVALID_ARG, "AIR %u: periodic column period exceeds the trace height", i);
+            size_t mp = (size_t)1 << a.log_max_period, np = a.num_periodic_columns, tl = mp << lb;
+            u64 wp_inv = gl::inv(gl::two_adic_generator(a.log_max_period)), mp_inv = gl::inv((u64)mp);
+            u64 sh = gl::exp_pow2(gl::lde_shift(traces[i].log_height + lb), traces[i].log_height - a.log_max_period);
+            u64 wq = gl::two_adic_generator(a.log_max_period + lb);
+            hostp.resize(per_off + np * tl);
+            std::vector<u64> coef(mp);
+            for (size_t c = 0; c < np; c++) {
+                for (size_t kq = 0; kq < mp; kq++) {        // naive inverse DFT (periods are tiny)
+                    u64 acc = 0, wk = gl::pow(wp_inv, kq), xx = 1;
+                    for (size_t rr = 0; rr < mp; rr++) {
+                        u64 v = a.periodic_values[rr * np + c];
+                        if (v >= gl::P) fail(MDN_ERR_INVALID_ARG, "AIR %u: non-canonical periodic value", i);
+                        acc = gl::add(acc, gl::mul(v, xx)); xx = gl::mul(xx, wk);
+                    }
+                    coef[kq] = gl::mul(acc, mp_inv);
+                }
+                u64 pt = sh;
+                for (size_t m2 = 0; m2 < tl; m2++) {
+                    u64 acc = 0;
+                    for (size_t kq = mp; kq-- > 0;) acc = gl::add(gl::mul(acc, pt), coef[kq]);
+                    hostp[per_off + c * tl + m2] = acc;
+                    pt = gl::mul(pt, wq);
+                }
+            }
         }
         h.program.alloc(hostp.size(), stream);
         CUDA_OK(cudaMemcpyAsync(h.program.p, hostp.data(), hostp.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
-        h.dev.nodes = (const u32*)h.program.p;
-        h.dev.constraints = (const u32*)h.program.p + 3 * (size_t)nn;
-        h.dev.consts = h.program.p + (words32 + 1) / 2;
-        h.dev.n_nodes = nn; h.dev.n_constraints = nc; h.dev.uses_selectors = uses_sel;
+        h.dev.code = (const u32*)h.program.p;
+        h.dev.consts = h.program.p + const_off;
+        h.dev.periodic = a.num_periodic_columns ? h.program.p + per_off : nullptr;
+        h.dev.n_instr = (u32)(code.size() / 4); h.dev.n_slots = std::max(1u, n_slots); h.dev.uses_selectors = uses_sel;
+        h.dev.log_max_period = a.log_max_period; h.dev.n_periodic = a.num_periodic_columns;
     }
     publics.assign(st->public_values, st->public_values + st->n_public_values);
     // TraceOrder: stable sort on (log_height, instance)  (order.rs)
@@ -678,7 +754,7 @@ void mdn_session::finish() {
                 if (!cm.width) continue;
                 u32 ln = cm.log_n, lr = log_max_n - ln;
                 size_t Nm = (size_t)1 << ln;
-                u32 n_chunks = (u32)std::min<size_t>(Nm, 64);
+                u32 n_chunks = (u32)std::max<size_t>(1, std::min<size_t>(Nm / 1024, 1024));
                 u64 n_inv = gl::inv((u64)Nm);   // launch_intt leaves coefficients scaled by N
                 if (g < 2) {
                     auto it = weights.find(ln);
@@ -950,7 +1026,9 @@ int mdn_session_create(const mdn_pcs_params* params, int cuda_device, mdn_sessio
 void mdn_session_destroy(mdn_session* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    // every stream-ordered allocation must be returned before the stream goes away
     s->reset_proof();
+    s->d_publics.release(); s->d_randomness.release(); s->d_aux_values.release();
     s->ntt_plans.clear(); s->premul_plans.clear();
     cudaStreamSynchronize(s->stream);
     for (auto& evn : s->ev) cudaEventDestroy(evn);

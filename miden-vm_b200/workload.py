@@ -58,7 +58,7 @@ class Workload:
 
     def __init__(self, log_heights, widths=MIDEN_WIDTHS, aux_widths=MIDEN_AUX_WIDTHS, seed=SEED,
                  programs=None, num_randomness=2, public_values=(), log_quotient_degrees=None, traces=None,
-                 num_aux_values=None):
+                 num_aux_values=None, periodic=None):
         self.k = len(log_heights)
         self.log_heights = list(log_heights)
         self.widths = list(widths)[: self.k]
@@ -76,6 +76,13 @@ class Workload:
             a.log_quotient_degree = lqd[i]
             a.program_words = len(self.programs[i])
             a.program = self.programs[i].ctypes.data_as(u32p)
+            per = periodic[i] if periodic is not None else None
+            if per is not None:
+                per = np.ascontiguousarray(per, dtype=np.uint64)     # (max_period, n_cols) row-major
+                self._periodic_keep = getattr(self, "_periodic_keep", []) + [per]
+                a.periodic_values = per.ctypes.data_as(u64p)
+                a.num_periodic_columns = per.shape[1]
+                a.log_max_period = int(per.shape[0]).bit_length() - 1
         self.public_values = np.array(list(public_values), dtype=np.uint64)
         # default MultiAir::observe: len(air_inputs), air_inputs, max_aux_inputs (0), len(aux_inputs) (0)
         self.observe_felts = np.array([len(self.public_values), *self.public_values, 0, 0], dtype=np.uint64)

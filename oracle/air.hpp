@@ -28,6 +28,7 @@ enum AirOp : uint32_t {
     OP_EXT_CONST = 9,   // a = constant-pool index of (c0, c1)                     -> EF
     OP_ADD = 10, OP_SUB = 11, OP_MUL = 12,  // a, b = node ids; EF if either is EF
     OP_NEG = 13,        // a = node id
+    OP_PERIODIC = 14,   // a = periodic column index                               -> F
 };
 
 struct AirNode { uint32_t op, a, b; };
@@ -63,7 +64,7 @@ struct AirProgram {
                     if (nd.a >= i) throw std::runtime_error("air program: forward reference");
                     p.is_ext[i] = p.is_ext[nd.a]; break;
                 default:
-                    if (nd.op > OP_NEG) throw std::runtime_error("air program: unknown op");
+                    if (nd.op > OP_PERIODIC) throw std::runtime_error("air program: unknown op");
                     p.is_ext[i] = 0;
             }
         }
@@ -77,6 +78,7 @@ struct AirPoint {
     const Fp* main_local; const Fp* main_next;
     const Fp* aux_local; const Fp* aux_next;   // base-field layout: EF column c = (aux[2c], aux[2c+1])
     const Fp* publics; const Ef* challenges; const Ef* aux_values;
+    const Ef* periodic = nullptr;              // periodic column values at this point
     Ef is_first, is_last, is_transition;       // EF so the same evaluator serves the OOD check
     // For the OOD check main/aux cells are EF; then these are used instead of the Fp pointers.
     const Ef* main_local_ef = nullptr; const Ef* main_next_ef = nullptr;
@@ -110,6 +112,7 @@ inline Ef air_eval_folded(const AirProgram& p, const AirPoint& pt, Ef alpha, std
             case OP_SUB: v = scratch[nd.a] - scratch[nd.b]; break;
             case OP_MUL: v = scratch[nd.a] * scratch[nd.b]; break;
             case OP_NEG: v = -scratch[nd.a]; break;
+            case OP_PERIODIC: v = pt.periodic[nd.a]; break;
         }
         scratch[i] = v;
     }

@@ -14,7 +14,8 @@ extern "C" {
 
 struct orc_pcs_params { uint32_t log_blowup, log_folding_arity, log_final_degree, folding_pow_bits, deep_pow_bits, num_queries, query_pow_bits; };
 struct orc_challenger { uint64_t sponge_state[12]; uint64_t input_buffer[8]; uint32_t input_len, output_len; };
-struct orc_air { uint32_t width, aux_width, num_aux_values, num_randomness, log_quotient_degree, program_words; const uint32_t* program; };
+struct orc_air { uint32_t width, aux_width, num_aux_values, num_randomness, log_quotient_degree, program_words; const uint32_t* program;
+                 const uint64_t* periodic_values; uint32_t num_periodic_columns, log_max_period; };
 struct orc_matrix { const uint64_t* values; uint32_t log_height, width; };
 struct orc_statement { const orc_air* airs; uint32_t n_airs; const uint64_t* public_values; uint32_t n_public_values; const uint64_t* observe_felts; uint32_t n_observe_felts; };
 typedef int (*orc_aux_builder)(void* ctx, uint32_t instance, const orc_matrix* main, const uint64_t* randomness, uint64_t* aux_out, uint64_t* aux_values);
@@ -112,6 +113,9 @@ static Statement to_statement(const orc_statement* st) {
         d.width = a.width; d.aux_width = a.aux_width; d.num_aux_values = a.num_aux_values;
         d.num_randomness = a.num_randomness; d.log_quotient_degree = a.log_quotient_degree;
         d.program = AirProgram::parse(a.program, a.program_words);
+        d.n_periodic = a.num_periodic_columns; d.log_max_period = a.log_max_period;
+        for (size_t q = 0; q < ((size_t)a.num_periodic_columns << a.log_max_period); q++) d.periodic.push_back(Fp(a.periodic_values[q]));
+        for (auto& nd : d.program.nodes) if (nd.op == OP_PERIODIC && nd.a >= d.n_periodic) throw std::runtime_error("air program: periodic column out of range");
         s.airs.push_back(std::move(d));
     }
     for (uint32_t i = 0; i < st->n_public_values; i++) s.public_values.push_back(Fp(st->public_values[i]));

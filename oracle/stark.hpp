@@ -33,6 +33,20 @@ struct AirDesc {
     size_t num_randomness = 0;
     unsigned log_quotient_degree = 0;   // domain.rs:585-598 (symbolic degree analysis is host-side)
     AirProgram program;
+    // periodic_columns_matrix(): max_period x n_periodic, row-major (prover/periodic.rs:49-98)
+    std::vector<Fp> periodic; size_t n_periodic = 0; unsigned log_max_period = 0;
+    // coefficients (ascending) of periodic column c over the size-max_period subgroup
+    std::vector<std::vector<Fp>> periodic_coeffs() const {
+        size_t mp = size_t(1) << log_max_period;
+        std::vector<std::vector<Fp>> out;
+        for (size_t c = 0; c < n_periodic; c++) {
+            Matrix m(mp, 1);
+            for (size_t r = 0; r < mp; r++) m.row(r)[0] = periodic[r * n_periodic + c];
+            idft_rows(m);
+            out.push_back(m.v);
+        }
+        return out;
+    }
 };
 
 // (aux trace as EF row-major flattened to base: N x 2*aux_width, aux values)
@@ -120,9 +134,11 @@ inline std::vector<Ef> eval_quotient(const AirDesc& air, const Matrix& main_lde,
     // The committed LDE (bit-reversed rows, height n*B) holds gJ as its first gj rows
     // (commit.rs:95-106): natural row i of gJ = physical row bitrev_{log_gj}(i).
     std::vector<Ef> out(gj);
+    auto pcoef = air.periodic_coeffs();
 #pragma omp parallel if (gj > 1024)
     {
         std::vector<Ef> scratch;
+        std::vector<Ef> per(air.n_periodic);
 #pragma omp for schedule(static)
         for (size_t i = 0; i < gj; i++) {
             size_t inext = (i + D) & (gj - 1);
@@ -134,6 +150,11 @@ inline std::vector<Ef> eval_quotient(const AirDesc& air, const Matrix& main_lde,
             pt.publics = publics.data(); pt.challenges = randomness.data(); pt.aux_values = aux_values.data();
             Fp z = zh[i & (D - 1)];
             pt.is_first = Ef(z * d_first[i]); pt.is_last = Ef(z * d_last[i]); pt.is_transition = Ef(xs[i] - omega_h_inv);
+            if (air.n_periodic) {
+                Fp y = fp_exp_pow2(xs[i], log_n - air.log_max_period);
+                for (size_t c = 0; c < air.n_periodic; c++) per[c] = Ef(horner_eval(pcoef[c], y));
+                pt.periodic = per.data();
+            }
             Ef folded = air_eval_folded(air.program, pt, alpha, scratch);
             out[i] = folded * inv_zh[i & (D - 1)];
         }
@@ -605,6 +626,12 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
         std::vector<Ef> r(randomness.begin(), randomness.begin() + air.num_randomness);
         pt.publics = st.public_values.data(); pt.challenges = r.data(); pt.aux_values = auxv[j].data();
         pt.is_first = van * ef_inv(zl - Fp::raw(1)); pt.is_last = van * ef_inv(zl - ohi); pt.is_transition = zl - ohi;
+        std::vector<Ef> per;
+        if (air.n_periodic) {   // verifier/periodic.rs:55-71: z^(N_max / period)
+            Ef y = ef_exp_pow2(z, log_max_n - air.log_max_period);
+            for (auto& cf : air.periodic_coeffs()) { Ef a; for (size_t q = cf.size(); q-- > 0;) a = a * y + cf[q]; per.push_back(a); }
+            pt.periodic = per.data();
+        }
         Ef folded = air_eval_folded(air.program, pt, alpha, scratch);
         accumulated = accumulated * beta + folded;
     }

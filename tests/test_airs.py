@@ -82,3 +82,52 @@ def fib_product_workload(log_heights, with_dummy=False, lqd=1):
         return 0
 
     return wl, build_aux
+
+
+def periodic_workload(log_h: int, lqd: int = 3):
+    """Two periodic columns (periods 4 and 2): col0 = per0 * col1, col2 = col1 + per1."""
+    n = 1 << log_h
+    per = np.array([[1, 5], [2, 7], [3, 5], [4, 7]], dtype=np.uint64)     # periodic_columns_matrix(): max period 4
+    t = W.synthetic_trace(7, log_h, 3)
+    for r in range(n):
+        c1 = int(t[r, 1])
+        t[r, 0] = int(per[r % 4, 0]) * c1 % P
+        t[r, 2] = (c1 + int(per[r % 4, 1])) % P
+    b = AP.ProgramBuilder()
+    b.assert_zero(b.main(0, 0) - b.periodic(0) * b.main(0, 1))
+    b.assert_zero(b.main(0, 2) - b.main(0, 1) - b.periodic(1))
+    wl = W.Workload([log_h], widths=[3], aux_widths=[0], programs=[b.serialize()], traces=[t],
+                    log_quotient_degrees=[lqd], periodic=[per], num_aux_values=[0])
+    return wl
+
+
+def big_program_workload(log_h: int, n_terms: int = 300, seed: int = 3, lqd: int = 3):
+    """A program with thousands of nodes whose constraints vanish identically (E - E' with E, E' built
+    separately), exercising the liveness-based slot allocation of the constraint interpreter."""
+    import random
+    rng = random.Random(seed)
+    width = 12
+    b = AP.ProgramBuilder()
+
+    def expr(rs):
+        acc = b.const(rs.randrange(P))
+        for _ in range(n_terms):
+            x = b.main(rs.randrange(2), rs.randrange(width))
+            y = b.main(0, rs.randrange(width))
+            k = rs.randrange(3)
+            term = x * y if k == 0 else (x + y if k == 1 else x - b.const(rs.randrange(P)))
+            acc = acc + term if rs.randrange(2) else acc - term
+        return acc
+
+    for c in range(4):
+        s1 = random.Random(seed * 100 + c)
+        s2 = random.Random(seed * 100 + c)
+        e1 = expr(s1)
+        e2 = expr(s2)
+        b.assert_zero(e1 - e2)
+        if c == 2:
+            b.assert_zero_ext((e1 - e2) * b.challenge(0))
+    t = W.synthetic_trace(9, log_h, width)
+    wl = W.Workload([log_h], widths=[width], aux_widths=[1], programs=[b.serialize()], traces=[t],
+                    log_quotient_degrees=[lqd], num_aux_values=[1])
+    return wl

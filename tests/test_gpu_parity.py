@@ -144,6 +144,17 @@ def test_prove_with_aux_selectors_transitions(sess_fast):
     _compare_proofs(sess_fast, W.fast_pcs_params(), wl, builder)
 
 
+def test_prove_periodic_columns(sess_fast):
+    import test_airs
+    _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=3))
+
+
+def test_prove_big_constraint_program(sess_fast):
+    # ~2.4k nodes per constraint pair: far above the old 256-node interpreter limit
+    import test_airs
+    _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.big_program_workload(5, n_terms=300))
+
+
 def test_config2_synthetic_2_16_roots(sess):
     """BASELINE config 2: synthetic 2^16 x (51, 22, 16): NTT + Poseidon2 commit, bit-exact root."""
     wl = W.Workload([16, 16, 16])

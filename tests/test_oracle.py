@@ -178,6 +178,17 @@ def test_prove_verify_with_aux_and_transitions():
     _roundtrip(W.fast_pcs_params(), wl, builder)
 
 
+def test_prove_verify_periodic_columns():
+    import test_airs
+    _roundtrip(W.fast_pcs_params(), test_airs.periodic_workload(5, lqd=1))
+    _roundtrip(W.fast_pcs_params(), test_airs.periodic_workload(4, lqd=3))
+
+
+def test_prove_verify_big_program():
+    import test_airs
+    _roundtrip(W.fast_pcs_params(), test_airs.big_program_workload(4, n_terms=60))
+
+
 def test_violated_constraint_is_rejected():
     wl = W.Workload([5], widths=(9,), aux_widths=(1,))
     wl.traces[0][3, 0] = 1   # column 0 must vanish for the product constraint
