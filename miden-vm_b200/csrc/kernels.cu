@@ -23,22 +23,28 @@ void upload_constants() {
 // =============================================================================================
 // transpose: row-major (n_rows x width) -> column-major
 // =============================================================================================
-__global__ void k_transpose(const u64* __restrict__ src, u64* __restrict__ dst, u32 n_rows, u32 width) {
+__global__ void k_transpose(const u64* __restrict__ src, u64* __restrict__ dst, u32 n_rows, u32 width, u32* bad) {
     __shared__ u64 tile[32][33];
     u32 r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    bool any_bad = false;
     for (u32 i = threadIdx.y; i < 32; i += 8) {
         u32 r = r0 + i, c = c0 + threadIdx.x;
-        if (r < n_rows && c < width) tile[i][threadIdx.x] = src[(size_t)r * width + c];
+        if (r < n_rows && c < width) {
+            u64 v = src[(size_t)r * width + c];
+            any_bad |= (v >= gl::P);        // Felt values are canonical by construction in the reference
+            tile[i][threadIdx.x] = v;
+        }
     }
+    if (any_bad && bad) atomicOr(bad, 1u);
     __syncthreads();
     for (u32 i = threadIdx.y; i < 32; i += 8) {
         u32 c = c0 + i, r = r0 + threadIdx.x;
         if (r < n_rows && c < width) dst[(size_t)c * n_rows + r] = tile[threadIdx.x][i];
     }
 }
-void launch_transpose_rm_to_cm(const u64* src, u64* dst, u32 n_rows, u32 width, cudaStream_t st) {
+void launch_transpose_rm_to_cm(const u64* src, u64* dst, u32 n_rows, u32 width, u32* d_bad_flag, cudaStream_t st) {
     dim3 grid((n_rows + 31) / 32, (width + 31) / 32), block(32, 8);
-    k_transpose<<<grid, block, 0, st>>>(src, dst, n_rows, width);
+    k_transpose<<<grid, block, 0, st>>>(src, dst, n_rows, width, d_bad_flag);
     COUNT_LAUNCH();
 }
 

@@ -39,7 +39,8 @@ struct PremulTables {
     const u64* tab_b;   // n_bases x N1
 };
 
-void launch_transpose_rm_to_cm(const u64* src_rm, u64* dst_cm, u32 n_rows, u32 width, cudaStream_t st);
+// d_bad_flag (optional): set to 1 if any value is not a canonical field element (>= p)
+void launch_transpose_rm_to_cm(const u64* src_rm, u64* dst_cm, u32 n_rows, u32 width, u32* d_bad_flag, cudaStream_t st);
 
 // In-place inverse NTT of `n_cols` columns (stride col_stride): natural evaluations over H ->
 // coefficients (unscaled by 1/N; the forward premul tables carry it), stored bit-reversed.

@@ -125,7 +125,8 @@ struct mdn_session {
     std::vector<E2> randomness;
     Committed main_c, aux_c, quot_c;
     std::vector<std::vector<u64>> aux_values_p;   // proof order, EF pairs
-    DevBuf d_publics, d_randomness, d_aux_values;
+    DevBuf d_publics, d_randomness, d_aux_values, d_flag;
+    void check_input_flag(const char* what);
     std::vector<size_t> aux_values_off;           // proof order offsets (in u64) into d_aux_values
     // outputs
     std::vector<uint8_t> out_heights;
@@ -265,19 +266,26 @@ void mdn_session::reset_proof() {
     tr = Transcript();
 }
 
+void mdn_session::check_input_flag(const char* what) {
+    u32 flag = 0;
+    CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    if (flag) { CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); fail(MDN_ERR_INVALID_ARG, "%s contains a non-canonical field element (>= p)", what); }
+}
+
 // row-major (host or device) -> column-major device
 void mdn_session::upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm) {
     size_t N = (size_t)1 << m.log_height;
     if (m.width == 0) return;
     if (on_device) {
         ProfScope ps(prof, PC_TRANSPOSE);
-        mk::launch_transpose_rm_to_cm(m.values, dst_cm, (u32)N, m.width, stream);
+        mk::launch_transpose_rm_to_cm(m.values, dst_cm, (u32)N, m.width, (u32*)d_flag.p, stream);
         return;
     }
     DevBuf staging; staging.alloc(N * m.width, stream);
     CUDA_OK(cudaMemcpyAsync(staging.p, m.values, N * m.width * sizeof(u64), cudaMemcpyHostToDevice, stream));
     ProfScope ps(prof, PC_TRANSPOSE);
-    mk::launch_transpose_rm_to_cm(staging.p, dst_cm, (u32)N, m.width, stream);
+    mk::launch_transpose_rm_to_cm(staging.p, dst_cm, (u32)N, m.width, (u32*)d_flag.p, stream);
 }
 
 // a1 + a2 + a3: coset LDE of every matrix of `c` (coefficients already in c.coef as natural
@@ -404,6 +412,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     memset(&timings, 0, sizeof timings);
     mk::reset_launch_count();
     prof.st = stream; prof.reset(); leaf_bytes = ntt_bytes = 0; perms = 0;
+    if (!d_flag.p) { d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
     if (!st || !traces || !chal) fail(MDN_ERR_INVALID_ARG, "null argument");
     if (st->n_airs == 0 || st->n_airs > 256) fail(MDN_ERR_INVALID_ARG, "AIR count must be in 1..=256");
     if (params.log_folding_arity != 2) fail(MDN_ERR_UNSUPPORTED, "only FRI folding arity 4 is implemented");
@@ -578,6 +587,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         co += N * w; lo += (N << lb) * w;
     }
     CUDA_OK(cudaEventRecord(ev[1], stream));
+    check_input_flag("a main trace");
     lde_and_commit(main_c, &timings.lde_main, &timings.hash_main);
     CUDA_OK(cudaEventRecord(ev[2], stream));
     tr.send_commitment(main_c.root);
@@ -627,6 +637,7 @@ void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values
         }
         co += N * w; lo += (N << lb) * w;
     }
+    if (!zero_aux) check_input_flag("an aux trace");
     lde_and_commit(aux_c, nullptr, nullptr);
     tr.send_commitment(aux_c.root);
     memcpy(dbg_roots[1], aux_c.root, 32);
@@ -1028,7 +1039,7 @@ void mdn_session_destroy(mdn_session* s) {
     cudaSetDevice(s->device);
     // every stream-ordered allocation must be returned before the stream goes away
     s->reset_proof();
-    s->d_publics.release(); s->d_randomness.release(); s->d_aux_values.release();
+    s->d_publics.release(); s->d_randomness.release(); s->d_aux_values.release(); s->d_flag.release();
     s->ntt_plans.clear(); s->premul_plans.clear();
     cudaStreamSynchronize(s->stream);
     for (auto& evn : s->ev) cudaEventDestroy(evn);
@@ -1097,7 +1108,6 @@ int mdn_prove(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces,
             r.push_back(0);
             if (build_aux(aux_ctx, i, &traces[i], r.data(), aux_bufs[i].data(), val_bufs[i].data()) != 0)
                 fail(MDN_ERR_AUX_BUILDER, "aux builder failed for instance %u", i);
-            for (u64 v : aux_bufs[i]) if (v >= gl::P) fail(MDN_ERR_INVALID_ARG, "non-canonical aux trace value");
             aux_mats[i] = mdn_matrix{aux_bufs[i].data(), traces[i].log_height, 2 * a.aux_width};
             val_ptrs[i] = val_bufs[i].data();
         }
@@ -1124,12 +1134,13 @@ int mdn_coset_lde_batch(mdn_session* s, const mdn_matrix* mat, uint32_t added_bi
     CUDA_OK(cudaSetDevice(s->device));
     if (added_bits != s->params.log_blowup) fail(MDN_ERR_UNSUPPORTED, "added_bits must equal the session's log_blowup");
     if (shift != gl::lde_shift(mat->log_height + added_bits)) fail(MDN_ERR_UNSUPPORTED, "only the canonical LDE shift 7^(2^(32-log_lde)) is supported");
-    for (size_t i = 0; i < ((size_t)mat->width << mat->log_height); i++) if (mat->values[i] >= gl::P) fail(MDN_ERR_INVALID_ARG, "non-canonical input");
+    if (!s->d_flag.p) { s->d_flag.alloc(1, s->stream); CUDA_OK(cudaMemsetAsync(s->d_flag.p, 0, 8, s->stream)); }
     Committed c;
     size_t N = (size_t)1 << mat->log_height, L = N << added_bits;
     c.coef_buf.alloc(N * mat->width, s->stream); c.lde_buf.alloc(L * mat->width, s->stream);
     c.mats.push_back(CommittedMat{c.lde_buf.p, c.coef_buf.p, mat->log_height, mat->width});
     s->upload_matrix(*mat, false, c.coef_buf.p);
+    s->check_input_flag("the matrix");
     s->lde_and_commit(c, nullptr, nullptr);
     DevBuf rm; rm.alloc(L * mat->width, s->stream);
     mk::launch_export_lde_bitrev_rm(c.lde_buf.p, mat->log_height, added_bits, mat->width, rm.p, s->stream);
@@ -1145,6 +1156,7 @@ int mdn_lmcs_commit(mdn_session* s, const mdn_matrix* mats, uint32_t n_mats, uin
     API_TRY(s)
     CUDA_OK(cudaSetDevice(s->device));
     u32 lb = s->params.log_blowup;
+    if (!s->d_flag.p) { s->d_flag.alloc(1, s->stream); CUDA_OK(cudaMemsetAsync(s->d_flag.p, 0, 8, s->stream)); }
     Committed c;
     size_t ct = 0, lt = 0;
     for (u32 i = 0; i < n_mats; i++) {
@@ -1159,6 +1171,7 @@ int mdn_lmcs_commit(mdn_session* s, const mdn_matrix* mats, uint32_t n_mats, uin
         s->upload_matrix(mats[i], false, c.coef_buf.p + co);
         co += N * mats[i].width; lo += (N << lb) * mats[i].width;
     }
+    s->check_input_flag("a matrix");
     s->lde_and_commit(c, nullptr, nullptr);
     memcpy(root, c.root, 32);
     API_CATCH(s)

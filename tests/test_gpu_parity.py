@@ -186,6 +186,41 @@ def test_full_size_2_20_verifies():
     s.close()
 
 
+def test_large_height_2_21_commit_root(lib, sess, oracle):
+    """Heights above 2^20 (n1 = 10, n2 = 11 NTT split; BASELINE config 5 is 2^22): LMCS root of a narrow
+    2^21-row matrix against the oracle."""
+    lh, w = 21, 3
+    m = rand_felts((1 << lh, w), 77)
+    out = np.zeros(((1 << lh) << 3, w), dtype=np.uint64)
+    om = ob.Matrix(ob.ptr(m.reshape(-1)), lh, w)
+    oracle.orc_coset_lde_batch(C.byref(om), 3, oracle.orc_lde_shift(lh + 3), ob.ptr(out.reshape(-1)))
+    bits = lh + 3
+    idx = np.arange(1 << bits, dtype=np.uint64)
+    rev = np.zeros_like(idx)
+    for b in range(bits):
+        rev |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(bits - 1 - b)
+    nat = np.ascontiguousarray(out[rev.astype(np.int64)])
+    omat = (ob.Matrix * 1)(ob.Matrix(ob.ptr(nat.reshape(-1)), bits, w))
+    exp = np.zeros(4, dtype=np.uint64)
+    oracle.orc_lmcs_commit(omat, 1, ob.ptr(exp), None)
+    pm = (B.Matrix * 1)(B.Matrix(B.ptr(m.reshape(-1)), lh, w))
+    got = np.zeros(4, dtype=np.uint64)
+    assert lib.mdn_lmcs_commit(sess.handle, pm, 1, B.ptr(got)) == 0, lib.mdn_last_error(sess.handle)
+    assert np.array_equal(got, exp)
+
+
+def test_non_canonical_input_rejected(lib, sess):
+    wl = W.Workload([5], widths=(9,), aux_widths=(1,))
+    wl.traces[0][7, 3] = np.uint64(P)          # not a canonical Felt
+    ch = W.initial_challenger(W.miden_pcs_params(), prod_observe)
+    with pytest.raises(B.ProverError) as e:
+        sess.prove(wl.statement, wl.matrices, ch)
+    assert "non-canonical" in str(e.value)
+    # the session stays usable afterwards
+    wl = W.Workload([5], widths=(9,), aux_widths=(1,))
+    sess.prove(wl.statement, wl.matrices, ch)
+
+
 def test_error_paths(lib, sess):
     wl = W.Workload([5], widths=(9,), aux_widths=(1,))
     wl._airs[0].width = 10   # trace width mismatch -> InstanceError
