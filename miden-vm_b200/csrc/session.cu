@@ -121,6 +121,7 @@ struct mdn_session {
     std::vector<u32> order;                 // proof position -> instance
     std::vector<u64> publics;
     u32 log_max_n = 0;
+    u32 log_qd = 0;                         // max log_quotient_degree over the AIRs (number of quotient chunks)
     Transcript tr;
     std::vector<E2> randomness;
     Committed main_c, aux_c, quot_c;
@@ -143,7 +144,7 @@ struct mdn_session {
 
     NttPlan& ntt(u32 n);
     PremulPlan& premul_trace(u32 n);
-    PremulPlan& premul_quotient(u32 n);
+    PremulPlan& premul_quotient(u32 n, u32 log_d);
     void build_tree(Committed& c, bool aligned_unused);
     void lde_and_commit(Committed& c, float* t_lde, float* t_hash);
     void upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm);
@@ -241,16 +242,17 @@ PremulPlan& mdn_session::premul_trace(u32 n) {
     premul_plans[key] = std::move(plan);
     return ref;
 }
-// bases w_J^(-t) * w_L^(t'), id = t*B + t'  (quotient.rs:186-209: chunk t scaled by w_J^(-kt), then a
+// bases w_J^(-t) * w_L^(t'), id = t*B + t' for chunk t < D and LDE coset t' < B, with J the quotient
+// domain of order N*D (w_J = w_L^(B/D))  (quotient.rs:186-209: chunk t scaled by w_J^(-kt), then a
 // plain DFT over K evaluates on g*K because the iDFT over H left g^k baked into the coefficients)
-PremulPlan& mdn_session::premul_quotient(u32 n) {
-    auto key = std::make_pair(n, 1u);
+PremulPlan& mdn_session::premul_quotient(u32 n, u32 log_d) {
+    auto key = std::make_pair(n, 1u + log_d);
     auto it = premul_plans.find(key);
     if (it != premul_plans.end()) return *it->second;
-    u32 lb = params.log_blowup, B = 1u << lb;
-    u64 wl = gl::two_adic_generator(n + lb), wji = gl::inv(wl);   // D == B  =>  J == K
-    std::vector<u64> bases(B * B);
-    for (u32 t = 0; t < B; t++)
+    u32 lb = params.log_blowup, B = 1u << lb, D = 1u << log_d;
+    u64 wl = gl::two_adic_generator(n + lb), wji = gl::inv(gl::two_adic_generator(n + log_d));
+    std::vector<u64> bases(D * B);
+    for (u32 t = 0; t < D; t++)
         for (u32 t2 = 0; t2 < B; t2++) bases[t * B + t2] = gl::mul(gl::pow(wji, t), gl::pow(wl, t2));
     auto plan = make_premul(bases, n, stream);
     auto& ref = *plan;
@@ -409,6 +411,7 @@ u64 mdn_session::grind(u32 bits) {
 // ---------------------------------------------------------------------------------------------
 void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* chal, u32 flags) {
     reset_proof();
+    log_qd = 0;
     memset(&timings, 0, sizeof timings);
     mk::reset_launch_count();
     prof.st = stream; prof.reset(); leaf_bytes = ntt_bytes = 0; perms = 0;
@@ -428,8 +431,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         if (traces[i].width != a.width) fail(MDN_ERR_INVALID_ARG, "trace %u width %u does not match AIR width %u", i, traces[i].width, a.width);
         if (a.log_quotient_degree > lb)
             fail(MDN_ERR_DOMAIN, "log_quotient_degree %u > log_blowup %u", a.log_quotient_degree, lb);
-        if (a.log_quotient_degree != lb)
-            fail(MDN_ERR_UNSUPPORTED, "AIR %u: log_quotient_degree %u != log_blowup %u (upsampling path not implemented)", i, a.log_quotient_degree, lb);
+        log_qd = std::max(log_qd, a.log_quotient_degree);
         if (traces[i].log_height + lb > 32) fail(MDN_ERR_DOMAIN, "LDE log order %u exceeds two-adicity 32", traces[i].log_height + lb);
         if (a.width == 0) fail(MDN_ERR_INVALID_ARG, "AIR %u has zero width", i);
         log_heights[i] = traces[i].log_height;
@@ -693,36 +695,41 @@ void mdn_session::finish() {
         std::vector<u64> planes(2 * L);
         CUDA_OK(cudaMemcpyAsync(planes.data(), acc.p, 2 * L * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
-        dbg_quot_acc.assign(2 * L, 0);
-        for (size_t t = 0; t < B; t++)
+        // natural order on gJ_max (N*D points): index r*D + t  <- coset t*(B/D) of the planes
+        u32 Dq = 1u << log_qd, cs = B >> log_qd;
+        dbg_quot_acc.assign(2 * Nmax * Dq, 0);
+        for (size_t t = 0; t < Dq; t++)
             for (size_t r = 0; r < Nmax; r++) {
-                dbg_quot_acc[2 * (r * B + t)] = planes[t * Nmax + r];
-                dbg_quot_acc[2 * (r * B + t) + 1] = planes[L + t * Nmax + r];
+                dbg_quot_acc[2 * (r * Dq + t)] = planes[t * cs * Nmax + r];
+                dbg_quot_acc[2 * (r * Dq + t) + 1] = planes[L + t * cs * Nmax + r];
             }
     }
-    // 5. quotient commit (quotient.rs:143-217).  acc planes = 2*B columns of height N (column
-    // coord*B + t); the committed matrix has column 2t + coord.
+    // 5. quotient commit (quotient.rs:143-217).  The accumulator was evaluated on all B cosets of gK
+    //    (for a satisfied AIR that equals the reference's evaluate-on-gJ-then-upsample, quotient.rs:45-56,
+    //    because C/Z_H is then a polynomial of degree < N*D); chunk t < D is the LDE coset t*(B/D).
+    //    The committed matrix has column 2t + coord.
+    const u32 D = 1u << log_qd, cstep = B >> log_qd;
     {
         NttPlan& plan = ntt(log_max_n);
-        PremulPlan& pm = premul_quotient(log_max_n);
+        PremulPlan& pm = premul_quotient(log_max_n, log_qd);
         size_t rq = prof.begin(PC_NTT);
-        ntt_bytes += (double)(Nmax + L) * 2 * B * 8.0;
-        mk::launch_intt(acc.p, Nmax, 2 * B, plan.T, stream);
-        quot_c.lde_buf.alloc(L * 2 * B, stream);
+        ntt_bytes += (double)(Nmax + L) * 2 * D * 8.0;
+        for (u32 coord = 0; coord < 2; coord++) mk::launch_intt(acc.p + (size_t)coord * L, (size_t)cstep * Nmax, D, plan.T, stream);
+        quot_c.lde_buf.alloc(L * 2 * D, stream);
         quot_c.coef_buf = std::move(acc);
-        quot_c.mats.push_back(CommittedMat{quot_c.lde_buf.p, quot_c.coef_buf.p, log_max_n, 2 * B});
+        quot_c.mats.push_back(CommittedMat{quot_c.lde_buf.p, quot_c.coef_buf.p, log_max_n, 2 * D});
         std::vector<mk::FwdItem> items;
-        for (u32 t = 0; t < B; t++)
+        for (u32 t = 0; t < D; t++)
             for (u32 coord = 0; coord < 2; coord++)
                 for (u32 t2 = 0; t2 < B; t2++)
-                    items.push_back(mk::FwdItem{quot_c.coef_buf.p + (size_t)(coord * B + t) * Nmax,
+                    items.push_back(mk::FwdItem{quot_c.coef_buf.p + (size_t)coord * L + (size_t)t * cstep * Nmax,
                                                 quot_c.lde_buf.p + (size_t)(2 * t + coord) * L + (size_t)t2 * Nmax, t * B + t2, 0});
         DevBuf d_items; d_items.alloc(items.size() * sizeof(mk::FwdItem) / sizeof(u64), stream);
         CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(mk::FwdItem), cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
         // column-pair groups keep the working set near L2 size
         u32 per = 2 * B;   // items per chunk t
-        for (u32 t = 0; t < B; t++) mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)t * per, per, plan.T, pm.P, stream);
+        for (u32 t = 0; t < D; t++) mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)t * per, per, plan.T, pm.P, stream);
         prof.end(rq);
         build_tree(quot_c, true);
         tr.send_commitment(quot_c.root);
@@ -780,16 +787,16 @@ void mdn_session::finish() {
                     CUDA_OK(cudaMemcpyAsync(evals[g][m].v.data(), outv.p, (size_t)cm.width * 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
                     CUDA_OK(cudaStreamSynchronize(stream));
                 } else {
-                    // quotient chunk t: stored coefficients are a_k * (g*w_J^t)^k (columns t and B+t of
-                    // the coefficient buffer), so q_t(y) is their evaluation at y / (g * w_J^t).
-                    u64 wj_inv = gl::inv(gl::two_adic_generator(log_lde));
-                    for (u32 t = 0; t < B; t++) {
+                    // quotient chunk t: stored coefficients are a_k * (g*w_J^t)^k (planes coord, column t*(B/D)),
+                    // so q_t(y) is their evaluation at y / (g * w_J^t).
+                    u64 wj_inv = gl::inv(gl::two_adic_generator(log_max_n + log_qd));
+                    for (u32 t = 0; t < D; t++) {
                         u64 f = gl::mul(shift_inv, gl::pow(wj_inv, t));
                         std::pair<DevBuf, DevBuf> wv;
                         get_w(ln, gl::e2_mulf(z, f), gl::e2_mulf(z_next, f), wv);
                         DevBuf partial; partial.alloc((size_t)2 * n_chunks * 4, stream);
                         DevBuf outv; outv.alloc(8, stream);
-                        mk::launch_ood_dot(cm.coef + (size_t)t * Nm, (size_t)B * Nm, 2, ln, wv.first.p, wv.second.p, partial.p, n_chunks, stream);
+                        mk::launch_ood_dot(cm.coef + (size_t)t * cstep * Nm, (size_t)B * Nm, 2, ln, wv.first.p, wv.second.p, partial.p, n_chunks, stream);
                         mk::launch_ood_reduce(partial.p, 2, n_chunks, outv.p, stream);
                         u64 tmp[8];
                         CUDA_OK(cudaMemcpyAsync(tmp, outv.p, sizeof tmp, cudaMemcpyDeviceToHost, stream));

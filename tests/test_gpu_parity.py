@@ -144,6 +144,24 @@ def test_prove_with_aux_selectors_transitions(sess_fast):
     _compare_proofs(sess_fast, W.fast_pcs_params(), wl, builder)
 
 
+def test_prove_mixed_quotient_degrees(sess_fast):
+    # fib/product AIR with its native log_quotient_degree 1 next to a degree-9 AIR (log 3): the
+    # reference evaluates the first on gJ_j and upsamples (quotient.rs:45-56)
+    import test_airs
+    wl, builder = test_airs.fib_product_workload([6, 4], lqd=1)
+    _compare_proofs(sess_fast, W.fast_pcs_params(), wl, builder)
+    wl, builder = test_airs.fib_product_workload([4, 7], lqd=1)
+    _compare_proofs(sess_fast, W.fast_pcs_params(), wl, builder)
+
+
+def test_prove_low_max_quotient_degree(sess_fast):
+    # every AIR below the blowup: D_max = 2 < B = 8 quotient chunks
+    import test_airs
+    wl, builder = test_airs.fib_product_workload([5], lqd=1)
+    _compare_proofs(sess_fast, W.fast_pcs_params(), wl, builder)
+    _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=1))
+
+
 def test_prove_periodic_columns(sess_fast):
     import test_airs
     _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=3))
@@ -227,6 +245,6 @@ def test_error_paths(lib, sess):
     ch = W.initial_challenger(W.miden_pcs_params(), prod_observe)
     with pytest.raises(B.ProverError):
         sess.prove(wl.statement, wl.matrices, ch)
-    wl = W.Workload([5], widths=(9,), aux_widths=(1,), log_quotient_degrees=[4])
+    wl = W.Workload([5], widths=(9,), aux_widths=(1,), log_quotient_degrees=[4])   # > log_blowup: DomainError
     with pytest.raises(B.ProverError):
         sess.prove(wl.statement, wl.matrices, ch)
