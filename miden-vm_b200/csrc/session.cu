@@ -146,7 +146,10 @@ struct mdn_session {
     PremulPlan& premul_trace(u32 n);
     PremulPlan& premul_quotient(u32 n, u32 log_d);
     void build_tree(Committed& c, bool aligned_unused);
-    void lde_and_commit(Committed& c, float* t_lde, float* t_hash);
+    void lde_matrix(CommittedMat& m);
+    void lde_and_commit(Committed& c, float* t_lde, float* t_hash, bool lde_done = false);
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[8];
     void upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm);
     void prove_begin(const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* ch, u32 flags);
     void commit_aux(const mdn_matrix* aux, const u64* const* aux_values, bool zero_aux);
@@ -294,33 +297,35 @@ void mdn_session::upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm
 // evaluations over H), leaf hashing and tree compression.
 //   reference: commit_traces (prover/commit.rs:142-180) -> coset_lde_batch (:173) +
 //   build_aligned_tree (:178; lmcs/lifted_tree.rs:202-284)
-void mdn_session::lde_and_commit(Committed& c, float* t_lde, float* t_hash) {
+void mdn_session::lde_matrix(CommittedMat& m) {
+    if (!m.width) return;
     u32 lb = params.log_blowup, B = 1u << lb;
+    size_t N = (size_t)1 << m.log_n, L = N << lb;
+    NttPlan& plan = ntt(m.log_n);
+    PremulPlan& pm = premul_trace(m.log_n);
+    ProfScope ps(prof, PC_NTT);
+    ntt_bytes += (double)(N + L) * m.width * 8.0;   // read the trace column once, write the LDE once
+    mk::launch_intt(m.coef, N, m.width, plan.T, stream);
+    // column groups sized so a group's LDE (the fwd passes' working set) stays L2-resident
+    size_t col_bytes = L * sizeof(u64);
+    u32 group = (u32)std::max<size_t>(1, (48u << 20) / col_bytes);
+    std::vector<mk::FwdItem> items;
+    for (u32 cc = 0; cc < m.width; cc++)
+        for (u32 t = 0; t < B; t++)
+            items.push_back(mk::FwdItem{m.coef + (size_t)cc * N, m.lde + (size_t)cc * L + (size_t)t * N, t, 0});
+    DevBuf d_items;
+    d_items.alloc(items.size() * sizeof(mk::FwdItem) / sizeof(u64), stream);
+    CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(mk::FwdItem), cudaMemcpyHostToDevice, stream));
+    for (u32 c0 = 0; c0 < m.width; c0 += group) {
+        u32 cn = std::min(group, m.width - c0);
+        mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)c0 * B, cn * B, plan.T, pm.P, stream);
+    }
+}
+
+void mdn_session::lde_and_commit(Committed& c, float* t_lde, float* t_hash, bool lde_done) {
     cudaEvent_t e0 = ev[12], e1 = ev[13], e2 = ev[14];
     CUDA_OK(cudaEventRecord(e0, stream));
-    for (auto& m : c.mats) {
-        if (!m.width) continue;
-        size_t N = (size_t)1 << m.log_n, L = N << lb;
-        NttPlan& plan = ntt(m.log_n);
-        PremulPlan& pm = premul_trace(m.log_n);
-        ProfScope ps(prof, PC_NTT);
-        ntt_bytes += (double)(N + L) * m.width * 8.0;   // read the trace column once, write the LDE once
-        mk::launch_intt(m.coef, N, m.width, plan.T, stream);
-        // column groups sized so a group's LDE (the fwd passes' working set) stays L2-resident
-        size_t col_bytes = L * sizeof(u64);
-        u32 group = (u32)std::max<size_t>(1, (48u << 20) / col_bytes);
-        std::vector<mk::FwdItem> items;
-        for (u32 cc = 0; cc < m.width; cc++)
-            for (u32 t = 0; t < B; t++)
-                items.push_back(mk::FwdItem{m.coef + (size_t)cc * N, m.lde + (size_t)cc * L + (size_t)t * N, t, 0});
-        DevBuf d_items;
-        d_items.alloc(items.size() * sizeof(mk::FwdItem) / sizeof(u64), stream);
-        CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(mk::FwdItem), cudaMemcpyHostToDevice, stream));
-        for (u32 c0 = 0; c0 < m.width; c0 += group) {
-            u32 cn = std::min(group, m.width - c0);
-            mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)c0 * B, cn * B, plan.T, pm.P, stream);
-        }
-    }
+    if (!lde_done) for (auto& m : c.mats) lde_matrix(m);
     CUDA_OK(cudaEventRecord(e1, stream));
     build_tree(c, true);
     CUDA_OK(cudaEventRecord(e2, stream));
@@ -585,12 +590,40 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         size_t N = (size_t)1 << log_heights[inst];
         u32 w = airs[inst].desc.width;
         main_c.mats.push_back(CommittedMat{main_c.lde_buf.p + lo, main_c.coef_buf.p + co, log_heights[inst], w});
-        upload_matrix(traces[inst], on_device, main_c.coef_buf.p + co);
         co += N * w; lo += (N << lb) * w;
     }
-    CUDA_OK(cudaEventRecord(ev[1], stream));
+    // H2D copies run on a second stream, so the LDE of matrix j overlaps the copy of matrix j+1
+    // (copies of pinned buffers are asynchronous; pageable buffers degrade to a staged copy).
+    std::vector<DevBuf> staging(k);
+    if (!on_device) {
+        for (u32 j = 0; j < k; j++) staging[j].alloc(((size_t)1 << main_c.mats[j].log_n) * main_c.mats[j].width, stream);
+        CUDA_OK(cudaEventRecord(copy_ev[7], stream));
+        CUDA_OK(cudaStreamWaitEvent(copy_stream, copy_ev[7], 0));
+        for (u32 j = 0; j < k; j++) {
+            const mdn_matrix& m = traces[order[j]];
+            CUDA_OK(cudaMemcpyAsync(staging[j].p, m.values, staging[j].n * sizeof(u64), cudaMemcpyHostToDevice, copy_stream));
+            CUDA_OK(cudaEventRecord(copy_ev[j % 7], copy_stream));
+            if (j % 7 == 6 || j + 1 == k) {
+                // at most 7 copies in flight per batch of events
+                for (u32 q = j - (j % 7); q <= j; q++) {
+                    CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[q % 7], 0));
+                    {
+                        ProfScope ps(prof, PC_TRANSPOSE);
+                        mk::launch_transpose_rm_to_cm(staging[q].p, main_c.mats[q].coef, 1u << main_c.mats[q].log_n, main_c.mats[q].width, (u32*)d_flag.p, stream);
+                    }
+                    if (q + 1 == k) CUDA_OK(cudaEventRecord(ev[1], stream));
+                    lde_matrix(main_c.mats[q]);
+                }
+            }
+        }
+    } else {
+        for (u32 j = 0; j < k; j++) upload_matrix(traces[order[j]], true, main_c.mats[j].coef);
+        CUDA_OK(cudaEventRecord(ev[1], stream));
+        for (u32 j = 0; j < k; j++) lde_matrix(main_c.mats[j]);
+    }
+    staging.clear();
     check_input_flag("a main trace");
-    lde_and_commit(main_c, &timings.lde_main, &timings.hash_main);
+    lde_and_commit(main_c, &timings.lde_main, &timings.hash_main, true);
     CUDA_OK(cudaEventRecord(ev[2], stream));
     tr.send_commitment(main_c.root);
     memcpy(dbg_roots[0], main_c.root, 32);
@@ -1029,6 +1062,8 @@ int mdn_session_create(const mdn_pcs_params* params, int cuda_device, mdn_sessio
     try {
         CUDA_OK(cudaSetDevice(cuda_device));
         CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (auto& evn : s->copy_ev) CUDA_OK(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
         for (auto& evn : s->ev) CUDA_OK(cudaEventCreate(&evn));
         cudaMemPool_t pool;
         CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, cuda_device));
@@ -1050,6 +1085,8 @@ void mdn_session_destroy(mdn_session* s) {
     s->ntt_plans.clear(); s->premul_plans.clear();
     cudaStreamSynchronize(s->stream);
     for (auto& evn : s->ev) cudaEventDestroy(evn);
+    for (auto& evn : s->copy_ev) cudaEventDestroy(evn);
+    cudaStreamDestroy(s->copy_stream);
     cudaStreamDestroy(s->stream);
     delete s;
 }

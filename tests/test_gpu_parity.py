@@ -162,6 +162,21 @@ def test_prove_low_max_quotient_degree(sess_fast):
     _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=1))
 
 
+@pytest.mark.parametrize("log_blowup", [1, 2, 4])
+def test_prove_other_blowups(log_blowup):
+    # PcsParams are generic (pcs/params.rs:53-99); the Miden value is 3
+    import test_airs
+    params = B.PcsParams(log_blowup, 2, 1, 1, 2, 6, 3)
+    s = B.Session(params, 0)
+    B.lib().mdn_set_debug(s.handle, 1)
+    try:
+        wl, builder = test_airs.fib_product_workload([6], lqd=1)
+        _compare_proofs(s, params, wl, builder)
+        _compare_proofs(s, params, test_airs.periodic_workload(5, lqd=1))
+    finally:
+        s.close()
+
+
 def test_prove_periodic_columns(sess_fast):
     import test_airs
     _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=3))

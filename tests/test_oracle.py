@@ -189,6 +189,14 @@ def test_prove_verify_big_program():
     _roundtrip(W.fast_pcs_params(), test_airs.big_program_workload(4, n_terms=60))
 
 
+@pytest.mark.parametrize("log_blowup", [1, 2, 4])
+def test_prove_verify_other_blowups(log_blowup):
+    import test_airs
+    params = H.B.PcsParams(log_blowup, 2, 1, 1, 2, 6, 3)
+    wl, builder = test_airs.fib_product_workload([6], lqd=1)
+    _roundtrip(params, wl, builder)
+
+
 def test_violated_constraint_is_rejected():
     wl = W.Workload([5], widths=(9,), aux_widths=(1,))
     wl.traces[0][3, 0] = 1   # column 0 must vanish for the product constraint
