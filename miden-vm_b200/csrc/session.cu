@@ -791,12 +791,21 @@ void mdn_session::finish() {
     std::vector<std::vector<MatEval>> evals(3);
     {
         ProfScope ps_ood(prof, PC_OOD);
-        std::map<u32, std::pair<DevBuf, DevBuf>> weights;   // per log height: (w0, w1)
-        auto get_w = [&](u32 ln, E2 y0, E2 y1, std::pair<DevBuf, DevBuf>& slot) {
-            slot.first.alloc((size_t)2 << ln, stream); slot.second.alloc((size_t)2 << ln, stream);
-            mk::launch_pow_bitrev(y0, ln, slot.first.p, stream);
-            mk::launch_pow_bitrev(y1, ln, slot.second.p, stream);
+        // all dot products are queued first and fetched with ONE device->host copy
+        size_t total_cols = 0;
+        for (int g = 0; g < 3; g++) for (auto& cm : groups[g]->mats) total_cols += cm.width;
+        DevBuf d_out; d_out.alloc(std::max<size_t>(1, total_cols * 4), stream);
+        std::vector<DevBuf> keep;                              // weight vectors / partial sums stay alive until the copy
+        std::map<u32, std::pair<u64*, u64*>> weights;          // per log height: (w0, w1)
+        auto make_w = [&](u32 ln, E2 y0, E2 y1) {
+            keep.emplace_back(); keep.back().alloc((size_t)2 << ln, stream); u64* a = keep.back().p;
+            keep.emplace_back(); keep.back().alloc((size_t)2 << ln, stream); u64* b = keep.back().p;
+            mk::launch_pow_bitrev(y0, ln, a, stream);
+            mk::launch_pow_bitrev(y1, ln, b, stream);
+            return std::make_pair(a, b);
         };
+        size_t col_off = 0;
+        std::vector<std::pair<size_t, u64>> scale;             // (first u64 index, 1/N) per matrix
         for (int g = 0; g < 3; g++) {
             evals[g].resize(groups[g]->mats.size());
             for (size_t m = 0; m < groups[g]->mats.size(); m++) {
@@ -806,41 +815,39 @@ void mdn_session::finish() {
                 u32 ln = cm.log_n, lr = log_max_n - ln;
                 size_t Nm = (size_t)1 << ln;
                 u32 n_chunks = (u32)std::max<size_t>(1, std::min<size_t>(Nm / 1024, 1024));
-                u64 n_inv = gl::inv((u64)Nm);   // launch_intt leaves coefficients scaled by N
                 if (g < 2) {
                     auto it = weights.find(ln);
-                    if (it == weights.end()) {
-                        it = weights.emplace(ln, std::pair<DevBuf, DevBuf>()).first;
-                        get_w(ln, gl::e2_exp_pow2(z, lr), gl::e2_exp_pow2(z_next, lr), it->second);
-                    }
-                    DevBuf partial; partial.alloc((size_t)cm.width * n_chunks * 4, stream);
-                    DevBuf outv; outv.alloc((size_t)cm.width * 4, stream);
-                    mk::launch_ood_dot(cm.coef, Nm, cm.width, ln, it->second.first.p, it->second.second.p, partial.p, n_chunks, stream);
-                    mk::launch_ood_reduce(partial.p, cm.width, n_chunks, outv.p, stream);
-                    CUDA_OK(cudaMemcpyAsync(evals[g][m].v.data(), outv.p, (size_t)cm.width * 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
-                    CUDA_OK(cudaStreamSynchronize(stream));
+                    if (it == weights.end()) it = weights.emplace(ln, make_w(ln, gl::e2_exp_pow2(z, lr), gl::e2_exp_pow2(z_next, lr))).first;
+                    keep.emplace_back(); keep.back().alloc((size_t)cm.width * n_chunks * 4, stream);
+                    mk::launch_ood_dot(cm.coef, Nm, cm.width, ln, it->second.first, it->second.second, keep.back().p, n_chunks, stream);
+                    mk::launch_ood_reduce(keep.back().p, cm.width, n_chunks, d_out.p + col_off * 4, stream);
                 } else {
                     // quotient chunk t: stored coefficients are a_k * (g*w_J^t)^k (planes coord, column t*(B/D)),
-                    // so q_t(y) is their evaluation at y / (g * w_J^t).
+                    // so q_t(y) is their evaluation at y / (g * w_J^t); outputs land at columns 2t, 2t+1.
                     u64 wj_inv = gl::inv(gl::two_adic_generator(log_max_n + log_qd));
                     for (u32 t = 0; t < D; t++) {
                         u64 f = gl::mul(shift_inv, gl::pow(wj_inv, t));
-                        std::pair<DevBuf, DevBuf> wv;
-                        get_w(ln, gl::e2_mulf(z, f), gl::e2_mulf(z_next, f), wv);
-                        DevBuf partial; partial.alloc((size_t)2 * n_chunks * 4, stream);
-                        DevBuf outv; outv.alloc(8, stream);
-                        mk::launch_ood_dot(cm.coef + (size_t)t * cstep * Nm, (size_t)B * Nm, 2, ln, wv.first.p, wv.second.p, partial.p, n_chunks, stream);
-                        mk::launch_ood_reduce(partial.p, 2, n_chunks, outv.p, stream);
-                        u64 tmp[8];
-                        CUDA_OK(cudaMemcpyAsync(tmp, outv.p, sizeof tmp, cudaMemcpyDeviceToHost, stream));
-                        CUDA_OK(cudaStreamSynchronize(stream));
-                        for (u32 coord = 0; coord < 2; coord++)
-                            for (int q = 0; q < 4; q++) evals[g][m].v[4 * (2 * t + coord) + q] = tmp[4 * coord + q];
+                        auto wv = make_w(ln, gl::e2_mulf(z, f), gl::e2_mulf(z_next, f));
+                        keep.emplace_back(); keep.back().alloc((size_t)2 * n_chunks * 4, stream);
+                        mk::launch_ood_dot(cm.coef + (size_t)t * cstep * Nm, (size_t)B * Nm, 2, ln, wv.first, wv.second, keep.back().p, n_chunks, stream);
+                        mk::launch_ood_reduce(keep.back().p, 2, n_chunks, d_out.p + (col_off + 2 * t) * 4, stream);
                     }
                 }
-                for (u64& x : evals[g][m].v) x = gl::mul(x, n_inv);
+                scale.emplace_back(col_off * 4, gl::inv((u64)Nm));   // launch_intt leaves coefficients scaled by N
+                col_off += cm.width;
             }
         }
+        std::vector<u64> host(total_cols * 4);
+        CUDA_OK(cudaMemcpyAsync(host.data(), d_out.p, host.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        size_t si = 0;
+        for (int g = 0; g < 3; g++)
+            for (size_t m = 0; m < groups[g]->mats.size(); m++) {
+                CommittedMat& cm = groups[g]->mats[m];
+                if (!cm.width) continue;
+                size_t off = scale[si].first; u64 n_inv = scale[si].second; si++;
+                for (size_t q = 0; q < (size_t)cm.width * 4; q++) evals[g][m].v[q] = gl::mul(host[off + q], n_inv);
+            }
     }
     // aligned flat evaluation lists per point (deep/prover.rs:150-154)
     std::vector<E2> flat[2];

@@ -263,3 +263,26 @@ def test_error_paths(lib, sess):
     wl = W.Workload([5], widths=(9,), aux_widths=(1,), log_quotient_degrees=[4])   # > log_blowup: DomainError
     with pytest.raises(B.ProverError):
         sess.prove(wl.statement, wl.matrices, ch)
+
+
+def test_gpu_matches_committed_golden_proofs():
+    """The CUDA path against the committed fixtures (tests/golden/oracle_proofs.json), without
+    running the oracle prover."""
+    import importlib.util, json, os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gdir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = json.load(open(os.path.join(gdir, "oracle_proofs.json")))
+    for name, params, wl, builder in mg.cases():
+        s = B.Session(params, 0)
+        try:
+            ch = W.initial_challenger(params, prod_observe)
+            cb = B.AUX_BUILDER(builder) if builder else None
+            heights, fields, comms = s.prove(wl.statement, wl.matrices, ch, cb)
+            g = gold[name]
+            assert [int(x) for x in s.info(0)] == g["main_root"], name
+            assert [int(x) for x in s.info(2)] == g["quotient_root"], name
+            assert [int(x) for x in s.info(7)] == g["query_indices"], name
+            assert mg.digest(heights, fields, comms) == g["proof_sha256"], name
+        finally:
+            s.close()

@@ -205,3 +205,22 @@ def test_violated_constraint_is_rejected():
     h, heights, fields, comms = H.oracle_prove(params, wl, ch)
     ob.lib().orc_prove_free(h)
     assert H.oracle_verify(params, wl, ch, heights, fields, comms)[0] != 0
+
+
+def test_oracle_reproduces_committed_golden_proofs():
+    """tests/golden/oracle_proofs.json (made by tests/golden/make_golden.py) pins the oracle itself."""
+    sys_path = os.path.join(GOLDEN)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = json.load(open(os.path.join(GOLDEN, "oracle_proofs.json")))
+    for name, params, wl, builder in mg.cases():
+        ch = W.initial_challenger(params, H.oracle_observe)
+        h, heights, fields, comms = H.oracle_prove(params, wl, ch, builder)
+        try:
+            g = gold[name]
+            assert [int(x) for x in H.oracle_info(h, 0)] == g["main_root"], name
+            assert [int(x) for x in H.oracle_info(h, 2)] == g["quotient_root"], name
+            assert mg.digest(heights, fields, comms) == g["proof_sha256"], name
+        finally:
+            ob.lib().orc_prove_free(h)
