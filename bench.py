@@ -135,8 +135,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log-height", type=int, default=20)
-    ap.add_argument("--ref-log-height", type=int, default=15)
-    ap.add_argument("--cpu-log-height", type=int, default=15)
+    ap.add_argument("--ref-log-height", type=int, default=16)
+    ap.add_argument("--cpu-log-height", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

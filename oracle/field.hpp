@@ -33,24 +33,31 @@ struct Fp {
     bool is_zero() const { return v == 0; }
 };
 
+// branch-free forms (the compiler emits cmov/sbb): the proving path is dominated by these
 inline Fp operator+(Fp a, Fp b) {
-    u64 s = a.v + b.v;
-    if (s < a.v || s >= P) s -= P;  // wraps correctly when the 64-bit add overflowed
-    return Fp::raw(s);
+    u64 s;
+    bool c = __builtin_add_overflow(a.v, b.v, &s);
+    u64 t = s - P;                       // valid when the add overflowed or s >= P
+    return Fp::raw((c | (s >= P)) ? t : s);
 }
-inline Fp operator-(Fp a, Fp b) { return Fp::raw(a.v >= b.v ? a.v - b.v : a.v + (P - b.v)); }
+inline Fp operator-(Fp a, Fp b) {
+    u64 d;
+    bool bw = __builtin_sub_overflow(a.v, b.v, &d);
+    return Fp::raw(bw ? d + P : d);
+}
 inline Fp operator-(Fp a) { return Fp::raw(a.v ? P - a.v : 0); }
 // 128-bit product reduced with 2^64 = 2^32 - 1 and 2^96 = -1 (mod p).
 inline u64 reduce128(u128 x) {
     u64 lo = (u64)x, hi = (u64)(x >> 64);
     u64 hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
-    u64 t = lo - hh;
-    if (lo < hh) t -= 0xFFFFFFFFULL;          // borrow: add p back (== subtract 2^32 - 1 mod 2^64)
+    u64 t;
+    bool bw = __builtin_sub_overflow(lo, hh, &t);
+    t -= bw ? 0xFFFFFFFFULL : 0;              // borrow: add p back (== subtract 2^32 - 1 mod 2^64)
     u64 m = hl * 0xFFFFFFFFULL;               // hl * (2^32 - 1) < 2^64
-    u64 r = t + m;
-    if (r < t) r += 0xFFFFFFFFULL;            // carry: 2^64 = 2^32 - 1
-    if (r >= P) r -= P;
-    return r;
+    u64 r;
+    bool cy = __builtin_add_overflow(t, m, &r);
+    r += cy ? 0xFFFFFFFFULL : 0;              // carry: 2^64 = 2^32 - 1
+    return r >= P ? r - P : r;
 }
 inline Fp operator*(Fp a, Fp b) { return Fp::raw(reduce128((u128)a.v * b.v)); }
 inline Fp& operator+=(Fp& a, Fp b) { a = a + b; return a; }

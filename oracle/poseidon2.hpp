@@ -21,11 +21,11 @@ inline Fp sbox7(Fp x) { Fp x2 = x * x; Fp x3 = x2 * x; Fp x4 = x2 * x2; return x
 inline void p2_external(State& s) {
     for (int c = 0; c < 3; c++) {
         Fp x0 = s[4 * c], x1 = s[4 * c + 1], x2 = s[4 * c + 2], x3 = s[4 * c + 3];
-        Fp two = Fp::raw(2), three = Fp::raw(3);
-        s[4 * c + 0] = two * x0 + three * x1 + x2 + x3;
-        s[4 * c + 1] = x0 + two * x1 + three * x2 + x3;
-        s[4 * c + 2] = x0 + x1 + two * x2 + three * x3;
-        s[4 * c + 3] = three * x0 + x1 + x2 + two * x3;
+        Fp sum = (x0 + x1) + (x2 + x3);
+        s[4 * c + 0] = sum + x0 + (x1 + x1);      // 2 x0 + 3 x1 + x2 + x3
+        s[4 * c + 1] = sum + x1 + (x2 + x2);
+        s[4 * c + 2] = sum + x2 + (x3 + x3);
+        s[4 * c + 3] = sum + x3 + (x0 + x0);
     }
     Fp col[4];
     for (int l = 0; l < 4; l++) col[l] = s[l] + s[4 + l] + s[8 + l];

@@ -18,8 +18,19 @@
 #include "air.hpp"
 #include <functional>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace orc {
+
+// optional phase timing (ORC_PROFILE=1)
+struct OrcTimer {
+    const char* name; std::chrono::steady_clock::time_point t0; bool on;
+    OrcTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("ORC_PROFILE") != nullptr) {}
+    ~OrcTimer() { if (on) fprintf(stderr, "[oracle] %-28s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
+#define ORC_TIMER(n) OrcTimer orc_timer_##__LINE__(n)
 
 struct PcsParams {   // crates/lifted-stark/src/pcs/params.rs:35-99; Miden values air/src/config.rs:55-67
     unsigned log_blowup = 3, log_folding_arity = 2, log_final_degree = 7;
@@ -102,9 +113,11 @@ inline size_t fri_final_poly_degree(const PcsParams& p, unsigned log_lde) {   //
 inline LmcsTree commit_traces(const std::vector<Matrix>& traces_proof_order, unsigned log_blowup) {
     std::vector<Matrix> ldes;
     for (const Matrix& t : traces_proof_order) {
+        ORC_TIMER("  coset lde");
         unsigned lh = log2_strict(t.height);
         ldes.push_back(coset_lde_bitrev(t, log_blowup, lde_shift(lh + log_blowup)));
     }
+    ORC_TIMER("  lmcs build");
     return LmcsTree::build(std::move(ldes), 8);   // build_aligned_tree: alignment = RATE
 }
 
@@ -402,7 +415,7 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
     // 1. main commit
     std::vector<Matrix> main_p;
     for (size_t j = 0; j < k; j++) main_p.push_back(traces[ord.proof_to_instance[j]]);
-    LmcsTree main_tree = commit_traces(main_p, lb);
+    LmcsTree main_tree = [&] { ORC_TIMER("commit main"); return commit_traces(main_p, lb); }();
     ch.send_commitment(main_tree.root());
     // 2. randomness, aux traces (instance order), aux commit
     size_t max_rand = 0;
@@ -418,7 +431,7 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
     }
     std::vector<Matrix> aux_p; std::vector<std::vector<Ef>> auxv_p;
     for (size_t j = 0; j < k; j++) { aux_p.push_back(aux_i[ord.proof_to_instance[j]]); auxv_p.push_back(auxv_i[ord.proof_to_instance[j]]); }
-    LmcsTree aux_tree = commit_traces(aux_p, lb);
+    LmcsTree aux_tree = [&] { ORC_TIMER("commit aux"); return commit_traces(aux_p, lb); }();
     ch.send_commitment(aux_tree.root());
     for (auto& vs : auxv_p) for (const Ef& v : vs) ch.send_ext(v);
     // 3. alpha, beta
@@ -426,6 +439,7 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
     // 4. constraints -> accumulator
     std::vector<Ef> acc;
     for (size_t j = 0; j < k; j++) {
+        ORC_TIMER("constraints");
         const AirDesc& air = st.airs[ord.proof_to_instance[j]];
         unsigned ln = lh[ord.proof_to_instance[j]];
         std::vector<Ef> r(randomness.begin(), randomness.begin() + air.num_randomness);
@@ -434,9 +448,9 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
         cyclic_extend_and_accumulate(acc, q, beta);
     }
     // 5. quotient commit
-    Matrix qlde = quotient_chunk_lde(acc, log_max_n, log_qd, lb);
+    Matrix qlde = [&] { ORC_TIMER("quotient lde"); return quotient_chunk_lde(acc, log_max_n, log_qd, lb); }();
     std::vector<Matrix> ql; ql.push_back(qlde);
-    LmcsTree q_tree = LmcsTree::build(std::move(ql), 8);
+    LmcsTree q_tree = [&] { ORC_TIMER("quotient tree"); return LmcsTree::build(std::move(ql), 8); }();
     ch.send_commitment(q_tree.root());
     // 6. OOD point (domain.rs:539-552)
     unsigned log_lde = log_max_n + lb;
@@ -451,6 +465,7 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
     }
     Ef z_next = z * two_adic_generator(log_max_n);
     // coefficient matrices for OOD evaluation
+    OrcTimer* tco = new OrcTimer("ood coefficients");
     std::vector<std::vector<Matrix>> coeffs(3);
     for (size_t j = 0; j < k; j++) { Matrix c = main_p[j]; idft_rows(c); coeffs[0].push_back(std::move(c)); }
     for (size_t j = 0; j < k; j++) { Matrix c = aux_p[j]; idft_rows(c); coeffs[1].push_back(std::move(c)); }
@@ -465,12 +480,13 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
         for (size_t r = 0; r < n; r++) { for (size_t col = 0; col < c.width; col++) cc.row(r)[col] = c.row(r)[col] * sp; sp = sp * gi; }
         coeffs[2].push_back(std::move(cc));
     }
+    delete tco;
     std::vector<const LmcsTree*> trees{&main_tree, &aux_tree, &q_tree};
     if (dbg) {
         dbg->main_root = main_tree.root(); dbg->aux_root = aux_tree.root(); dbg->quotient_root = q_tree.root();
         dbg->randomness = randomness; dbg->alpha = alpha; dbg->beta = beta; dbg->z = z; dbg->quotient_acc = acc;
     }
-    pcs_open(params, log_max_n, z, z_next, trees, coeffs, ch, dbg ? &dbg->open : nullptr);
+    { ORC_TIMER("pcs open"); pcs_open(params, log_max_n, z, z_next, trees, coeffs, ch, dbg ? &dbg->open : nullptr); }
     Proof pf;
     for (unsigned h : lh) pf.log_trace_heights.push_back((uint8_t)h);
     pf.fields = std::move(ch.fields);
