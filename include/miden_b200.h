@@ -142,6 +142,17 @@ int mdn_session_create(const mdn_pcs_params* params, int cuda_device, mdn_sessio
 void mdn_session_destroy(mdn_session* s);
 const char* mdn_last_error(const mdn_session* s);   /* s may be NULL: last create error */
 
+/* ---- one proof on several GPUs (hash sharding) -----------------------------------------------------
+ * One process per GPU, every rank calls mdn_prove with the SAME statement/traces/challenger.  Each rank
+ * computes the (cheap) LDEs itself and hashes only its contiguous range of Merkle leaves of every
+ * commitment (rank g: leaves [g*L/G, (g+1)*L/G)), builds that sub-tree, and the ranks exchange the G
+ * sub-roots with ONE all-gather per commitment; sibling digests needed by the query openings are
+ * exchanged the same way.  All ranks return the identical proof.  `fn` must gather `n_u64` words from
+ * every rank into `recv` (rank-major) -- e.g. torch.distributed.all_gather over NCCL/NVLink; the
+ * payloads are 32 bytes per rank per commitment.  world must be a power of two; world = 1 disables. */
+typedef int (*mdn_allgather_fn)(void* ctx, const uint64_t* send, uint64_t* recv, size_t n_u64);
+int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_allgather_fn fn, void* ctx);
+
 /* ---- the drop-in: ProverInstance::prove (prover/mod.rs:230-578) ------------------------------
  * `challenger` is the caller's pre-bound challenger (protocol params observed,
  * prover/src/lib.rs:329-330); the statement felts and instance shape are observed inside, as the

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libmiden_b200.so")
+LIB_PATH = os.environ.get("MDN_LIB_PATH") or os.path.join(HERE, "csrc", "libmiden_b200.so")   # override only for A/B kernel experiments
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
 
@@ -55,6 +55,7 @@ class Timings(C.Structure):
 
 
 AUX_BUILDER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Matrix), u64p, u64p, u64p)
+ALLGATHER = C.CFUNCTYPE(C.c_int, C.c_void_p, u64p, u64p, C.c_size_t)
 FLAG_DEVICE_TRACES = 1
 
 # Every symbol include/miden_b200.h declares (checked by tests/test_abi.py).
@@ -62,7 +63,7 @@ EXPORTS = [
     "mdn_session_create", "mdn_session_destroy", "mdn_last_error", "mdn_prove", "mdn_prove_begin",
     "mdn_prove_commit_aux", "mdn_prove_finish", "mdn_proof_serialize", "mdn_coset_lde_batch",
     "mdn_lmcs_commit", "mdn_poseidon2_permute", "mdn_get_info", "mdn_get_timings",
-    "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug",
+    "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug", "mdn_session_set_shard",
 ]
 
 _lib = None
@@ -97,6 +98,7 @@ def lib():
         L.mdn_get_info.restype = C.c_longlong
         L.mdn_get_info.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t]
         L.mdn_set_debug.argtypes = [C.c_void_p, C.c_int]
+        L.mdn_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHER, C.c_void_p]
         L.mdn_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.mdn_challenger_observe.argtypes = [C.POINTER(Challenger), u64p, C.c_size_t]
         L.mdn_challenger_sample.restype = C.c_uint64
@@ -141,6 +143,11 @@ class Session:
     @property
     def handle(self):
         return self._h
+
+    def set_shard(self, rank: int, world: int, allgather_cb):
+        """Hash-shard every proof of this session over `world` ranks (mdn_session_set_shard)."""
+        self._allgather_cb = allgather_cb      # keep the ctypes trampoline alive
+        self._check(lib().mdn_session_set_shard(self._h, rank, world, allgather_cb, None))
 
     def prove(self, statement: Statement, traces, challenger: Challenger, aux_builder=None, flags=0):
         """`ProverInstance::new(config, statement, None)?.prove(challenger)`; returns

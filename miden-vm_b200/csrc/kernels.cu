@@ -275,15 +275,21 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
 // Poseidon2 hashing
 // =============================================================================================
 static constexpr int HASH_THREADS = 128;
+#ifndef HASH_MIN_BLOCKS
+#define HASH_MIN_BLOCKS 1
+#endif
 
-__global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev,
+__global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_leaf_hash(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev,
                                                             u32 prev_log_n, u64* __restrict__ states_out,
-                                                            u64* __restrict__ dig) {
+                                                            u64* __restrict__ dig, u32 r0, u32 log_rn) {
+    // rows r0 .. r0 + 2^log_rn of every coset (the whole tree when r0 = 0, log_rn = log_n; a
+    // contiguous range of Merkle leaves [r0*B, (r0 + 2^log_rn)*B) when the hashing is sharded)
     size_t L = (size_t)1 << (log_n + log_b);
-    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= L) return;
-    u32 t = (u32)(pos >> log_n);
-    u32 r = (u32)(pos & (((size_t)1 << log_n) - 1));
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((size_t)1 << (log_rn + log_b))) return;
+    u32 t = (u32)(idx >> log_rn);
+    u32 r = r0 + (u32)(idx & (((size_t)1 << log_rn) - 1));
+    size_t pos = ((size_t)t << log_n) + r;
     u64 s[12];
     if (prev) {
         size_t Lp = (size_t)1 << (prev_log_n + log_b);
@@ -315,14 +321,14 @@ __global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash(LeafArgs a, u32 log_
     }
 }
 void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
-                      u64* states_out, u64* digests_out, cudaStream_t st) {
-    size_t L = (size_t)1 << (log_n + log_blowup);
-    unsigned blocks = (unsigned)((L + HASH_THREADS - 1) / HASH_THREADS);
-    k_leaf_hash<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, digests_out);
+                      u64* states_out, u64* digests_out, u32 r0, u32 log_rn, cudaStream_t st) {
+    size_t cnt = (size_t)1 << (log_rn + log_blowup);
+    unsigned blocks = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
+    k_leaf_hash<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, digests_out, r0, log_rn);
     COUNT_LAUNCH();
 }
 
-__global__ void __launch_bounds__(HASH_THREADS) k_compress(const u64* __restrict__ ch, u64* __restrict__ par, size_t n) {
+__global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_compress(const u64* __restrict__ ch, u64* __restrict__ par, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(ch + i * 8);

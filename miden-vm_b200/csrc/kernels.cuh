@@ -61,8 +61,9 @@ struct LeafArgs { LeafMat m[8]; int n_mats; };
 //   prev_states  : SoA [12][B << prev_log_n] states of the previous (shorter) group, or NULL
 //   states_out   : SoA [12][B << log_n] if more groups follow, else NULL
 //   digests_out  : tree leaf layer (4 u64 per leaf, indexed by DOMAIN index r*B + t), or NULL
+//   r0, log_rn   : only rows r0 .. r0 + 2^log_rn of each coset are hashed (leaf range [r0*B, ...))
 void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
-                      u64* states_out, u64* digests_out, cudaStream_t st);
+                      u64* states_out, u64* digests_out, u32 r0, u32 log_rn, cudaStream_t st);
 // parent[i] = perm(child[2i] | child[2i+1] | 0000)[0..4]
 void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
 // FRI round leaves: leaf i' (< quarter) = sponge([f[i'], f[i'+2q], f[i'+q], f[i'+3q]]) (8 felts, one block)

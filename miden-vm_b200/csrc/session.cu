@@ -111,6 +111,11 @@ struct mdn_session {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string error;
+    // hash sharding across ranks (mdn_session_set_shard): rank g hashes the contiguous leaf range g of every
+    // commitment tree; the only exchange is an all-gather of the G sub-roots
+    u32 shard_rank = 0, shard_world = 1, shard_log_g = 0;
+    mdn_allgather_fn allgather = nullptr; void* allgather_ctx = nullptr;
+    bool tree_sharded(u32 depth) const { return shard_world > 1 && depth >= shard_log_g + 6; }
     std::map<u32, std::unique_ptr<NttPlan>> ntt_plans;
     std::map<std::pair<u32, u32>, std::unique_ptr<PremulPlan>> premul_plans;   // (n, kind)
 
@@ -364,18 +369,42 @@ void mdn_session::build_tree(Committed& c, bool) {
         if (!last) out.alloc((size_t)12 << (ln + lb), stream);
         {
             ProfScope ps(prof, PC_LEAF);
-            size_t Lg = (size_t)1 << (ln + lb);
+            // only the last (tallest) group is sharded; shorter groups are cheap and their states are
+            // needed by every rank
+            bool sh = last && tree_sharded(depth);
+            u32 log_rn = sh ? ln - shard_log_g : ln;
+            u32 r0 = sh ? shard_rank << log_rn : 0;
+            size_t Lg = (size_t)1 << (log_rn + lb);
             for (int q = 0; q < args.n_mats; q++) { leaf_bytes += (double)Lg * args.m[q].width * 8.0; perms += Lg * ((args.m[q].width + 7) / 8); }
             leaf_bytes += last ? (double)Lg * 32.0 : (double)Lg * 96.0;
-            mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? c.tree.layer(depth) : nullptr, stream);
+            mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? c.tree.layer(depth) : nullptr, r0, log_rn, stream);
         }
         prev = out.p; prev_log = ln;
         i = j;
     }
-    {
+    if (!tree_sharded(depth)) {
         ProfScope ps(prof, PC_COMPRESS);
         perms += L - 1;
         for (u32 d = depth; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
+    } else {
+        // this rank's contiguous sub-tree, then ONE all-gather of the G sub-roots (32 bytes each), then the
+        // top log2(G) layers on every rank
+        u32 lg = shard_log_g;
+        {
+            ProfScope ps(prof, PC_COMPRESS);
+            for (u32 d = depth; d-- > lg;) {
+                size_t cnt = (size_t)1 << (d - lg), start = (size_t)shard_rank << (d - lg);
+                perms += cnt;
+                mk::launch_compress_layer(c.tree.layer(d + 1) + 2 * start * 4, c.tree.layer(d) + start * 4, cnt, stream);
+            }
+        }
+        std::vector<u64> mine(4), all(4 * (size_t)shard_world);
+        CUDA_OK(cudaMemcpyAsync(mine.data(), c.tree.layer(lg) + (size_t)shard_rank * 4, 32, cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        if (allgather(allgather_ctx, mine.data(), all.data(), 4) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed");
+        CUDA_OK(cudaMemcpyAsync(c.tree.layer(lg), all.data(), all.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+        ProfScope ps(prof, PC_COMPRESS);
+        for (u32 d = lg; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
     }
     CUDA_OK(cudaMemcpyAsync(c.root, c.tree.layer(0), 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -972,6 +1001,7 @@ void mdn_session::finish() {
     Indices ti = Indices::make(qs, log_lde);
     // 7f. openings: one pointer list, one gather (pcs/prover.rs:89-101; lifted_tree.rs:155-180)
     std::vector<const u64*> ptrs;
+    std::vector<int> sib_owner;   // per input-tree sibling (emission order): owning rank or -1 (replicated)
     struct Emit { int kind; size_t count; size_t pad; };   // kind 0: `count` fields then `pad` zero fields; 1: commitment (4)
     std::vector<Emit> plan;
     for (int g = 0; g < 3; g++) {
@@ -988,7 +1018,11 @@ void mdn_session::finish() {
             }
         for (auto& ds : hostfs::missing_siblings(leafs)) {
             for (int q = 0; q < 4; q++) ptrs.push_back(c.tree.layer(ds.first) + ds.second * 4 + q);
+            // sharded tree: a node below the sub-root level exists only on the rank owning its leaf range
+            int owner = -1;
+            if (tree_sharded(c.tree.depth) && ds.first > shard_log_g) owner = (int)(ds.second >> (ds.first - shard_log_g));
             plan.push_back(Emit{1, 4, 0});
+            sib_owner.push_back(owner);
         }
     }
     {
@@ -1017,6 +1051,23 @@ void mdn_session::finish() {
         std::vector<u64> vals(ptrs.size());
         CUDA_OK(cudaMemcpyAsync(vals.data(), d_vals.p, vals.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
+        if (shard_world > 1) {
+            // exchange the sibling digests that live in another rank's sub-tree: every rank contributes the
+            // ones it owns (zeros elsewhere), one all-gather, take each from its owner
+            std::vector<size_t> pos; std::vector<int> own;
+            size_t o2 = 0, si = 0;
+            for (auto& e : plan) {
+                if (e.kind == 0) { o2 += e.count; continue; }
+                if (si < sib_owner.size()) { if (sib_owner[si] >= 0) { pos.push_back(o2); own.push_back(sib_owner[si]); } si++; }
+                o2 += 4;
+            }
+            if (!pos.empty()) {
+                std::vector<u64> mine(4 * pos.size(), 0), all(4 * pos.size() * shard_world);
+                for (size_t q = 0; q < pos.size(); q++) if (own[q] == (int)shard_rank) for (int w4 = 0; w4 < 4; w4++) mine[4 * q + w4] = vals[pos[q] + w4];
+                if (allgather(allgather_ctx, mine.data(), all.data(), mine.size()) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed");
+                for (size_t q = 0; q < pos.size(); q++) for (int w4 = 0; w4 < 4; w4++) vals[pos[q] + w4] = all[(size_t)own[q] * mine.size() + 4 * q + w4];
+            }
+        }
         size_t o = 0;
         for (auto& e : plan) {
             if (e.kind == 0) { for (size_t i = 0; i < e.count; i++) tr.hint_field(vals[o++]); for (size_t i = 0; i < e.pad; i++) tr.hint_field(0); }
@@ -1278,6 +1329,14 @@ long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap)
     }
     if (out) for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
     return (long long)v.size();
+}
+
+int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_allgather_fn fn, void* ctx) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    if (world == 0 || (world & (world - 1)) || rank >= world || (world > 1 && !fn)) { s->error = "invalid shard configuration (world must be a power of two, callback required)"; return MDN_ERR_INVALID_ARG; }
+    s->shard_rank = rank; s->shard_world = world; s->allgather = fn; s->allgather_ctx = ctx;
+    s->shard_log_g = 0; while ((1u << s->shard_log_g) < world) s->shard_log_g++;
+    return MDN_OK;
 }
 
 int mdn_set_debug(mdn_session* s, int enable) {

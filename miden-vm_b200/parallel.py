@@ -39,3 +39,29 @@ def gather_roots(root: np.ndarray, device: str = "cpu") -> np.ndarray:
     out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(out, t)
     return np.stack([o.cpu().numpy().view(np.uint64) for o in out])
+
+
+def make_allgather_callback(device: str = "cpu"):
+    """`mdn_allgather_fn` for mdn_session_set_shard on top of torch.distributed: gathers `n` u64 words from
+    every rank (rank-major).  With the NCCL backend the 32-byte sub-roots travel over NVLink; the
+    transport is int64 because NCCL/gloo have no uint64."""
+    import ctypes as C
+    from .binding import ALLGATHER
+
+    def fn(ctx, send, recv, n):
+        try:
+            world = dist.get_world_size()
+            a = np.ctypeslib.as_array(send, shape=(n,)).view(np.int64).copy()
+            t = torch.from_numpy(a).to(device)
+            outs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(outs, t)
+            r = np.ctypeslib.as_array(recv, shape=(world * n,))
+            for k, o in enumerate(outs):
+                r[k * n:(k + 1) * n] = o.cpu().numpy().view(np.uint64)
+            return 0
+        except Exception:        # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    return ALLGATHER(fn)

@@ -65,3 +65,24 @@ def test_host_challenger_matches_oracle(oracle):
                                      ob.ptr(np.zeros(1, dtype=np.uint64)), 1, ob.ptr(out))
         assert va == int(out[0])
     assert bytes(a) == bytes(b)
+
+
+def test_proof_serialize_layout():
+    """mdn_proof_serialize is pure host code: u64-LE length + height bytes, u64-LE length + u64-LE felts,
+    u64-LE length + 32-byte commitments (bincode-default layout expected of wincode)."""
+    import numpy as np
+    lib = B.lib()
+    heights = (C.c_uint8 * 3)(10, 9, 8)
+    fields = np.array([1, 2, 0xFFFFFFFF00000000], dtype=np.uint64)
+    comms = np.arange(8, dtype=np.uint64)
+    pf = B.Proof(heights, 3, B.ptr(fields), 3, B.ptr(comms), 2)
+    need = lib.mdn_proof_serialize(C.byref(pf), None, 0)
+    assert need == 8 + 3 + 8 + 24 + 8 + 64
+    buf = (C.c_uint8 * need)()
+    assert lib.mdn_proof_serialize(C.byref(pf), buf, need) == need
+    raw = bytes(buf)
+    assert raw[:8] == (3).to_bytes(8, "little") and raw[8:11] == bytes([10, 9, 8])
+    assert raw[11:19] == (3).to_bytes(8, "little")
+    assert raw[19:43] == fields.astype("<u8").tobytes()
+    assert raw[43:51] == (2).to_bytes(8, "little")
+    assert raw[51:] == comms.astype("<u8").tobytes()

@@ -286,3 +286,70 @@ def test_gpu_matches_committed_golden_proofs():
             assert mg.digest(heights, fields, comms) == g["proof_sha256"], name
         finally:
             s.close()
+
+
+def test_staged_api_matches_one_shot(sess_fast):
+    """mdn_prove_begin / _commit_aux / _finish (host drives the aux build itself) must give the same
+    bytes as mdn_prove with a callback."""
+    import test_airs
+    lib = B.lib()
+    params = W.fast_pcs_params()
+    wl, builder = test_airs.fib_product_workload([6, 4], lqd=3)
+    ch = W.initial_challenger(params, prod_observe)
+    ref = sess_fast.prove(wl.statement, wl.matrices, ch, B.AUX_BUILDER(builder))
+    root = np.zeros(4, dtype=np.uint64)
+    rnd = np.zeros(4, dtype=np.uint64)
+    h = sess_fast.handle
+    assert lib.mdn_prove_begin(h, C.byref(wl.statement), wl.matrices, C.byref(ch), 0, B.ptr(root), B.ptr(rnd)) == 0, lib.mdn_last_error(h)
+    # the host-side aux build, exactly what the callback does
+    aux_bufs, val_bufs = [], []
+    for i in range(wl.k):
+        n = 1 << wl.log_heights[i]
+        ab = np.zeros(n * 2 * wl.aux_widths[i], dtype=np.uint64)
+        vb = np.zeros(2, dtype=np.uint64)
+        assert builder(None, i, C.pointer(wl.matrices[i]), rnd.ctypes.data_as(B.u64p), ab.ctypes.data_as(B.u64p), vb.ctypes.data_as(B.u64p)) == 0
+        aux_bufs.append(ab); val_bufs.append(vb)
+    aux_m = (B.Matrix * wl.k)()
+    vals = (B.u64p * wl.k)()
+    for i in range(wl.k):
+        aux_m[i] = B.Matrix(B.ptr(aux_bufs[i]), wl.log_heights[i], 2 * wl.aux_widths[i])
+        vals[i] = B.ptr(val_bufs[i])
+    aux_root = np.zeros(4, dtype=np.uint64)
+    assert lib.mdn_prove_commit_aux(h, aux_m, vals, B.ptr(aux_root)) == 0, lib.mdn_last_error(h)
+    proof = B.Proof()
+    assert lib.mdn_prove_finish(h, C.byref(proof)) == 0, lib.mdn_last_error(h)
+    got = B.proof_to_numpy(proof)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    assert np.array_equal(root, sess_fast.info(0)) and np.array_equal(aux_root, sess_fast.info(1))
+    # out-of-order calls are rejected, not crashed
+    assert lib.mdn_prove_finish(h, C.byref(proof)) != 0
+
+
+def test_two_sessions_are_independent():
+    params = W.fast_pcs_params()
+    a, b = B.Session(params, 0), B.Session(params, 0)
+    try:
+        wl1 = W.Workload([6], widths=(9,), aux_widths=(1,), seed=1)
+        wl2 = W.Workload([5, 7], widths=(9, 10), aux_widths=(1, 2), seed=2)
+        ch = W.initial_challenger(params, prod_observe)
+        p1 = a.prove(wl1.statement, wl1.matrices, ch)
+        p2 = b.prove(wl2.statement, wl2.matrices, ch)
+        q2 = a.prove(wl2.statement, wl2.matrices, ch)      # sessions are reusable across statements
+        q1 = b.prove(wl1.statement, wl1.matrices, ch)
+        assert np.array_equal(p1[1], q1[1]) and np.array_equal(p2[1], q2[1])
+        assert np.array_equal(p1[2], q1[2]) and np.array_equal(p2[2], q2[2])
+    finally:
+        a.close(); b.close()
+
+
+def test_hash_sharded_proof_matches_single_gpu():
+    """mdn_session_set_shard: the same proof split over 2 GPUs (leaf ranges + all-gather of sub-roots over
+    NCCL) must be byte-identical.  Needs two visible GPUs (run with `gpurun --gpus 2`)."""
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "run_sharded.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert "SHARDED_OK world 2" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

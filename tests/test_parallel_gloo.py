@@ -23,6 +23,14 @@ def _worker(rank, world, port, q):
     root = np.arange(4, dtype=np.uint64) + np.uint64(0xFFFFFFFF00000000) * np.uint64(rank)
     roots = par.gather_roots(root)
     seeds = par.rank_seed(2025, rank)
+    # the all-gather callback handed to mdn_session_set_shard, called the way the C library calls it
+    import ctypes as C
+    cb = par.make_allgather_callback("cpu")
+    send = np.array([rank + 1, 0xFFFFFFFF00000000 + rank, 7, 8], dtype=np.uint64)
+    recv = np.zeros(8, dtype=np.uint64)
+    u64p = C.POINTER(C.c_uint64)
+    assert cb(None, send.ctypes.data_as(u64p), recv.ctypes.data_as(u64p), 4) == 0
+    assert recv.tolist() == [1, 0xFFFFFFFF00000000, 7, 8, 2, 0xFFFFFFFF00000001, 7, 8]
     q.put((rank, tput, roots.tolist(), seeds))
     dist.destroy_process_group()
 
