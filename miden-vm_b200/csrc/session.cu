@@ -15,6 +15,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 using gl::E2;
@@ -155,6 +156,10 @@ struct mdn_session {
     void lde_and_commit(Committed& c, float* t_lde, float* t_hash, bool lde_done = false);
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev[8];
+    // pinned bounce buffers for pageable host inputs (a Rust Vec<Felt> is pageable)
+    u64* bounce[2] = {nullptr, nullptr}; cudaEvent_t bounce_ev[2]; bool bounce_busy[2] = {false, false};
+    static constexpr size_t BOUNCE_WORDS = (size_t)4 << 20;   // 32 MiB each
+    void host_to_device(u64* dst, const u64* src, size_t n);
     void upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm);
     void prove_begin(const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* ch, u32 flags);
     void commit_aux(const mdn_matrix* aux, const u64* const* aux_values, bool zero_aux);
@@ -283,6 +288,34 @@ void mdn_session::check_input_flag(const char* what) {
     if (flag) { CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); fail(MDN_ERR_INVALID_ARG, "%s contains a non-canonical field element (>= p)", what); }
 }
 
+// Host -> device copy on the copy stream.  Pinned (or registered) memory goes straight to the DMA engine;
+// pageable memory is staged through two pinned 32 MiB bounce buffers filled by a few host threads, which
+// sustains ~3x the throughput of a plain cudaMemcpyAsync from pageable memory (profiles/r1_summary.md).
+void mdn_session::host_to_device(u64* dst, const u64* src, size_t n) {
+    cudaPointerAttributes at{};
+    bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) { CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(u64), cudaMemcpyHostToDevice, copy_stream)); return; }
+    for (int b = 0; b < 2; b++) if (!bounce[b]) { CUDA_OK(cudaHostAlloc((void**)&bounce[b], BOUNCE_WORDS * sizeof(u64), cudaHostAllocDefault)); CUDA_OK(cudaEventCreateWithFlags(&bounce_ev[b], cudaEventDisableTiming)); }
+    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    int b = 0;
+    for (size_t off = 0; off < n; off += BOUNCE_WORDS, b ^= 1) {
+        size_t cnt = std::min(BOUNCE_WORDS, n - off);
+        if (bounce_busy[b]) CUDA_OK(cudaEventSynchronize(bounce_ev[b]));
+        std::vector<std::thread> th;
+        size_t per = (cnt + nt - 1) / nt;
+        for (unsigned q = 0; q < nt; q++) {
+            size_t a = (size_t)q * per, e = std::min(cnt, a + per);
+            if (a >= e) break;
+            th.emplace_back([=] { memcpy(bounce[b] + a, src + off + a, (e - a) * sizeof(u64)); });
+        }
+        for (auto& t : th) t.join();
+        CUDA_OK(cudaMemcpyAsync(dst + off, bounce[b], cnt * sizeof(u64), cudaMemcpyHostToDevice, copy_stream));
+        CUDA_OK(cudaEventRecord(bounce_ev[b], copy_stream));
+        bounce_busy[b] = true;
+    }
+}
+
 // row-major (host or device) -> column-major device
 void mdn_session::upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm) {
     size_t N = (size_t)1 << m.log_height;
@@ -293,7 +326,11 @@ void mdn_session::upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm
         return;
     }
     DevBuf staging; staging.alloc(N * m.width, stream);
-    CUDA_OK(cudaMemcpyAsync(staging.p, m.values, N * m.width * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaEventRecord(copy_ev[7], stream));
+    CUDA_OK(cudaStreamWaitEvent(copy_stream, copy_ev[7], 0));
+    host_to_device(staging.p, m.values, N * m.width);
+    CUDA_OK(cudaEventRecord(copy_ev[6], copy_stream));
+    CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[6], 0));
     ProfScope ps(prof, PC_TRANSPOSE);
     mk::launch_transpose_rm_to_cm(staging.p, dst_cm, (u32)N, m.width, (u32*)d_flag.p, stream);
 }
@@ -630,20 +667,15 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         CUDA_OK(cudaStreamWaitEvent(copy_stream, copy_ev[7], 0));
         for (u32 j = 0; j < k; j++) {
             const mdn_matrix& m = traces[order[j]];
-            CUDA_OK(cudaMemcpyAsync(staging[j].p, m.values, staging[j].n * sizeof(u64), cudaMemcpyHostToDevice, copy_stream));
+            host_to_device(staging[j].p, m.values, staging[j].n);
             CUDA_OK(cudaEventRecord(copy_ev[j % 7], copy_stream));
-            if (j % 7 == 6 || j + 1 == k) {
-                // at most 7 copies in flight per batch of events
-                for (u32 q = j - (j % 7); q <= j; q++) {
-                    CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[q % 7], 0));
-                    {
-                        ProfScope ps(prof, PC_TRANSPOSE);
-                        mk::launch_transpose_rm_to_cm(staging[q].p, main_c.mats[q].coef, 1u << main_c.mats[q].log_n, main_c.mats[q].width, (u32*)d_flag.p, stream);
-                    }
-                    if (q + 1 == k) CUDA_OK(cudaEventRecord(ev[1], stream));
-                    lde_matrix(main_c.mats[q]);
-                }
+            CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[j % 7], 0));
+            {
+                ProfScope ps(prof, PC_TRANSPOSE);
+                mk::launch_transpose_rm_to_cm(staging[j].p, main_c.mats[j].coef, 1u << main_c.mats[j].log_n, main_c.mats[j].width, (u32*)d_flag.p, stream);
             }
+            if (j + 1 == k) CUDA_OK(cudaEventRecord(ev[1], stream));
+            lde_matrix(main_c.mats[j]);   // queued behind the copy of matrix j; overlaps the copy of matrix j+1
         }
     } else {
         for (u32 j = 0; j < k; j++) upload_matrix(traces[order[j]], true, main_c.mats[j].coef);
@@ -1144,6 +1176,7 @@ void mdn_session_destroy(mdn_session* s) {
     cudaStreamSynchronize(s->stream);
     for (auto& evn : s->ev) cudaEventDestroy(evn);
     for (auto& evn : s->copy_ev) cudaEventDestroy(evn);
+    for (int b = 0; b < 2; b++) if (s->bounce[b]) { cudaFreeHost(s->bounce[b]); cudaEventDestroy(s->bounce_ev[b]); }
     cudaStreamDestroy(s->copy_stream);
     cudaStreamDestroy(s->stream);
     delete s;
