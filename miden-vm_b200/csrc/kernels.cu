@@ -345,20 +345,33 @@ void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, 
     COUNT_LAUNCH();
 }
 
-__global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict__ ev, size_t q, u64* __restrict__ dig) {
+// FRI round leaf: physical row of 2^la extension values [f[i + bitrev_la(j) * q]]_j (fri/prover.rs:137-165),
+// flattened to 2 * 2^la felts and absorbed with the rate-8 sponge (unaligned tree).
+__global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict__ ev, size_t q, u32 la, u64* __restrict__ dig) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q) return;
     const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
-    ulonglong2 y0 = e[i], y2 = e[i + 2 * q], y1 = e[i + q], y3 = e[i + 3 * q];
-    u64 s[12] = {y0.x, y0.y, y2.x, y2.y, y1.x, y1.y, y3.x, y3.y, 0, 0, 0, 0};
-    p2f::permute(s);
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+    u32 a = 1u << la;
+    for (u32 j0 = 0; j0 < a; j0 += 4) {
+#pragma unroll
+        for (u32 j = 0; j < 4; j++) {
+            if (j0 + j < a) {
+                ulonglong2 v = e[i + (size_t)gl::bitrev32(j0 + j, la) * q];
+                s[2 * j] = v.x; s[2 * j + 1] = v.y;
+            } else { s[2 * j] = 0; s[2 * j + 1] = 0; }
+        }
+        p2f::permute(s);
+    }
     ulonglong2* d = reinterpret_cast<ulonglong2*>(dig + i * 4);
     d[0] = make_ulonglong2(glf::canon(s[0]), glf::canon(s[1]));
     d[1] = make_ulonglong2(glf::canon(s[2]), glf::canon(s[3]));
 }
-void launch_fri_leaf_hash(const u64* evals, size_t quarter, u64* digests, cudaStream_t st) {
-    unsigned blocks = (unsigned)((quarter + HASH_THREADS - 1) / HASH_THREADS);
-    k_fri_leaf<<<blocks, HASH_THREADS, 0, st>>>(evals, quarter, digests);
+void launch_fri_leaf_hash(const u64* evals, size_t rows, u32 log_arity, u64* digests, cudaStream_t st) {
+    unsigned blocks = (unsigned)((rows + HASH_THREADS - 1) / HASH_THREADS);
+    k_fri_leaf<<<blocks, HASH_THREADS, 0, st>>>(evals, rows, log_arity, digests);
     COUNT_LAUNCH();
 }
 
@@ -631,33 +644,39 @@ void launch_deep(const DeepArgs& a, cudaStream_t st) {
 }
 
 // =============================================================================================
-// FRI fold (arity 4), natural domain order
+// FRI fold (arity 2 / 4 / 8), natural domain order: interpolate the 2^la values of the coset
+// s*<w_a> (inverse DFT), evaluate at beta/s, divide by the arity
+// (pcs/fri/fold/arity2.rs, arity4.rs:46-121, arity8.rs:35-75 compute the same field element)
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_fri_fold(const u64* __restrict__ ev, u32 log_dom, E2 beta, u64 w_inv, u64 w4,
-                                                  u64 four_inv, u64* __restrict__ next) {
-    size_t q = (size_t)1 << (log_dom - 2);
+struct FoldArgs { u64 winv[8]; u64 arity_inv; u64 w_dom_inv; u32 log_dom, la; E2 beta; };
+__global__ void __launch_bounds__(256) k_fri_fold(const u64* __restrict__ ev, FoldArgs fa, u64* __restrict__ next) {
+    size_t q = (size_t)1 << (fa.log_dom - fa.la);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q) return;
     const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
-    ulonglong2 v0 = e[i], v2 = e[i + 2 * q], v1 = e[i + q], v3 = e[i + 3 * q];
-    E2 y0 = gl::e2(v0.x, v0.y), y2 = gl::e2(v2.x, v2.y), y1 = gl::e2(v1.x, v1.y), y3 = gl::e2(v3.x, v3.y);
-    // size-4 inverse DFT of [y0,y1,y2,y3] (pcs/fri/fold/arity4.rs:86-121), then Horner at beta/s
-    E2 s02 = gl::e2_add(y0, y2), d02 = gl::e2_sub(y0, y2), s13 = gl::e2_add(y1, y3);
-    E2 d31 = gl::e2_mulf(gl::e2_sub(y3, y1), w4);
-    E2 c0 = gl::e2_add(s02, s13), c1 = gl::e2_add(d02, d31), c2 = gl::e2_sub(s02, s13), c3 = gl::e2_sub(d02, d31);
-    u64 s_inv = gl::pow(w_inv, (u64)i);
-    E2 x = gl::e2_mulf(beta, s_inv);
-    E2 acc = gl::e2_add(gl::e2_mul(c3, x), c2);
-    acc = gl::e2_add(gl::e2_mul(acc, x), c1);
-    acc = gl::e2_add(gl::e2_mul(acc, x), c0);
-    acc = gl::e2_mulf(acc, four_inv);
+    u32 a = 1u << fa.la;
+    E2 y[8];
+    for (u32 k = 0; k < a; k++) { ulonglong2 v = e[i + (size_t)k * q]; y[k] = gl::e2(v.x, v.y); }   // y_k = f(s * w_a^k)
+    u64 s_inv = gl::pow(fa.w_dom_inv, (u64)i);
+    E2 x = gl::e2_mulf(fa.beta, s_inv);
+    E2 acc = gl::e2(0, 0);
+    for (u32 m = a; m-- > 0;) {                      // Horner over c_m = sum_k y_k * w_a^(-m k)
+        E2 c = y[0];
+        for (u32 k = 1; k < a; k++) c = gl::e2_add(c, gl::e2_mulf(y[k], fa.winv[(m * k) & (a - 1)]));
+        acc = gl::e2_add(gl::e2_mul(acc, x), c);
+    }
+    acc = gl::e2_mulf(acc, fa.arity_inv);
     reinterpret_cast<ulonglong2*>(next)[i] = make_ulonglong2(acc.a, acc.b);
 }
-void launch_fri_fold(const u64* evals, u32 log_dom, E2 beta, u64* next, cudaStream_t st) {
-    size_t q = (size_t)1 << (log_dom - 2);
-    u64 w_inv = gl::inv(gl::two_adic_generator(log_dom));
-    k_fri_fold<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(evals, log_dom, beta, w_inv, gl::two_adic_generator(2),
-                                                            gl::inv(4), next);
+void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, u64* next, cudaStream_t st) {
+    size_t q = (size_t)1 << (log_dom - log_arity);
+    FoldArgs fa;
+    u32 a = 1u << log_arity;
+    u64 wi = gl::inv(gl::two_adic_generator(log_arity)), x = 1;
+    for (u32 j = 0; j < 8; j++) { fa.winv[j] = j < a ? x : 0; x = gl::mul(x, wi); }
+    fa.arity_inv = gl::inv((u64)a); fa.w_dom_inv = gl::inv(gl::two_adic_generator(log_dom));
+    fa.log_dom = log_dom; fa.la = log_arity; fa.beta = beta;
+    k_fri_fold<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(evals, fa, next);
     COUNT_LAUNCH();
 }
 

@@ -67,7 +67,7 @@ void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* p
 // parent[i] = perm(child[2i] | child[2i+1] | 0000)[0..4]
 void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
 // FRI round leaves: leaf i' (< quarter) = sponge([f[i'], f[i'+2q], f[i'+q], f[i'+3q]]) (8 felts, one block)
-void launch_fri_leaf_hash(const u64* evals /* EF interleaved, 4q */, size_t quarter, u64* digests, cudaStream_t st);
+void launch_fri_leaf_hash(const u64* evals /* EF interleaved */, size_t rows, u32 log_arity, u64* digests, cudaStream_t st);
 void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
@@ -124,7 +124,7 @@ struct DeepArgs {
 void launch_deep(const DeepArgs& a, cudaStream_t st);
 
 // next[i'] = fold4([f[i'], f[i'+2q], f[i'+q], f[i'+3q]], s_inv = w_dom^(-i'), beta)
-void launch_fri_fold(const u64* evals, u32 log_dom, E2 beta, u64* next, cudaStream_t st);
+void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, u64* next, cudaStream_t st);
 
 // Proof-of-work: smallest w such that the duplexed state has (st[7] & mask) == 0.
 //   base_state: 12 u64 with the pending inputs already written at rate[0..in_len) and the rest of

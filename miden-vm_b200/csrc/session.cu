@@ -489,7 +489,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     if (!d_flag.p) { d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
     if (!st || !traces || !chal) fail(MDN_ERR_INVALID_ARG, "null argument");
     if (st->n_airs == 0 || st->n_airs > 256) fail(MDN_ERR_INVALID_ARG, "AIR count must be in 1..=256");
-    if (params.log_folding_arity != 2) fail(MDN_ERR_UNSUPPORTED, "only FRI folding arity 4 is implemented");
+    if (params.log_folding_arity < 1 || params.log_folding_arity > 3) fail(MDN_ERR_INVALID_ARG, "invalid folding arity: log_arity %u (must be 1, 2, or 3)", params.log_folding_arity);
     u32 lb = params.log_blowup;
     if (lb == 0 || lb > 4) fail(MDN_ERR_UNSUPPORTED, "log_blowup must be in 1..=4");
     bool on_device = (flags & MDN_FLAG_DEVICE_TRACES) != 0;
@@ -968,27 +968,28 @@ void mdn_session::finish() {
         }
     }
     // 7d. FRI commit phase (fri/prover.rs:93-242)
+    const u32 la = params.log_folding_arity;
     u32 rounds; size_t final_deg;
     {
         u32 target = params.log_final_degree + lb;
         u32 steps = log_lde > target ? log_lde - target : 0;
-        rounds = (steps + 1) / 2;
-        u32 lf = log_lde > 2 * rounds ? log_lde - 2 * rounds : 0;
+        rounds = (steps + la - 1) / la;                       // fri/mod.rs:80-94
+        u32 lf = log_lde > la * rounds ? log_lde - la * rounds : 0;
         final_deg = (size_t)1 << (lf > lb ? lf - lb : 0);
     }
     std::vector<Tree> fri_trees(rounds);
     dbg_fri_roots.clear();
     u32 log_dom = log_lde;
     for (u32 r = 0; r < rounds; r++) {
-        if (log_dom < 2) fail(MDN_ERR_INVALID_ARG, "FRI domain too small for arity 4");
-        size_t q = (size_t)1 << (log_dom - 2);
+        if (log_dom < la) fail(MDN_ERR_INVALID_ARG, "FRI domain too small for the folding arity");
+        size_t q = (size_t)1 << (log_dom - la);
         Tree& t = fri_trees[r];
-        t.depth = log_dom - 2;
+        t.depth = log_dom - la;
         t.nodes.alloc((2 * q - 1) * 4, stream);
         {
             ProfScope ps(prof, PC_FRI);
-            perms += 2 * q - 1;
-            mk::launch_fri_leaf_hash(fri_layers[r].p, q, t.layer(t.depth), stream);
+            perms += q * (la == 3 ? 2 : 1) + q - 1;
+            mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, t.layer(t.depth), stream);
             for (u32 d = t.depth; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
         }
         u64 root[4];
@@ -999,8 +1000,8 @@ void mdn_session::finish() {
         grind(params.folding_pow_bits);
         E2 fb = tr.ch.sample_ext();
         fri_layers.emplace_back(); fri_layers[r + 1].alloc(2 * q, stream);
-        { ProfScope ps(prof, PC_FRI); mk::launch_fri_fold(fri_layers[r].p, log_dom, fb, fri_layers[r + 1].p, stream); }
-        log_dom -= 2;
+        { ProfScope ps(prof, PC_FRI); mk::launch_fri_fold(fri_layers[r].p, log_dom, la, fb, fri_layers[r + 1].p, stream); }
+        log_dom -= la;
     }
     // final polynomial (fri/prover.rs:228-239): values on the size-final_deg subgroup are the
     // final-layer entries at natural indices i*B; iDFT on the host, sent in descending order.
@@ -1061,19 +1062,22 @@ void mdn_session::finish() {
         Indices fi = ti;
         u32 ld = log_lde;
         for (u32 r = 0; r < rounds; r++) {
-            fi = fi.folded(fi.depth > 2 ? fi.depth - 2 : 0);
-            size_t q = (size_t)1 << (ld - 2);
+            fi = fi.folded(fi.depth > la ? fi.depth - la : 0);
+            size_t q = (size_t)1 << (ld - la);
             const u64* lay = fri_layers[r].p;
+            u32 a = 1u << la;
             for (size_t idx : fi.idx) {
-                size_t src[4] = {idx, idx + 2 * q, idx + q, idx + 3 * q};
-                for (int e = 0; e < 4; e++) { ptrs.push_back(lay + 2 * src[e]); ptrs.push_back(lay + 2 * src[e] + 1); }
-                plan.push_back(Emit{0, 8, 0});
+                for (u32 e = 0; e < a; e++) {
+                    size_t src = idx + (size_t)gl::bitrev32(e, la) * q;
+                    ptrs.push_back(lay + 2 * src); ptrs.push_back(lay + 2 * src + 1);
+                }
+                plan.push_back(Emit{0, 2 * (size_t)a, 0});
             }
             for (auto& ds : hostfs::missing_siblings(fi)) {
                 for (int qq = 0; qq < 4; qq++) ptrs.push_back(fri_trees[r].layer(ds.first) + ds.second * 4 + qq);
                 plan.push_back(Emit{1, 4, 0});
             }
-            ld -= 2;
+            ld -= la;
         }
     }
     {

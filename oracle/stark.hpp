@@ -242,9 +242,25 @@ inline Ef fold2(const Ef* ev, Fp s_inv, Ef beta) {   // fold/arity2.rs: (y0+y1)/
     Ef s = (ev[0] + ev[1]) * half, d = (ev[0] - ev[1]) * half;
     return s + d * (beta * s_inv);
 }
+// Arity 8 (fold/arity8.rs:35-75): inverse DFT of the eight coset evaluations, evaluate at beta/s, divide by 8.
+// The physical row is in bit-reversed order [y0, y4, y2, y6, y1, y5, y3, y7].
+inline Ef fold8(const Ef* ev, Fp s_inv, Ef beta) {
+    Ef y[8];
+    for (unsigned j = 0; j < 8; j++) y[reverse_bits(j, 3)] = ev[j];
+    Fp w_inv = fp_inv(two_adic_generator(3));
+    Ef x = beta * s_inv, xp = ef_one(), acc;
+    for (unsigned m = 0; m < 8; m++) {
+        Ef c;
+        for (unsigned k = 0; k < 8; k++) c = c + y[k] * fp_pow(w_inv, (u64)m * k);
+        acc = acc + c * xp;
+        xp = xp * x;
+    }
+    return acc * fp_inv(Fp::raw(8));
+}
 inline Ef fold_row(unsigned log_arity, const Ef* ev, Fp s_inv, Ef beta) {
     if (log_arity == 2) return fold4(ev, s_inv, beta);
     if (log_arity == 1) return fold2(ev, s_inv, beta);
+    if (log_arity == 3) return fold8(ev, s_inv, beta);
     throw std::runtime_error("fri: unsupported arity");
 }
 

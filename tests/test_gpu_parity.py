@@ -177,6 +177,21 @@ def test_prove_other_blowups(log_blowup):
         s.close()
 
 
+@pytest.mark.parametrize("log_arity", [1, 3])
+def test_prove_other_fri_arities(log_arity):
+    # FriFold::new accepts log_arity 1, 2, 3 (pcs/fri/fold/mod.rs:38-46); Miden uses 2
+    import test_airs
+    params = B.PcsParams(3, log_arity, 2, 2, 3, 7, 4)
+    s = B.Session(params, 0)
+    B.lib().mdn_set_debug(s.handle, 1)
+    try:
+        _compare_proofs(s, params, W.Workload([7, 9], widths=(9, 12), aux_widths=(1, 2)))
+        wl, builder = test_airs.fib_product_workload([8], lqd=1)
+        _compare_proofs(s, params, wl, builder)
+    finally:
+        s.close()
+
+
 def test_prove_periodic_columns(sess_fast):
     import test_airs
     _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=3))

@@ -197,6 +197,12 @@ def test_prove_verify_other_blowups(log_blowup):
     _roundtrip(params, wl, builder)
 
 
+@pytest.mark.parametrize("log_arity", [1, 3])
+def test_prove_verify_other_fri_arities(log_arity):
+    params = H.B.PcsParams(3, log_arity, 2, 2, 3, 7, 4)
+    _roundtrip(params, W.Workload([7, 9], widths=(9, 12), aux_widths=(1, 2)))
+
+
 def test_violated_constraint_is_rejected():
     wl = W.Workload([5], widths=(9,), aux_widths=(1,))
     wl.traces[0][3, 0] = 1   # column 0 must vanish for the product constraint
