@@ -37,7 +37,7 @@ typedef enum {
     MDN_ERR_INVALID_ARG = -1,      /* malformed statement / trace shape (InstanceError) */
     MDN_ERR_DOMAIN = -2,           /* DomainError: LDE order too large, degree > blowup */
     MDN_ERR_CUDA = -3,             /* device error (message carries the CUDA string) */
-    MDN_ERR_UNSUPPORTED = -4,      /* e.g. folding arity other than 4, preprocessed columns */
+    MDN_ERR_UNSUPPORTED = -4,      /* e.g. log_blowup > 4, > 1024 live constraint values */
     MDN_ERR_AUX_BUILDER = -5,      /* aux-trace callback failed */
     MDN_ERR_NO_DEVICE = -6,
 } mdn_status;
@@ -74,6 +74,7 @@ typedef struct {
  *   0 MAIN(a=row offset 0|1, b=col)  1 AUX(a=offset, b=EF col)  2 PUBLIC(a)  3 CHALLENGE(a)
  *   4 AUX_VALUE(a)  5 IS_FIRST_ROW  6 IS_LAST_ROW  7 IS_TRANSITION  8 CONST(a)  9 EXT_CONST(a)
  *   10 ADD(a,b)  11 SUB(a,b)  12 MUL(a,b)  13 NEG(a)  14 PERIODIC(a=periodic column)
+ *   15 PREPROCESSED(a=row offset 0|1, b=col)
  * Constraints are folded as acc <- acc*alpha + C_k in emission order
  * (crates/lifted-stark/src/verifier/constraints.rs:83,108). */
 typedef struct {
@@ -90,6 +91,7 @@ typedef struct {
     const uint64_t* periodic_values;
     uint32_t num_periodic_columns;
     uint32_t log_max_period;
+    uint32_t preprocessed_width;    /* BaseAir::preprocessed_width(): 0 = the AIR declares no preprocessed columns */
 } mdn_air;
 
 /* p3 RowMajorMatrix<Felt>: `values` has (1 << log_height) * width entries.  With
@@ -152,6 +154,19 @@ const char* mdn_last_error(const mdn_session* s);   /* s may be NULL: last creat
  * payloads are 32 bytes per rank per commitment.  world must be a power of two; world = 1 disables. */
 typedef int (*mdn_allgather_fn)(void* ctx, const uint64_t* send, uint64_t* recv, size_t n_u64);
 int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_allgather_fn fn, void* ctx);
+
+/* ---- preprocessed columns: Preprocessed::build (crates/lifted-stark/src/preprocessed.rs:63-131) -----
+ * `preprocessed[i]` = `BaseAir::preprocessed_trace()` of AIR i (HOST pointer; width 0 where the AIR declares
+ * none, otherwise width == airs[i].preprocessed_width).  The declared matrices are sorted by (height, AIR
+ * index), LDE'd on the canonical coset of their own height and committed in one aligned LMCS tree that stays
+ * on the device and is borrowed by every later proof of this session (prover/mod.rs:118-123), until replaced.
+ * `commitment_out` receives `Preprocessed::commitment()` -- the value the verifier is constructed with
+ * (verifier/mod.rs:101-121).  A bundle must be installed exactly when some AIR of the proved statement
+ * declares preprocessed columns, and each preprocessed height must equal the AIR's main trace height
+ * (validate_preprocessed, preprocessed.rs:147-260): otherwise mdn_prove returns MDN_ERR_INVALID_ARG.
+ * preprocessed == NULL removes the bundle. */
+int mdn_session_set_preprocessed(mdn_session* s, const mdn_statement* st, const mdn_matrix* preprocessed,
+                                 uint64_t commitment_out[4]);
 
 /* ---- the drop-in: ProverInstance::prove (prover/mod.rs:230-578) ------------------------------
  * `challenger` is the caller's pre-bound challenger (protocol params observed,

@@ -16,7 +16,7 @@ MAGIC = 0x5249414D
 
 OP_MAIN, OP_AUX, OP_PUBLIC, OP_CHALLENGE, OP_AUX_VALUE = 0, 1, 2, 3, 4
 OP_IS_FIRST, OP_IS_LAST, OP_IS_TRANSITION, OP_CONST, OP_EXT_CONST = 5, 6, 7, 8, 9
-OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_PERIODIC = 10, 11, 12, 13, 14
+OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_PERIODIC, OP_PREPROCESSED = 10, 11, 12, 13, 14, 15
 
 
 class Expr:
@@ -58,6 +58,7 @@ class ProgramBuilder:
     def is_last_row(self) -> Expr: return self._node(OP_IS_LAST)
     def is_transition(self) -> Expr: return self._node(OP_IS_TRANSITION)
     def periodic(self, col: int) -> Expr: return self._node(OP_PERIODIC, col)
+    def preprocessed(self, offset: int, col: int) -> Expr: return self._node(OP_PREPROCESSED, offset, col)
 
     def const(self, v: int) -> Expr:
         self.consts.append(v % P)

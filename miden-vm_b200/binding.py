@@ -28,7 +28,8 @@ class Air(C.Structure):
     _fields_ = [("width", C.c_uint32), ("aux_width", C.c_uint32), ("num_aux_values", C.c_uint32),
                 ("num_randomness", C.c_uint32), ("log_quotient_degree", C.c_uint32),
                 ("program_words", C.c_uint32), ("program", u32p),
-                ("periodic_values", u64p), ("num_periodic_columns", C.c_uint32), ("log_max_period", C.c_uint32)]
+                ("periodic_values", u64p), ("num_periodic_columns", C.c_uint32), ("log_max_period", C.c_uint32),
+                ("preprocessed_width", C.c_uint32)]
 
 
 class Matrix(C.Structure):
@@ -64,6 +65,7 @@ EXPORTS = [
     "mdn_prove_commit_aux", "mdn_prove_finish", "mdn_proof_serialize", "mdn_coset_lde_batch",
     "mdn_lmcs_commit", "mdn_poseidon2_permute", "mdn_get_info", "mdn_get_timings",
     "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug", "mdn_session_set_shard",
+    "mdn_session_set_preprocessed",
 ]
 
 _lib = None
@@ -99,6 +101,7 @@ def lib():
         L.mdn_get_info.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t]
         L.mdn_set_debug.argtypes = [C.c_void_p, C.c_int]
         L.mdn_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHER, C.c_void_p]
+        L.mdn_session_set_preprocessed.argtypes = [C.c_void_p, C.POINTER(Statement), C.POINTER(Matrix), u64p]
         L.mdn_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.mdn_challenger_observe.argtypes = [C.POINTER(Challenger), u64p, C.c_size_t]
         L.mdn_challenger_sample.restype = C.c_uint64
@@ -148,6 +151,14 @@ class Session:
         """Hash-shard every proof of this session over `world` ranks (mdn_session_set_shard)."""
         self._allgather_cb = allgather_cb      # keep the ctypes trampoline alive
         self._check(lib().mdn_session_set_shard(self._h, rank, world, allgather_cb, None))
+
+    def set_preprocessed(self, statement: Statement, preprocessed):
+        """`Preprocessed::build(statement, config)` on the device; returns the commitment (u64[4]).
+        `preprocessed` = Matrix array in instance order (width 0 = none), or None to remove the bundle."""
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(lib().mdn_session_set_preprocessed(self._h, C.byref(statement) if statement is not None else None,
+                                                       preprocessed, out.ctypes.data_as(u64p)))
+        return out
 
     def prove(self, statement: Statement, traces, challenger: Challenger, aux_builder=None, flags=0):
         """`ProverInstance::new(config, statement, None)?.prove(challenger)`; returns

@@ -394,7 +394,7 @@ void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st) {
 // Constraint evaluation (op-list interpreter) + quotient accumulation
 // =============================================================================================
 struct ConstraintKArgs {
-    const u64* main_lde; const u64* aux_lde;
+    const u64* main_lde; const u64* aux_lde; const u64* prep_lde;
     u32 log_n, log_b;
     AirDev air;
     const u64* publics; const u64* challenges; const u64* aux_values;
@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(128) k_constraints(ConstraintKArgs a) {
             case 12: v = ext ? gl::e2_mul(slot[x], slot[y]) : gl::e2(gl::mul(slot[x].a, slot[y].a), 0); break;
             case 13: v = ext ? gl::e2_neg(slot[x]) : gl::e2(gl::neg(slot[x].a), 0); break;
             case 14: v = gl::e2(a.air.periodic[x * per_stride + per_idx], 0); break;
+            case 16: v = gl::e2(a.prep_lde[(size_t)y * L + (x ? pos_next : pos)], 0); break;
             default: acc = gl::e2_add(gl::e2_mul(acc, a.alpha), slot[x]); continue;
         }
         slot[ins.y] = v;
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(128) k_constraints(ConstraintKArgs a) {
 
 int launch_constraints(const ConstraintArgs& a, cudaStream_t st) {
     ConstraintKArgs k;
-    k.main_lde = a.main_lde; k.aux_lde = a.aux_lde; k.log_n = a.log_n; k.log_b = a.log_blowup; k.air = a.air;
+    k.main_lde = a.main_lde; k.aux_lde = a.aux_lde; k.prep_lde = a.prep_lde; k.log_n = a.log_n; k.log_b = a.log_blowup; k.air = a.air;
     k.publics = a.publics; k.challenges = a.challenges; k.aux_values = a.aux_values;
     k.alpha = a.alpha; k.beta = a.beta; k.acc_in = a.acc_in; k.acc_in_log_n = a.acc_in_log_n; k.acc_out = a.acc_out;
     k.w_hi = a.T->w_hi; k.w_lo = a.T->w_lo; k.lo_bits = a.T->lo_bits;

@@ -75,7 +75,7 @@ void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
 // ---------------------------------------------------------------------------------------------
 // Compiled constraint program: 4 words per instruction {op | ext << 8, dst slot, a, b}.  Ops 0..14 as in
 // include/miden_b200.h (operands of ADD/SUB/MUL/NEG are SLOTS), 15 = FOLD slot a into the accumulator
-// (acc <- acc * alpha + slot).  `ext` = 1 selects extension-field arithmetic for ADD/SUB/MUL/NEG.
+// (acc <- acc * alpha + slot), 16 = PREPROCESSED (a = row offset, b = column).  `ext` = 1 selects extension-field arithmetic for ADD/SUB/MUL/NEG.
 // Slots are assigned by liveness on the host, so the interpreter's register file is the program's
 // maximum number of simultaneously live values, not its node count.
 struct AirDev {
@@ -89,6 +89,7 @@ struct AirDev {
 struct ConstraintArgs {
     const u64* main_lde; u32 main_width;
     const u64* aux_lde; u32 aux_width_base;
+    const u64* prep_lde;     // preprocessed LDE of this AIR (same height as main), or NULL
     u32 log_n, log_blowup;
     AirDev air;
     const u64* publics;      // device

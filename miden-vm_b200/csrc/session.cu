@@ -131,6 +131,11 @@ struct mdn_session {
     Transcript tr;
     std::vector<E2> randomness;
     Committed main_c, aux_c, quot_c;
+    // Preprocessed bundle (mdn_session_set_preprocessed): persists across proofs like the reference's borrowed
+    // `Preprocessed` (preprocessed.rs:49-61).  prep_air[q] = instance of committed preprocessed trace q.
+    Committed prep_c; bool has_prep = false;
+    std::vector<u32> prep_air, prep_log_h;
+    void set_preprocessed(const mdn_statement* st, const mdn_matrix* mats);
     std::vector<std::vector<u64>> aux_values_p;   // proof order, EF pairs
     DevBuf d_publics, d_randomness, d_aux_values, d_flag;
     void check_input_flag(const char* what);
@@ -516,7 +521,8 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         bool uses_sel = false;
         for (u32 j = 0; j < nn; j++) {
             u32 op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
-            if (op > 14) fail(MDN_ERR_INVALID_ARG, "AIR %u: unknown op %u", i, op);
+            if (op > 15) fail(MDN_ERR_INVALID_ARG, "AIR %u: unknown op %u", i, op);
+            if (op == 15 && (x > 1 || y >= a.preprocessed_width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed column out of range", i);
             if (op >= 5 && op <= 7) uses_sel = true;
             if (op >= 10 && op <= 12 && (x >= j || y >= j)) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
             if (op == 13 && x >= j) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
@@ -570,7 +576,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
             if (!free_slots.empty()) { dst = free_slots.back(); free_slots.pop_back(); }
             else dst = n_slots++;
             slot_of[j] = dst;
-            code.insert(code.end(), {op | ((u32)is_ext[j] << 8), dst, ox, oy});
+            code.insert(code.end(), {(op == 15 ? 16u : op) | ((u32)is_ext[j] << 8), dst, ox, oy});   // compiled 15 = FOLD, 16 = PREPROCESSED
             if (last_use[j] == e) free_slots.push_back(dst);   // dead value
         }
         if (n_slots > 1024) fail(MDN_ERR_UNSUPPORTED, "AIR %u: constraint program needs %u live values (interpreter limit 1024)", i, n_slots);
@@ -623,6 +629,25 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         h.dev.n_instr = (u32)(code.size() / 4); h.dev.n_slots = std::max(1u, n_slots); h.dev.uses_selectors = uses_sel;
         h.dev.log_max_period = a.log_max_period; h.dev.n_periodic = a.num_periodic_columns;
     }
+    // preprocessed presence / shape parity (ProverInstance::new, prover/mod.rs:139-153; validate_preprocessed,
+    // preprocessed.rs:147-260): a bundle must be installed exactly when some AIR declares preprocessed columns,
+    // and each committed trace must have its AIR's declared width and its main trace's height
+    {
+        bool expected = false;
+        for (u32 i = 0; i < k; i++) expected |= st->airs[i].preprocessed_width > 0;
+        if (expected != has_prep) fail(MDN_ERR_INVALID_ARG, "preprocessed presence mismatch: AIRs %s preprocessed columns but %s bundle is installed", expected ? "declare" : "declare no", has_prep ? "a" : "no");
+        if (has_prep) {
+            std::vector<int> idx(k, -1);
+            for (size_t q = 0; q < prep_air.size(); q++) { if (prep_air[q] >= k) fail(MDN_ERR_INVALID_ARG, "preprocessed bundle was built for a different AIR list"); idx[prep_air[q]] = (int)q; }
+            for (u32 i = 0; i < k; i++) {
+                bool want = st->airs[i].preprocessed_width > 0;
+                if (want != (idx[i] >= 0)) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed trace presence mismatch", i);
+                if (!want) continue;
+                if (prep_c.mats[idx[i]].width != st->airs[i].preprocessed_width) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed width %u does not match the declared %u", i, prep_c.mats[idx[i]].width, st->airs[i].preprocessed_width);
+                if (prep_log_h[idx[i]] != traces[i].log_height) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed height 2^%u differs from the main trace height 2^%u", i, prep_log_h[idx[i]], traces[i].log_height);
+            }
+        }
+    }
     publics.assign(st->public_values, st->public_values + st->n_public_values);
     // TraceOrder: stable sort on (log_height, instance)  (order.rs)
     order.resize(k);
@@ -637,6 +662,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     if (chal->input_len > 7 || chal->output_len > 8) fail(MDN_ERR_INVALID_ARG, "malformed challenger state");
     for (u32 i = 0; i < chal->input_len; i++) ch.in[i] = chal->input_buffer[i];
     ch.in_len = chal->input_len; ch.out_len = chal->output_len;
+    if (has_prep) for (int q = 0; q < 4; q++) ch.observe(prep_c.root[q]);   // preprocessed commitment first (mod.rs:282-286)
     for (u32 i = 0; i < st->n_observe_felts; i++) ch.observe(st->observe_felts[i]);
     ch.observe(k);
     for (u32 i = 0; i < k; i++) ch.observe(log_heights[i]);
@@ -693,6 +719,44 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     for (auto& a : airs) max_rand = std::max(max_rand, a.desc.num_randomness);
     for (u32 i = 0; i < max_rand; i++) randomness.push_back(tr.ch.sample_ext());
     in_proof = true;
+}
+
+// Preprocessed::build (preprocessed.rs:63-131): the declared matrices sorted by (height, AIR index), coset LDE on
+// the canonical shift of their own height, one aligned LMCS tree.  Kept on the device until replaced.
+void mdn_session::set_preprocessed(const mdn_statement* st, const mdn_matrix* mats) {
+    if (in_proof) fail(MDN_ERR_INVALID_ARG, "set_preprocessed called inside a proof");
+    prep_c = Committed(); has_prep = false; prep_air.clear(); prep_log_h.clear();
+    if (!mats) return;
+    if (!st) fail(MDN_ERR_INVALID_ARG, "null argument");
+    u32 lb = params.log_blowup;
+    if (lb == 0 || lb > 4) fail(MDN_ERR_UNSUPPORTED, "log_blowup must be in 1..=4");
+    if (!d_flag.p) { d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
+    std::vector<u32> ids;
+    for (u32 i = 0; i < st->n_airs; i++) {
+        if (mats[i].width != st->airs[i].preprocessed_width) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed matrix width %u does not match the declared %u", i, mats[i].width, st->airs[i].preprocessed_width);
+        if (!mats[i].width) continue;
+        if (!mats[i].values) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed matrix is NULL", i);
+        if (mats[i].log_height + lb > 32) fail(MDN_ERR_DOMAIN, "LDE log order %u exceeds two-adicity 32", mats[i].log_height + lb);
+        ntt(mats[i].log_height);
+        ids.push_back(i);
+    }
+    if (ids.empty()) return;
+    std::stable_sort(ids.begin(), ids.end(), [&](u32 a, u32 b) { return mats[a].log_height < mats[b].log_height; });
+    size_t coef_total = 0, lde_total = 0;
+    for (u32 i : ids) { size_t N = (size_t)1 << mats[i].log_height; coef_total += N * mats[i].width; lde_total += (N << lb) * mats[i].width; }
+    prep_c.coef_buf.alloc(coef_total, stream); prep_c.lde_buf.alloc(lde_total, stream);
+    size_t co = 0, lo = 0;
+    for (u32 i : ids) {
+        size_t N = (size_t)1 << mats[i].log_height;
+        prep_c.mats.push_back(CommittedMat{prep_c.lde_buf.p + lo, prep_c.coef_buf.p + co, mats[i].log_height, mats[i].width});
+        co += N * mats[i].width; lo += (N << lb) * mats[i].width;
+        upload_matrix(mats[i], false, prep_c.mats.back().coef);
+    }
+    check_input_flag("a preprocessed trace");
+    lde_and_commit(prep_c, nullptr, nullptr);
+    prep_air = ids;
+    for (u32 i : ids) prep_log_h.push_back(mats[i].log_height);
+    has_prep = true;
 }
 
 // aux traces (instance order, EF flattened to base), aux values; commit + observe (mod.rs:397-422)
@@ -772,6 +836,8 @@ void mdn_session::finish() {
         mk::ConstraintArgs ca;
         ca.main_lde = main_c.mats[j].lde; ca.main_width = main_c.mats[j].width;
         ca.aux_lde = aux_c.mats[j].lde; ca.aux_width_base = aux_c.mats[j].width;
+        ca.prep_lde = nullptr;   // same height and coset as the main trace (mod.rs:463-476)
+        if (has_prep) for (size_t q = 0; q < prep_air.size(); q++) if (prep_air[q] == inst) ca.prep_lde = prep_c.mats[q].lde;
         ca.log_n = ln; ca.log_blowup = lb; ca.air = air.dev;
         ca.publics = d_publics.p; ca.challenges = d_randomness.p; ca.aux_values = d_aux_values.p + aux_values_off[j];
         ca.alpha = alpha; ca.beta = beta;
@@ -847,14 +913,18 @@ void mdn_session::finish() {
     // 7. PCS opening (pcs/prover.rs:34-102)
     // 7a. OOD evaluations of every committed column at z^(r_m), (z*w_H)^(r_m)
     //     (deep/interpolate.rs:127-203; computed here from the coefficient columns)
-    Committed* groups[3] = {&main_c, &aux_c, &quot_c};
+    // group order [preprocessed?, main, aux, quotient] (mod.rs:551-559)
+    std::vector<Committed*> groups;
+    if (has_prep) groups.push_back(&prep_c);
+    groups.push_back(&main_c); groups.push_back(&aux_c); groups.push_back(&quot_c);
+    const int ng = (int)groups.size(), gq = ng - 1;
     struct MatEval { std::vector<u64> v; };   // width x 4
-    std::vector<std::vector<MatEval>> evals(3);
+    std::vector<std::vector<MatEval>> evals(ng);
     {
         ProfScope ps_ood(prof, PC_OOD);
         // all dot products are queued first and fetched with ONE device->host copy
         size_t total_cols = 0;
-        for (int g = 0; g < 3; g++) for (auto& cm : groups[g]->mats) total_cols += cm.width;
+        for (int g = 0; g < ng; g++) for (auto& cm : groups[g]->mats) total_cols += cm.width;
         DevBuf d_out; d_out.alloc(std::max<size_t>(1, total_cols * 4), stream);
         std::vector<DevBuf> keep;                              // weight vectors / partial sums stay alive until the copy
         std::map<u32, std::pair<u64*, u64*>> weights;          // per log height: (w0, w1)
@@ -867,7 +937,7 @@ void mdn_session::finish() {
         };
         size_t col_off = 0;
         std::vector<std::pair<size_t, u64>> scale;             // (first u64 index, 1/N) per matrix
-        for (int g = 0; g < 3; g++) {
+        for (int g = 0; g < ng; g++) {
             evals[g].resize(groups[g]->mats.size());
             for (size_t m = 0; m < groups[g]->mats.size(); m++) {
                 CommittedMat& cm = groups[g]->mats[m];
@@ -876,7 +946,7 @@ void mdn_session::finish() {
                 u32 ln = cm.log_n, lr = log_max_n - ln;
                 size_t Nm = (size_t)1 << ln;
                 u32 n_chunks = (u32)std::max<size_t>(1, std::min<size_t>(Nm / 1024, 1024));
-                if (g < 2) {
+                if (g != gq) {
                     auto it = weights.find(ln);
                     if (it == weights.end()) it = weights.emplace(ln, make_w(ln, gl::e2_exp_pow2(z, lr), gl::e2_exp_pow2(z_next, lr))).first;
                     keep.emplace_back(); keep.back().alloc((size_t)cm.width * n_chunks * 4, stream);
@@ -902,7 +972,7 @@ void mdn_session::finish() {
         CUDA_OK(cudaMemcpyAsync(host.data(), d_out.p, host.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
         size_t si = 0;
-        for (int g = 0; g < 3; g++)
+        for (int g = 0; g < ng; g++)
             for (size_t m = 0; m < groups[g]->mats.size(); m++) {
                 CommittedMat& cm = groups[g]->mats[m];
                 if (!cm.width) continue;
@@ -914,7 +984,7 @@ void mdn_session::finish() {
     std::vector<E2> flat[2];
     std::vector<u32> aligned_off;   // per (group, matrix): offset in the aligned index space
     u32 W = 0;
-    for (int g = 0; g < 3; g++)
+    for (int g = 0; g < ng; g++)
         for (size_t m = 0; m < groups[g]->mats.size(); m++) {
             u32 w = groups[g]->mats[m].width, aw = (w + 7) / 8 * 8;
             aligned_off.push_back(W);
@@ -942,7 +1012,7 @@ void mdn_session::finish() {
     {
         mk::DeepArgs da; da.n_mats = 0;
         size_t mi = 0;
-        for (int g = 0; g < 3; g++)
+        for (int g = 0; g < ng; g++)
             for (size_t m = 0; m < groups[g]->mats.size(); m++, mi++) {
                 CommittedMat& cm = groups[g]->mats[m];
                 if (!cm.width) continue;
@@ -1037,7 +1107,7 @@ void mdn_session::finish() {
     std::vector<int> sib_owner;   // per input-tree sibling (emission order): owning rank or -1 (replicated)
     struct Emit { int kind; size_t count; size_t pad; };   // kind 0: `count` fields then `pad` zero fields; 1: commitment (4)
     std::vector<Emit> plan;
-    for (int g = 0; g < 3; g++) {
+    for (int g = 0; g < ng; g++) {
         Committed& c = *groups[g];
         Indices leafs = ti.folded(c.tree.depth);
         for (size_t idx : leafs.idx)
@@ -1175,6 +1245,7 @@ void mdn_session_destroy(mdn_session* s) {
     cudaSetDevice(s->device);
     // every stream-ordered allocation must be returned before the stream goes away
     s->reset_proof();
+    s->prep_c = Committed();
     s->d_publics.release(); s->d_randomness.release(); s->d_aux_values.release(); s->d_flag.release();
     s->ntt_plans.clear(); s->premul_plans.clear();
     cudaStreamSynchronize(s->stream);
@@ -1373,6 +1444,17 @@ int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_all
     if (world == 0 || (world & (world - 1)) || rank >= world || (world > 1 && !fn)) { s->error = "invalid shard configuration (world must be a power of two, callback required)"; return MDN_ERR_INVALID_ARG; }
     s->shard_rank = rank; s->shard_world = world; s->allgather = fn; s->allgather_ctx = ctx;
     s->shard_log_g = 0; while ((1u << s->shard_log_g) < world) s->shard_log_g++;
+    return MDN_OK;
+}
+
+int mdn_session_set_preprocessed(mdn_session* s, const mdn_statement* st, const mdn_matrix* preprocessed, uint64_t commitment_out[4]) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    try {
+        CUDA_OK(cudaSetDevice(s->device));
+        s->set_preprocessed(st, preprocessed);
+        if (commitment_out) { if (s->has_prep) memcpy(commitment_out, s->prep_c.root, 32); else memset(commitment_out, 0, 32); }
+    } catch (const MdnError& e) { s->error = e.what(); s->prep_c = Committed(); s->has_prep = false; return e.code; }
+    catch (const std::exception& e) { s->error = e.what(); s->prep_c = Committed(); s->has_prep = false; return MDN_ERR_INVALID_ARG; }
     return MDN_OK;
 }
 

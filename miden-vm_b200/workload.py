@@ -58,7 +58,7 @@ class Workload:
 
     def __init__(self, log_heights, widths=MIDEN_WIDTHS, aux_widths=MIDEN_AUX_WIDTHS, seed=SEED,
                  programs=None, num_randomness=2, public_values=(), log_quotient_degrees=None, traces=None,
-                 num_aux_values=None, periodic=None):
+                 num_aux_values=None, periodic=None, preprocessed=None):
         self.k = len(log_heights)
         self.log_heights = list(log_heights)
         self.widths = list(widths)[: self.k]
@@ -83,6 +83,15 @@ class Workload:
                 a.periodic_values = per.ctypes.data_as(u64p)
                 a.num_periodic_columns = per.shape[1]
                 a.log_max_period = int(per.shape[0]).bit_length() - 1
+        # BaseAir::preprocessed_trace per AIR (None = the AIR declares none); same height as the main trace
+        self.preprocessed = None
+        if preprocessed is not None and any(m is not None for m in preprocessed):
+            self.preprocessed = [None if m is None else np.ascontiguousarray(m, dtype=np.uint64) for m in preprocessed]
+            self.preprocessed_matrices = (Matrix * self.k)()
+            for i, m in enumerate(self.preprocessed):
+                if m is not None:
+                    self._airs[i].preprocessed_width = m.shape[1]
+                    self.preprocessed_matrices[i] = Matrix(m.ctypes.data_as(u64p), self.log_heights[i], m.shape[1])
         self.public_values = np.array(list(public_values), dtype=np.uint64)
         # default MultiAir::observe: len(air_inputs), air_inputs, max_aux_inputs (0), len(aux_inputs) (0)
         self.observe_felts = np.array([len(self.public_values), *self.public_values, 0, 0], dtype=np.uint64)

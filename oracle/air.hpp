@@ -29,6 +29,7 @@ enum AirOp : uint32_t {
     OP_ADD = 10, OP_SUB = 11, OP_MUL = 12,  // a, b = node ids; EF if either is EF
     OP_NEG = 13,        // a = node id
     OP_PERIODIC = 14,   // a = periodic column index                               -> F
+    OP_PREPROCESSED = 15,  // a = row offset, b = preprocessed column                 -> F
 };
 
 struct AirNode { uint32_t op, a, b; };
@@ -64,7 +65,7 @@ struct AirProgram {
                     if (nd.a >= i) throw std::runtime_error("air program: forward reference");
                     p.is_ext[i] = p.is_ext[nd.a]; break;
                 default:
-                    if (nd.op > OP_PERIODIC) throw std::runtime_error("air program: unknown op");
+                    if (nd.op > OP_PREPROCESSED) throw std::runtime_error("air program: unknown op");
                     p.is_ext[i] = 0;
             }
         }
@@ -79,6 +80,8 @@ struct AirPoint {
     const Fp* aux_local; const Fp* aux_next;   // base-field layout: EF column c = (aux[2c], aux[2c+1])
     const Fp* publics; const Ef* challenges; const Ef* aux_values;
     const Ef* periodic = nullptr;              // periodic column values at this point
+    const Fp* prep_local = nullptr; const Fp* prep_next = nullptr;        // preprocessed window (base)
+    const Ef* prep_local_ef = nullptr; const Ef* prep_next_ef = nullptr;  // ... at the OOD point
     Ef is_first, is_last, is_transition;       // EF so the same evaluator serves the OOD check
     // For the OOD check main/aux cells are EF; then these are used instead of the Fp pointers.
     const Ef* main_local_ef = nullptr; const Ef* main_next_ef = nullptr;
@@ -113,6 +116,10 @@ inline Ef air_eval_folded(const AirProgram& p, const AirPoint& pt, Ef alpha, std
             case OP_MUL: v = scratch[nd.a] * scratch[nd.b]; break;
             case OP_NEG: v = -scratch[nd.a]; break;
             case OP_PERIODIC: v = pt.periodic[nd.a]; break;
+            case OP_PREPROCESSED:
+                if (pt.prep_local_ef) v = (nd.a ? pt.prep_next_ef : pt.prep_local_ef)[nd.b];
+                else v = Ef((nd.a ? pt.prep_next : pt.prep_local)[nd.b]);
+                break;
         }
         scratch[i] = v;
     }

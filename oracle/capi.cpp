@@ -24,7 +24,7 @@ extern "C" {
 struct orc_pcs_params { uint32_t log_blowup, log_folding_arity, log_final_degree, folding_pow_bits, deep_pow_bits, num_queries, query_pow_bits; };
 struct orc_challenger { uint64_t sponge_state[12]; uint64_t input_buffer[8]; uint32_t input_len, output_len; };
 struct orc_air { uint32_t width, aux_width, num_aux_values, num_randomness, log_quotient_degree, program_words; const uint32_t* program;
-                 const uint64_t* periodic_values; uint32_t num_periodic_columns, log_max_period; };
+                 const uint64_t* periodic_values; uint32_t num_periodic_columns, log_max_period, preprocessed_width; };
 struct orc_matrix { const uint64_t* values; uint32_t log_height, width; };
 struct orc_statement { const orc_air* airs; uint32_t n_airs; const uint64_t* public_values; uint32_t n_public_values; const uint64_t* observe_felts; uint32_t n_observe_felts; };
 typedef int (*orc_aux_builder)(void* ctx, uint32_t instance, const orc_matrix* main, const uint64_t* randomness, uint64_t* aux_out, uint64_t* aux_values);
@@ -122,7 +122,7 @@ static Statement to_statement(const orc_statement* st) {
         d.width = a.width; d.aux_width = a.aux_width; d.num_aux_values = a.num_aux_values;
         d.num_randomness = a.num_randomness; d.log_quotient_degree = a.log_quotient_degree;
         d.program = AirProgram::parse(a.program, a.program_words);
-        d.n_periodic = a.num_periodic_columns; d.log_max_period = a.log_max_period;
+        d.n_periodic = a.num_periodic_columns; d.log_max_period = a.log_max_period; d.preprocessed_width = a.preprocessed_width;
         for (size_t q = 0; q < ((size_t)a.num_periodic_columns << a.log_max_period); q++) d.periodic.push_back(Fp(a.periodic_values[q]));
         for (auto& nd : d.program.nodes) if (nd.op == OP_PERIODIC && nd.a >= d.n_periodic) throw std::runtime_error("air program: periodic column out of range");
         s.airs.push_back(std::move(d));
@@ -146,11 +146,14 @@ static PcsParams to_params(const orc_pcs_params* p) {
     return q;
 }
 
-// Full prove.  Returns an opaque handle (NULL on error); `out` points into it.
-void* orc_prove(const orc_pcs_params* params, const orc_statement* st, const orc_matrix* traces,
-                const orc_challenger* challenger, orc_aux_builder cb, void* ctx, orc_proof* out) {
+// Full prove.  Returns an opaque handle (NULL on error); `out` points into it.  `preprocessed` (may be NULL):
+// one matrix per AIR in instance order, width 0 = none.
+void* orc_prove_pp(const orc_pcs_params* params, const orc_statement* st, const orc_matrix* traces, const orc_matrix* preprocessed,
+                   const orc_challenger* challenger, orc_aux_builder cb, void* ctx, orc_proof* out, uint64_t* prep_commitment_out) {
     try {
         Statement s = to_statement(st);
+        if (preprocessed) for (uint32_t i = 0; i < st->n_airs; i++) s.preprocessed.push_back(preprocessed[i].width ? to_matrix(preprocessed[i]) : Matrix());
+        if (preprocessed && prep_commitment_out && s.has_preprocessed()) { PreprocessedBundle b = build_preprocessed(s, params->log_blowup); for (int i = 0; i < 4; i++) prep_commitment_out[i] = b.tree.root()[i].v; }
         std::vector<Matrix> tr;
         for (uint32_t i = 0; i < st->n_airs; i++) tr.push_back(to_matrix(traces[i]));
         AuxBuilder ab;
@@ -172,6 +175,10 @@ void* orc_prove(const orc_pcs_params* params, const orc_statement* st, const orc
         out->commitments = res->commitments.data(); out->n_commitments = res->proof.commitments.size();
         return res;
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void* orc_prove(const orc_pcs_params* params, const orc_statement* st, const orc_matrix* traces,
+                const orc_challenger* challenger, orc_aux_builder cb, void* ctx, orc_proof* out) {
+    return orc_prove_pp(params, st, traces, nullptr, challenger, cb, ctx, out, nullptr);
 }
 void orc_prove_free(void* h) { delete (orc_prove_result*)h; }
 
@@ -197,7 +204,8 @@ long long orc_prove_info(void* h, int what, uint64_t* out, size_t cap) {
 }
 
 // Verify a proof given as raw streams.  0 = accepted; -1 = rejected (orc_last_error has the reason).
-int orc_verify(const orc_pcs_params* params, const orc_statement* st, const orc_proof* pf, const orc_challenger* challenger) {
+int orc_verify_pp(const orc_pcs_params* params, const orc_statement* st, const orc_proof* pf, const orc_challenger* challenger,
+                  const uint64_t* prep_commitment) {
     try {
         Statement s = to_statement(st);
         Proof p;
@@ -210,9 +218,13 @@ int orc_verify(const orc_pcs_params* params, const orc_statement* st, const orc_
             Digest d; for (int k = 0; k < 4; k++) d[k] = Fp(pf->commitments[4 * i + k]);
             p.commitments.push_back(d);
         }
-        stark_verify(to_params(params), s, p, to_challenger(challenger));
+        Digest pc; if (prep_commitment) for (int k = 0; k < 4; k++) pc[k] = Fp(prep_commitment[k]);
+        stark_verify(to_params(params), s, p, to_challenger(challenger), prep_commitment ? &pc : nullptr);
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+int orc_verify(const orc_pcs_params* params, const orc_statement* st, const orc_proof* pf, const orc_challenger* challenger) {
+    return orc_verify_pp(params, st, pf, challenger, nullptr);
 }
 
 }  // extern "C"

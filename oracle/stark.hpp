@@ -46,6 +46,7 @@ struct AirDesc {
     AirProgram program;
     // periodic_columns_matrix(): max_period x n_periodic, row-major (prover/periodic.rs:49-98)
     std::vector<Fp> periodic; size_t n_periodic = 0; unsigned log_max_period = 0;
+    size_t preprocessed_width = 0;       // BaseAir::preprocessed_width
     // coefficients (ascending) of periodic column c over the size-max_period subgroup
     std::vector<std::vector<Fp>> periodic_coeffs() const {
         size_t mp = size_t(1) << log_max_period;
@@ -68,7 +69,13 @@ struct Statement {
     std::vector<AirDesc> airs;           // instance order
     std::vector<Fp> public_values;       // shared air_inputs
     std::vector<Fp> observe_felts;       // what `Statement::observe` absorbs (host/AIR specific)
+    // BaseAir::preprocessed_trace per AIR (instance order; empty matrix = none): setup-fixed columns
+    // committed once (preprocessed.rs:41-110) and observed before everything else (prover/mod.rs:282-286)
+    std::vector<Matrix> preprocessed;
+    bool has_preprocessed() const { for (auto& m : preprocessed) if (m.width) return true; return false; }
 };
+
+
 
 struct Proof {
     std::vector<uint8_t> log_trace_heights;   // instance order (proof.rs:57-63)
@@ -121,10 +128,22 @@ inline LmcsTree commit_traces(const std::vector<Matrix>& traces_proof_order, uns
     return LmcsTree::build(std::move(ldes), 8);   // build_aligned_tree: alignment = RATE
 }
 
+// Preprocessed::build (preprocessed.rs:41-110): AIRs with preprocessed columns sorted by (height, air index),
+// LDE by the blowup on the canonical coset, aligned LMCS tree.  `air_of[i]` = AIR backing committed trace i.
+struct PreprocessedBundle { LmcsTree tree; std::vector<size_t> air_of; std::vector<Matrix> traces; };
+inline PreprocessedBundle build_preprocessed(const Statement& st, unsigned log_blowup) {
+    PreprocessedBundle b;
+    for (size_t i = 0; i < st.preprocessed.size(); i++) if (st.preprocessed[i].width) b.air_of.push_back(i);
+    std::stable_sort(b.air_of.begin(), b.air_of.end(), [&](size_t x, size_t y) { return st.preprocessed[x].height < st.preprocessed[y].height; });
+    for (size_t a : b.air_of) b.traces.push_back(st.preprocessed[a]);
+    b.tree = commit_traces(b.traces, log_blowup);
+    return b;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Constraint evaluation on gJ_j, natural order (constraints/mod.rs:83-278)
 // ---------------------------------------------------------------------------------------------
-inline std::vector<Ef> eval_quotient(const AirDesc& air, const Matrix& main_lde, const Matrix& aux_lde,
+inline std::vector<Ef> eval_quotient(const AirDesc& air, const Matrix& main_lde, const Matrix& aux_lde, const Matrix* prep_lde,
                                      unsigned log_n, unsigned log_blowup, Ef alpha,
                                      const std::vector<Ef>& randomness, const std::vector<Fp>& publics,
                                      const std::vector<Ef>& aux_values) {
@@ -160,6 +179,7 @@ inline std::vector<Ef> eval_quotient(const AirDesc& air, const Matrix& main_lde,
             pt.main_local = main_lde.row(pl); pt.main_next = main_lde.row(pn);
             pt.aux_local = aux_lde.width ? aux_lde.row(pl) : nullptr;
             pt.aux_next = aux_lde.width ? aux_lde.row(pn) : nullptr;
+            if (prep_lde) { pt.prep_local = prep_lde->row(pl); pt.prep_next = prep_lde->row(pn); }
             pt.publics = publics.data(); pt.challenges = randomness.data(); pt.aux_values = aux_values.data();
             Fp z = zh[i & (D - 1)];
             pt.is_first = Ef(z * d_first[i]); pt.is_last = Ef(z * d_last[i]); pt.is_transition = Ef(xs[i] - omega_h_inv);
@@ -418,7 +438,19 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
     TraceOrder ord = TraceOrder::make(lh);
     unsigned log_max_n = ord.max_log_height();
     unsigned lb = params.log_blowup;
-    // statement.observe + observe_shape (mod.rs:290-291; order.rs:154-163)
+    // preprocessed commitment first (mod.rs:282-286), then statement.observe + observe_shape (:290-291)
+    PreprocessedBundle prep;
+    bool has_prep = st.has_preprocessed();
+    if (has_prep) {
+        for (size_t i = 0; i < k; i++) {
+            bool want = st.airs[i].preprocessed_width > 0, have = i < st.preprocessed.size() && st.preprocessed[i].width > 0;
+            if (want != have) throw std::runtime_error("prove: preprocessed presence mismatch");
+            if (have && (st.preprocessed[i].width != st.airs[i].preprocessed_width || st.preprocessed[i].height != traces[i].height))
+                throw std::runtime_error("prove: preprocessed shape mismatch");
+        }
+        prep = build_preprocessed(st, lb);
+        challenger.observe_digest(prep.tree.root());
+    }
     for (Fp f : st.observe_felts) challenger.observe(f);
     challenger.observe(Fp::raw((u64)k));
     for (size_t i = 0; i < k; i++) challenger.observe(Fp::raw((u64)lh[i]));
@@ -459,7 +491,9 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
         const AirDesc& air = st.airs[ord.proof_to_instance[j]];
         unsigned ln = lh[ord.proof_to_instance[j]];
         std::vector<Ef> r(randomness.begin(), randomness.begin() + air.num_randomness);
-        std::vector<Ef> q = eval_quotient(air, main_tree.leaves[j], aux_tree.leaves[j], ln, lb, alpha, r, st.public_values, auxv_p[j]);
+        const Matrix* pl = nullptr;
+        if (has_prep) for (size_t q2 = 0; q2 < prep.air_of.size(); q2++) if (prep.air_of[q2] == ord.proof_to_instance[j]) pl = &prep.tree.leaves[q2];
+        std::vector<Ef> q = eval_quotient(air, main_tree.leaves[j], aux_tree.leaves[j], pl, ln, lb, alpha, r, st.public_values, auxv_p[j]);
         q = upsample_evals(q, log_qd - air.log_quotient_degree);
         cyclic_extend_and_accumulate(acc, q, beta);
     }
@@ -498,6 +532,12 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
     }
     delete tco;
     std::vector<const LmcsTree*> trees{&main_tree, &aux_tree, &q_tree};
+    if (has_prep) {   // group order [preprocessed, main, aux, quotient] (mod.rs:551-559)
+        trees.insert(trees.begin(), &prep.tree);
+        std::vector<Matrix> pc;
+        for (const Matrix& t : prep.traces) { Matrix c = t; idft_rows(c); pc.push_back(std::move(c)); }
+        coeffs.insert(coeffs.begin(), std::move(pc));
+    }
     if (dbg) {
         dbg->main_root = main_tree.root(); dbg->aux_root = aux_tree.root(); dbg->quotient_root = q_tree.root();
         dbg->randomness = randomness; dbg->alpha = alpha; dbg->beta = beta; dbg->z = z; dbg->quotient_acc = acc;
@@ -513,12 +553,17 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
 // ---------------------------------------------------------------------------------------------
 // verify()  (verifier/mod.rs:153-…)
 // ---------------------------------------------------------------------------------------------
-inline void stark_verify(const PcsParams& params, const Statement& st, const Proof& pf, Challenger challenger) {
+inline void stark_verify(const PcsParams& params, const Statement& st, const Proof& pf, Challenger challenger,
+                         const Digest* preprocessed_commitment = nullptr) {
     size_t k = st.airs.size();
     if (pf.log_trace_heights.size() != k) throw std::runtime_error("verify: height count");
     std::vector<unsigned> lh(pf.log_trace_heights.begin(), pf.log_trace_heights.end());
     TraceOrder ord = TraceOrder::make(lh);
     unsigned log_max_n = ord.max_log_height(), lb = params.log_blowup, log_lde = log_max_n + lb;
+    bool has_prep = false;
+    for (auto& a : st.airs) has_prep |= a.preprocessed_width > 0;
+    if (has_prep != (preprocessed_commitment != nullptr)) throw std::runtime_error("verify: preprocessed presence mismatch");
+    if (has_prep) challenger.observe_digest(*preprocessed_commitment);
     for (Fp f : st.observe_felts) challenger.observe(f);
     challenger.observe(Fp::raw((u64)k));
     for (size_t i = 0; i < k; i++) challenger.observe(Fp::raw((u64)lh[i]));
@@ -550,14 +595,28 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
     Fp omega_h = two_adic_generator(log_max_n);
     Ef pts[2] = {z, z * omega_h};
 
-    struct Group { Digest root; std::vector<size_t> widths, aligned; };
+    struct Group { Digest root; std::vector<size_t> widths, aligned; unsigned log_height; };
     std::vector<Group> groups(3);
     groups[0].root = main_root; groups[1].root = aux_root; groups[2].root = q_root;
+    for (auto& g : groups) g.log_height = log_lde;
     for (size_t j = 0; j < k; j++) {
         const AirDesc& air = st.airs[ord.proof_to_instance[j]];
         groups[0].widths.push_back(air.width); groups[1].widths.push_back(2 * air.aux_width);
     }
     groups[2].widths.push_back(2 * D);
+    std::vector<size_t> prep_pos(k, (size_t)-1);   // proof position -> index in the preprocessed group
+    if (has_prep) {   // committed preprocessed traces = preprocessed AIRs in proof order (verifier/mod.rs)
+        Group pg; pg.root = *preprocessed_commitment; pg.log_height = 0;
+        for (size_t j = 0; j < k; j++) {
+            const AirDesc& air = st.airs[ord.proof_to_instance[j]];
+            if (!air.preprocessed_width) continue;
+            prep_pos[j] = pg.widths.size();
+            pg.widths.push_back(air.preprocessed_width);
+            pg.log_height = std::max(pg.log_height, lh[ord.proof_to_instance[j]] + lb);
+        }
+        groups.insert(groups.begin(), pg);
+    }
+    const size_t gm = has_prep ? 1 : 0;   // index of the main group
     for (auto& g : groups) for (size_t w : g.widths) g.aligned.push_back(aligned_len(w, 8));
 
     // --- DEEP oracle (pcs/deep/verifier.rs): read evals, grind, alpha/beta, reduced openings
@@ -590,7 +649,7 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
     std::map<size_t, Ef> reduced_rows;
     for (size_t i : ti.idx) reduced_rows[i] = Ef();
     for (auto& g : groups) {
-        auto rows = lmcs_open_lifted_batch(g.root, g.aligned, ti, log_lde, ch);
+        auto rows = lmcs_open_lifted_batch(g.root, g.aligned, ti, g.log_height, ch);
         for (auto& kv : reduced_rows) { Ef a = kv.second; for (Fp f : rows.at(kv.first)) a = a * dalpha + Ef(f); kv.second = a; }
     }
     std::map<size_t, Ef> fevals;
@@ -631,10 +690,10 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
     }
     // --- constraint check at z (verifier/mod.rs step 9-12)
     size_t off = 0;
-    std::vector<size_t> goff(3);
-    for (size_t g = 0; g < 3; g++) { goff[g] = off; for (size_t w : groups[g].aligned) off += w; }
+    std::vector<size_t> goff(groups.size());
+    for (size_t g = 0; g < groups.size(); g++) { goff[g] = off; for (size_t w : groups[g].aligned) off += w; }
     Ef accumulated;
-    size_t moff = goff[0], aoff = goff[1];
+    size_t moff = goff[gm], aoff = goff[gm + 1];
     std::vector<Ef> scratch;
     for (size_t j = 0; j < k; j++) {
         const AirDesc& air = st.airs[ord.proof_to_instance[j]];
@@ -655,6 +714,14 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
         Fp ohi = fp_inv(two_adic_generator(ln));
         AirPoint pt{};
         pt.main_local_ef = ml.data(); pt.main_next_ef = mn.data(); pt.aux_local_ef = al.data(); pt.aux_next_ef = an.data();
+        std::vector<Ef> ppl, ppn;
+        if (has_prep && prep_pos[j] != (size_t)-1) {
+            size_t po = goff[0];
+            for (size_t q2 = 0; q2 < prep_pos[j]; q2++) po += groups[0].aligned[q2];
+            ppl.assign(evals[0].begin() + po, evals[0].begin() + po + air.preprocessed_width);
+            ppn.assign(evals[1].begin() + po, evals[1].begin() + po + air.preprocessed_width);
+            pt.prep_local_ef = ppl.data(); pt.prep_next_ef = ppn.data();
+        }
         std::vector<Ef> r(randomness.begin(), randomness.begin() + air.num_randomness);
         pt.publics = st.public_values.data(); pt.challenges = r.data(); pt.aux_values = auxv[j].data();
         pt.is_first = van * ef_inv(zl - Fp::raw(1)); pt.is_last = van * ef_inv(zl - ohi); pt.is_transition = zl - ohi;
@@ -671,7 +738,7 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
     {
         Ef u(Fp(), Fp::raw(1));
         std::vector<Ef> chunks;
-        for (size_t t = 0; t < D; t++) chunks.push_back(evals[0][goff[2] + 2 * t] + u * evals[0][goff[2] + 2 * t + 1]);
+        for (size_t t = 0; t < D; t++) chunks.push_back(evals[0][goff[gm + 2] + 2 * t] + u * evals[0][goff[gm + 2] + 2 * t + 1]);
         Fp omega_s = two_adic_generator(log_qd);
         Ef uu = ef_exp_pow2(z * sinv, log_max_n);
         Ef num, den; Fp ost = Fp::raw(1);

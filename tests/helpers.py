@@ -29,8 +29,14 @@ def oracle_prove(params, wl, challenger, aux_builder=None):
     """Run the oracle prover on a Workload; returns (handle, heights, fields, commitments)."""
     proof = ob.Proof()
     cb = ob.AUX_BUILDER(aux_builder) if aux_builder is not None else C.cast(None, ob.AUX_BUILDER)
-    h = ob.lib().orc_prove(cast(params, ob.PcsParams), cast(wl.statement, ob.Statement), cast(wl.matrices, ob.Matrix),
-                           cast(challenger, ob.Challenger), cb, None, C.byref(proof))
+    if getattr(wl, "preprocessed", None) is not None:
+        wl.oracle_prep_commitment = np.zeros(4, dtype=np.uint64)
+        h = ob.lib().orc_prove_pp(cast(params, ob.PcsParams), cast(wl.statement, ob.Statement), cast(wl.matrices, ob.Matrix),
+                                  cast(wl.preprocessed_matrices, ob.Matrix), cast(challenger, ob.Challenger), cb, None,
+                                  C.byref(proof), ob.ptr(wl.oracle_prep_commitment))
+    else:
+        h = ob.lib().orc_prove(cast(params, ob.PcsParams), cast(wl.statement, ob.Statement), cast(wl.matrices, ob.Matrix),
+                               cast(challenger, ob.Challenger), cb, None, C.byref(proof))
     if not h:
         raise RuntimeError(ob.lib().orc_last_error().decode())
     heights = bytes(proof.log_trace_heights[: proof.n_heights])
@@ -46,11 +52,18 @@ def oracle_info(h, what):
     return out
 
 
-def oracle_verify(params, wl, challenger, heights, fields, comms):
+def oracle_verify(params, wl, challenger, heights, fields, comms, prep_commitment=None):
     hb = (C.c_uint8 * len(heights))(*heights)
     fields = np.ascontiguousarray(fields, dtype=np.uint64)
     comms = np.ascontiguousarray(comms, dtype=np.uint64)
     pf = ob.Proof(hb, len(heights), ob.ptr(fields), len(fields), ob.ptr(comms.reshape(-1)), len(comms))
-    rc = ob.lib().orc_verify(cast(params, ob.PcsParams), cast(wl.statement, ob.Statement), C.byref(pf),
-                             cast(challenger, ob.Challenger))
+    if prep_commitment is None and getattr(wl, "preprocessed", None) is not None:
+        prep_commitment = wl.oracle_prep_commitment
+    if prep_commitment is not None:
+        pc = np.ascontiguousarray(prep_commitment, dtype=np.uint64)
+        rc = ob.lib().orc_verify_pp(cast(params, ob.PcsParams), cast(wl.statement, ob.Statement), C.byref(pf),
+                                    cast(challenger, ob.Challenger), ob.ptr(pc))
+    else:
+        rc = ob.lib().orc_verify(cast(params, ob.PcsParams), cast(wl.statement, ob.Statement), C.byref(pf),
+                                 cast(challenger, ob.Challenger))
     return rc, ob.lib().orc_last_error().decode()

@@ -24,7 +24,8 @@ class Air(C.Structure):
     _fields_ = [("width", C.c_uint32), ("aux_width", C.c_uint32), ("num_aux_values", C.c_uint32),
                 ("num_randomness", C.c_uint32), ("log_quotient_degree", C.c_uint32),
                 ("program_words", C.c_uint32), ("program", u32p),
-                ("periodic_values", u64p), ("num_periodic_columns", C.c_uint32), ("log_max_period", C.c_uint32)]
+                ("periodic_values", u64p), ("num_periodic_columns", C.c_uint32), ("log_max_period", C.c_uint32),
+                ("preprocessed_width", C.c_uint32)]
 
 
 class Matrix(C.Structure):
@@ -73,6 +74,11 @@ def lib():
         L.orc_prove.restype = C.c_void_p
         L.orc_prove.argtypes = [C.POINTER(PcsParams), C.POINTER(Statement), C.POINTER(Matrix),
                                 C.POINTER(Challenger), AUX_BUILDER, C.c_void_p, C.POINTER(Proof)]
+        L.orc_prove_pp.restype = C.c_void_p
+        L.orc_prove_pp.argtypes = [C.POINTER(PcsParams), C.POINTER(Statement), C.POINTER(Matrix), C.POINTER(Matrix),
+                                   C.POINTER(Challenger), AUX_BUILDER, C.c_void_p, C.POINTER(Proof), u64p]
+        L.orc_verify_pp.restype = C.c_int
+        L.orc_verify_pp.argtypes = [C.POINTER(PcsParams), C.POINTER(Statement), C.POINTER(Proof), C.POINTER(Challenger), u64p]
         L.orc_prove_free.argtypes = [C.c_void_p]
         L.orc_prove_info.restype = C.c_longlong
         L.orc_prove_info.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t]

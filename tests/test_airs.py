@@ -101,6 +101,36 @@ def periodic_workload(log_h: int, lqd: int = 3):
     return wl
 
 
+def preprocessed_workload(log_hs=(6, 8), with_prep=(True, True), lqd: int = 1):
+    """AIRs with preprocessed columns (fixed lookup/selector data, preprocessed.rs): for an AIR with them,
+    main[0] = prep[0] * main[1] and main[2] = prep_next[1] + main[1]; otherwise the Fibonacci-free identity
+    main[0] = main[1] * main[2].  Heights may differ, so the preprocessed tree is shorter than the max LDE
+    domain when only the short AIR declares preprocessed columns (virtual lifting, pcs/prover.rs:22-24)."""
+    traces, progs, preps, widths = [], [], [], []
+    for i, (lh, wp) in enumerate(zip(log_hs, with_prep)):
+        n = 1 << lh
+        t = W.synthetic_trace(20 + i, lh, 3)
+        b = AP.ProgramBuilder()
+        if wp:
+            pm = W.synthetic_trace(40 + i, lh, 2)
+            for r in range(n):
+                c1 = int(t[r, 1])
+                t[r, 0] = int(pm[r, 0]) * c1 % P
+                t[r, 2] = (int(pm[(r + 1) % n, 1]) + c1) % P
+            b.assert_zero(b.main(0, 0) - b.preprocessed(0, 0) * b.main(0, 1))
+            b.assert_zero(b.main(0, 2) - b.preprocessed(1, 1) - b.main(0, 1))
+            preps.append(pm)
+        else:
+            for r in range(n):
+                t[r, 0] = int(t[r, 1]) * int(t[r, 2]) % P
+            b.assert_zero(b.main(0, 0) - b.main(0, 1) * b.main(0, 2))
+            preps.append(None)
+        traces.append(t); progs.append(b.serialize()); widths.append(3)
+    k = len(log_hs)
+    return W.Workload(list(log_hs), widths=widths, aux_widths=[0] * k, programs=progs, traces=traces,
+                      log_quotient_degrees=[lqd] * k, num_aux_values=[0] * k, preprocessed=preps)
+
+
 def big_program_workload(log_h: int, n_terms: int = 300, seed: int = 3, lqd: int = 3):
     """A program with thousands of nodes whose constraints vanish identically (E - E' with E, E' built
     separately), exercising the liveness-based slot allocation of the constraint interpreter."""

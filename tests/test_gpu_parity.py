@@ -197,6 +197,37 @@ def test_prove_periodic_columns(sess_fast):
     _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=3))
 
 
+@pytest.mark.parametrize("log_hs,with_prep", [((6, 8), (True, True)), ((5, 7), (True, False)), ((5, 7), (False, True)),
+                                              ((6, 6, 4), (True, False, True)), ((12, 13), (True, True))])
+def test_prove_preprocessed_columns(log_hs, with_prep):
+    # Preprocessed::build on the device, commitment == oracle's, then bit-exact proofs with the
+    # preprocessed group first in the opening batch (shorter than the max LDE in case 2)
+    import test_airs
+    wl = test_airs.preprocessed_workload(log_hs, with_prep)
+    params = W.fast_pcs_params()
+    s = B.Session(params, device=0)
+    B.lib().mdn_set_debug(s.handle, 1)
+    commitment = s.set_preprocessed(wl.statement, wl.preprocessed_matrices)
+    _compare_proofs(s, params, wl)
+    assert np.array_equal(commitment, wl.oracle_prep_commitment)
+    # the bundle is borrowed across proofs: a second proof is identical
+    _compare_proofs(s, params, wl)
+    # presence parity (PreprocessedValidationError::PresenceMismatch)
+    ch = W.initial_challenger(params, prod_observe)
+    plain = W.Workload([5], widths=(9,), aux_widths=(1,))
+    with pytest.raises(B.ProverError):
+        s.prove(plain.statement, plain.matrices, ch)
+    s.set_preprocessed(None, None)
+    with pytest.raises(B.ProverError):
+        s.prove(wl.statement, wl.matrices, ch)
+    _compare_proofs(s, params, plain)
+    # height mismatch between the bundle and the main traces
+    wl_short = test_airs.preprocessed_workload(tuple(h - 1 for h in log_hs), with_prep)
+    s.set_preprocessed(wl_short.statement, wl_short.preprocessed_matrices)
+    with pytest.raises(B.ProverError):
+        s.prove(wl.statement, wl.matrices, ch)
+
+
 def test_prove_big_constraint_program(sess_fast):
     # ~2.4k nodes per constraint pair: far above the old 256-node interpreter limit
     import test_airs

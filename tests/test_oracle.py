@@ -184,6 +184,25 @@ def test_prove_verify_periodic_columns():
     _roundtrip(W.fast_pcs_params(), test_airs.periodic_workload(4, lqd=3))
 
 
+@pytest.mark.parametrize("log_hs,with_prep", [((6, 8), (True, True)), ((5, 7), (True, False)), ((5, 7), (False, True)),
+                                              ((6, 6, 4), (True, False, True))])
+def test_prove_verify_preprocessed(log_hs, with_prep):
+    # Preprocessed tree first in the opening batch, shorter than the max LDE when only short AIRs declare one
+    import test_airs
+    wl = test_airs.preprocessed_workload(log_hs, with_prep)
+    params = W.fast_pcs_params()
+    heights, fields, comms = _roundtrip(params, wl)
+    ch = W.initial_challenger(params, H.oracle_observe)
+    wrong = wl.oracle_prep_commitment.copy(); wrong[1] ^= np.uint64(1)
+    assert H.oracle_verify(params, wl, ch, heights, fields, comms, prep_commitment=wrong)[0] != 0
+    # a trace that violates the preprocessed relation is rejected
+    wl2 = test_airs.preprocessed_workload(log_hs, with_prep)
+    i = with_prep.index(True)
+    wl2.traces[i][2, 0] ^= np.uint64(1)
+    h, hh, ff, cc = H.oracle_prove(params, wl2, ch); ob.lib().orc_prove_free(h)
+    assert H.oracle_verify(params, wl2, ch, hh, ff, cc)[0] != 0
+
+
 def test_prove_verify_big_program():
     import test_airs
     _roundtrip(W.fast_pcs_params(), test_airs.big_program_workload(4, n_terms=60))
