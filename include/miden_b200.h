@@ -65,6 +65,27 @@ typedef struct {
     uint32_t output_len;
 } mdn_challenger;
 
+/* Lowering of `LookupAir::eval` (air/src/lookup/builder.rs) for AIRs whose `build_aux_trace` is
+ * `build_logup_aux_trace` (air/src/lookup/aux_builder.rs:49-97).  When `mdn_air.lookup` is set, the aux trace
+ * and its committed final are built ON THE DEVICE from the resident main trace right after the randomness is
+ * sampled -- no host callback, no aux-trace upload for that AIR.
+ *   program words[0..5) = { 0x504B4C4D ("MLKP"), 1, n_nodes, n_interactions, n_consts }
+ *   nodes        : as in mdn_air.program, restricted to what a LookupBuilder exposes: MAIN, PUBLIC,
+ *                  CHALLENGE (0 = alpha, 1 = beta), CONST, EXT_CONST, ADD, SUB, MUL, NEG, PERIODIC
+ *   interactions : 4 words { aux column, flag node | 0xFFFFFFFF, multiplicity node, denominator node } --
+ *                  one per `LookupGroup::insert` / `LookupBatch::insert` after `LookupMessage::encode`; it
+ *                  contributes multiplicity/denominator to its column on every row where the (0/1) flag is
+ *                  non-zero (air/src/lookup/prover.rs:338-362,421-444)
+ *   consts       : (lo, hi) word pairs
+ * Output (aux_builder.rs:1-20,215-268): f_c(r) = sum of m/d over column c's active interactions at row r;
+ * aux[r][c] = f_c(r) for c > 0; aux[r][0] = sum_{r' < r} sum_c f_c(r'); aux value 0 = the total over all rows.
+ * Requires aux_width == num_columns (<= 16) and num_aux_values == 1; a zero denominator is an error. */
+typedef struct {
+    uint32_t num_columns;           /* LookupAir::num_columns() */
+    uint32_t program_words;
+    const uint32_t* program;
+} mdn_lookup;
+
 /* One AIR of the MultiAir (crates/lifted-air/src/air.rs:47-202 `LiftedAir`): shape + constraint
  * program.  `program` is the op-list lowering of `air.eval()`:
  *   words[0..5) = { 0x5249414D ("MAIR"), 1, n_nodes, n_constraints, n_consts }
@@ -92,6 +113,7 @@ typedef struct {
     uint32_t num_periodic_columns;
     uint32_t log_max_period;
     uint32_t preprocessed_width;    /* BaseAir::preprocessed_width(): 0 = the AIR declares no preprocessed columns */
+    const mdn_lookup* lookup;       /* NULL: the aux trace comes from the host (mdn_aux_builder / commit_aux) */
 } mdn_air;
 
 /* p3 RowMajorMatrix<Felt>: `values` has (1 << log_height) * width entries.  With

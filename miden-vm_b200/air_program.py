@@ -81,6 +81,55 @@ class ProgramBuilder:
         return np.array(w, dtype=np.uint32)
 
 
+LOOKUP_MAGIC = 0x504B4C4D
+NO_FLAG = 0xFFFFFFFF
+
+
+class LookupProgramBuilder(ProgramBuilder):
+    """Host-side lowering of `LookupAir::eval` (air/src/lookup/builder.rs) for the device aux build: the node
+    surface a `LookupBuilder` exposes (main window, periodic values, challenges alpha = challenge(0) and
+    beta = challenge(1), constants) and one record per interaction -- `insert(column, flag, multiplicity,
+    denominator)` is `LookupGroup::insert` / `LookupBatch::insert` after `LookupMessage::encode`."""
+
+    def __init__(self, num_columns: int):
+        super().__init__()
+        self.num_columns = num_columns
+        self.interactions: list[tuple[int, int, int, int]] = []
+
+    def bus_prefix(self, bus: int, max_message_width: int) -> Expr:
+        """`Challenges::new`: bus_prefix[i] = alpha + (i + 1) * beta^W (air/src/lookup/challenges.rs)."""
+        beta = self.challenge(1)
+        g = beta
+        for _ in range(max_message_width - 1):
+            g = g * beta
+        return self.challenge(0) + g * self.const(bus + 1)
+
+    def encode(self, bus: int, max_message_width: int, elems) -> Expr:
+        """`Challenges::encode`: bus_prefix[bus] + sum_i beta^i * elems[i]."""
+        acc = self.bus_prefix(bus, max_message_width)
+        bp = None
+        for i, e in enumerate(elems):
+            bp = self.const(1) if i == 0 else (self.challenge(1) if i == 1 else bp * self.challenge(1))
+            acc = acc + (e if i == 0 else bp * e)
+        return acc
+
+    def insert(self, column: int, flag, multiplicity: Expr, denominator: Expr):
+        self.interactions.append((column, NO_FLAG if flag is None else flag.id, multiplicity.id, denominator.id))
+
+    def assert_zero(self, e):  # pragma: no cover - a lookup description emits no constraints
+        raise TypeError("LookupBuilder has no assert_* surface")
+
+    def serialize(self) -> np.ndarray:
+        w = [LOOKUP_MAGIC, 1, len(self.nodes), len(self.interactions), len(self.consts)]
+        for n in self.nodes:
+            w += list(n)
+        for it in self.interactions:
+            w += list(it)
+        for c in self.consts:
+            w += [c & 0xFFFFFFFF, c >> 32]
+        return np.array(w, dtype=np.uint32)
+
+
 def dummy_miden_air() -> np.ndarray:
     """`local[0] * local[1] * ... * local[8] == 0` (testing/airs/miden.rs:57-62): degree 9, so
     log_quotient_degree = 3.  The fold starts from ONE exactly like the reference's `fold`."""

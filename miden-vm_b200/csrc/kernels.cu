@@ -491,6 +491,132 @@ int launch_constraints(const ConstraintArgs& a, cudaStream_t st) {
 }
 
 // =============================================================================================
+// LogUp aux trace (trace-domain interpreter + EF scan)
+// =============================================================================================
+template <int MAXS>
+__global__ void __launch_bounds__(128) k_logup_rows(LogupArgs a) {
+    size_t N = (size_t)1 << a.log_n;
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    size_t rn = (r + 1) & (N - 1);
+    size_t per_row = (r & (((size_t)1 << a.prog.log_max_period) - 1)) * a.prog.n_periodic;
+    E2 slot[MAXS];
+    E2 V[LOGUP_MAX_COLS], U[LOGUP_MAX_COLS];
+    for (u32 c = 0; c < a.n_cols; c++) { V[c] = gl::e2(0, 0); U[c] = gl::e2(1, 0); }
+    const uint4* code = reinterpret_cast<const uint4*>(a.prog.code);
+    for (u32 i = 0; i < a.prog.n_instr; i++) {
+        uint4 ins = code[i];
+        u32 op = ins.x & 0xff, ext = ins.x >> 8, x = ins.z, y = ins.w;
+        E2 v;
+        switch (op) {
+            case 0: v = gl::e2(a.main_cm[(size_t)y * N + (x ? rn : r)], 0); break;
+            case 2: v = gl::e2(a.publics[x], 0); break;
+            case 3: v = gl::e2(a.challenges[2 * x], a.challenges[2 * x + 1]); break;
+            case 8: v = gl::e2(a.prog.consts[x], 0); break;
+            case 9: v = gl::e2(a.prog.consts[x], a.prog.consts[x + 1]); break;
+            case 10: v = ext ? gl::e2_add(slot[x], slot[y]) : gl::e2(gl::add(slot[x].a, slot[y].a), 0); break;
+            case 11: v = ext ? gl::e2_sub(slot[x], slot[y]) : gl::e2(gl::sub(slot[x].a, slot[y].a), 0); break;
+            case 12: v = ext ? gl::e2_mul(slot[x], slot[y]) : gl::e2(gl::mul(slot[x].a, slot[y].a), 0); break;
+            case 13: v = ext ? gl::e2_neg(slot[x]) : gl::e2(gl::neg(slot[x].a), 0); break;
+            case 14: v = gl::e2(a.prog.periodic[per_row + x], 0); break;
+            default: {   // 17 EMIT
+                u32 c = ins.y, fs = x & 0xffffu, ms = x >> 16;
+                if (fs != 0xffffu && slot[fs].a == 0) continue;          // prover.rs:357: flag == 0 skips the push
+                E2 d = slot[y];
+                if (d.a == 0 && d.b == 0) { *a.bad_flag = 2; continue; }
+                u64 m = slot[ms].a;
+                V[c] = gl::e2_add(gl::e2_mul(V[c], d), gl::e2_mulf(U[c], m));
+                U[c] = gl::e2_mul(U[c], d);
+                continue;
+            }
+        }
+        slot[ins.y] = v;
+    }
+    E2 t = gl::e2(0, 0);
+    for (u32 c = 0; c < a.n_cols; c++) {
+        E2 f = V[c];
+        if (!(U[c].a == 1 && U[c].b == 0)) f = gl::e2_mul(V[c], gl::e2_inv(U[c]));
+        t = gl::e2_add(t, f);
+        if (c > 0) { a.aux_cm[(size_t)(2 * c) * N + r] = f.a; a.aux_cm[(size_t)(2 * c + 1) * N + r] = f.b; }
+    }
+    reinterpret_cast<ulonglong2*>(a.totals)[r] = make_ulonglong2(t.a, t.b);
+}
+int launch_logup_rows(const LogupArgs& a, cudaStream_t st) {
+    if (a.n_cols == 0 || a.n_cols > LOGUP_MAX_COLS) return -1;
+    size_t N = (size_t)1 << a.log_n;
+    unsigned blocks = (unsigned)((N + 127) / 128);
+    if (a.prog.n_slots <= 16) k_logup_rows<16><<<blocks, 128, 0, st>>>(a);
+    else if (a.prog.n_slots <= 64) k_logup_rows<64><<<blocks, 128, 0, st>>>(a);
+    else if (a.prog.n_slots <= 256) k_logup_rows<256><<<blocks, 128, 0, st>>>(a);
+    else if (a.prog.n_slots <= 1024) k_logup_rows<1024><<<blocks, 128, 0, st>>>(a);
+    else return -1;
+    COUNT_LAUNCH();
+    return 0;
+}
+
+// three-phase scan, 2048 rows per block (8 per thread): block totals -> serial scan of the (<= 2048) block
+// totals by one block -> per-block exclusive prefix with the block offset
+static constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
+__device__ __forceinline__ E2 ld_e2(const u64* p, size_t i) { ulonglong2 v = reinterpret_cast<const ulonglong2*>(p)[i]; return gl::e2(v.x, v.y); }
+__global__ void __launch_bounds__(SCAN_T) k_scan_block_totals(const u64* __restrict__ totals, size_t n, u64* __restrict__ block_sums) {
+    __shared__ u64 sh[2 * SCAN_T];
+    size_t base = (size_t)blockIdx.x * SCAN_B + (size_t)threadIdx.x * SCAN_E;
+    E2 s = gl::e2(0, 0);
+    for (int e = 0; e < SCAN_E; e++) if (base + e < n) s = gl::e2_add(s, ld_e2(totals, base + e));
+    sh[2 * threadIdx.x] = s.a; sh[2 * threadIdx.x + 1] = s.b;
+    __syncthreads();
+    for (int off = SCAN_T / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            sh[2 * threadIdx.x] = gl::add(sh[2 * threadIdx.x], sh[2 * (threadIdx.x + off)]);
+            sh[2 * threadIdx.x + 1] = gl::add(sh[2 * threadIdx.x + 1], sh[2 * (threadIdx.x + off) + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { block_sums[2 * blockIdx.x] = sh[0]; block_sums[2 * blockIdx.x + 1] = sh[1]; }
+}
+__global__ void k_scan_block_sums(u64* block_sums, size_t n_blocks, u64* final2) {
+    if (threadIdx.x || blockIdx.x) return;
+    E2 acc = gl::e2(0, 0);
+    for (size_t b = 0; b < n_blocks; b++) {
+        E2 v = gl::e2(block_sums[2 * b], block_sums[2 * b + 1]);
+        block_sums[2 * b] = acc.a; block_sums[2 * b + 1] = acc.b;
+        acc = gl::e2_add(acc, v);
+    }
+    final2[0] = acc.a; final2[1] = acc.b;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const u64* __restrict__ totals, size_t n, const u64* __restrict__ block_sums,
+                                                       u64* __restrict__ acc0, u64* __restrict__ acc1) {
+    __shared__ u64 sh[2 * SCAN_T];
+    size_t base = (size_t)blockIdx.x * SCAN_B + (size_t)threadIdx.x * SCAN_E;
+    E2 v[SCAN_E];
+    E2 s = gl::e2(0, 0);
+    for (int e = 0; e < SCAN_E; e++) { v[e] = base + e < n ? ld_e2(totals, base + e) : gl::e2(0, 0); s = gl::e2_add(s, v[e]); }
+    sh[2 * threadIdx.x] = s.a; sh[2 * threadIdx.x + 1] = s.b;
+    __syncthreads();
+    // Hillis-Steele inclusive scan of the per-thread sums
+    for (int off = 1; off < SCAN_T; off <<= 1) {
+        u64 a0 = 0, a1 = 0;
+        if ((int)threadIdx.x >= off) { a0 = sh[2 * (threadIdx.x - off)]; a1 = sh[2 * (threadIdx.x - off) + 1]; }
+        __syncthreads();
+        if ((int)threadIdx.x >= off) { sh[2 * threadIdx.x] = gl::add(sh[2 * threadIdx.x], a0); sh[2 * threadIdx.x + 1] = gl::add(sh[2 * threadIdx.x + 1], a1); }
+        __syncthreads();
+    }
+    E2 run = gl::e2(block_sums[2 * blockIdx.x], block_sums[2 * blockIdx.x + 1]);
+    if (threadIdx.x > 0) run = gl::e2_add(run, gl::e2(sh[2 * (threadIdx.x - 1)], sh[2 * (threadIdx.x - 1) + 1]));
+    for (int e = 0; e < SCAN_E; e++) {
+        if (base + e < n) { acc0[base + e] = run.a; acc1[base + e] = run.b; }
+        run = gl::e2_add(run, v[e]);
+    }
+}
+void launch_ef_exclusive_scan(const u64* totals, size_t n, u64* acc0, u64* acc1, u64* final2, u64* scratch, cudaStream_t st) {
+    size_t nb = (n + SCAN_B - 1) / SCAN_B;
+    k_scan_block_totals<<<(unsigned)nb, SCAN_T, 0, st>>>(totals, n, scratch);
+    k_scan_block_sums<<<1, 32, 0, st>>>(scratch, nb, final2);
+    k_scan_apply<<<(unsigned)nb, SCAN_T, 0, st>>>(totals, n, scratch, acc0, acc1);
+    COUNT_LAUNCH(); COUNT_LAUNCH(); COUNT_LAUNCH();
+}
+
+// =============================================================================================
 // OOD evaluation: dot products of coefficient columns with y^(bitrev(p))
 // =============================================================================================
 struct PowTable { E2 sq[24]; };   // sq[i] = y^(2^i)

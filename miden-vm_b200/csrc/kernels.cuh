@@ -103,6 +103,28 @@ struct ConstraintArgs {
 int launch_constraints(const ConstraintArgs& a, cudaStream_t st);   // returns 0 or -1 (program too large)
 
 // ---------------------------------------------------------------------------------------------
+// LogUp aux trace on the device (build_logup_aux_trace, reference air/src/lookup/aux_builder.rs:49-97)
+// ---------------------------------------------------------------------------------------------
+// Compiled lookup program: the constraint instruction format with MAIN/PERIODIC reading the TRACE domain and
+// op 17 = EMIT {op, column, flag slot | multiplicity slot << 16, denominator slot} (flag slot 0xffff = none).
+// One thread per trace row keeps a rational (V_c, U_c) per aux column (V/U = sum of m/d over the row's
+// active interactions), inverts once per column, writes the fraction columns c > 0 and the row total.
+struct LogupArgs {
+    const u64* main_cm;      // raw main trace, column-major [col][row]
+    u32 log_n, n_cols;       // trace height, LookupAir::num_columns
+    AirDev prog;             // periodic = RAW periodic matrix, row-major (max_period x n_periodic)
+    const u64* publics; const u64* challenges;
+    u64* aux_cm;             // aux trace, column-major planes [2c + coord][row]; column 0 is written by the scan
+    u64* totals;             // EF interleaved row totals t(r)
+    u32* bad_flag;           // set to 2 on a zero denominator
+};
+int launch_logup_rows(const LogupArgs& a, cudaStream_t st);   // 0, or -1 when the program needs too many slots/columns
+// Exclusive prefix sum over EF row totals: acc[r] = sum_{r' < r} t(r') into planes acc0/acc1, grand total into
+// final2 (device, 2 u64).  `scratch` needs 2 * ceil(n / 2048) + 2 u64.
+void launch_ef_exclusive_scan(const u64* totals, size_t n, u64* acc0, u64* acc1, u64* final2, u64* scratch, cudaStream_t st);
+static constexpr u32 LOGUP_MAX_COLS = 16;
+
+// ---------------------------------------------------------------------------------------------
 // DEEP / FRI / misc
 // ---------------------------------------------------------------------------------------------
 // wvec[p] = y^(bitrev_n(p)) for p < 2^n  (EF interleaved)

@@ -103,6 +103,11 @@ struct AirHost {
     mdn_air desc;
     DevBuf program;   // nodes | constraints | consts(lo,hi pairs as u64)
     mk::AirDev dev;
+    // lowered LookupAir (mdn_air.lookup): compiled program, raw periodic matrix, and the raw column-major main
+    // trace kept from before the in-place inverse NTT (the LogUp fractions are evaluated on the trace domain)
+    bool has_lookup = false;
+    DevBuf lookup_program, raw_main;
+    mk::AirDev lookup_dev;
 };
 
 }  // namespace
@@ -158,6 +163,8 @@ struct mdn_session {
     PremulPlan& premul_quotient(u32 n, u32 log_d);
     void build_tree(Committed& c, bool aligned_unused);
     void lde_matrix(CommittedMat& m);
+    void keep_raw_main(u32 j);
+    void build_logup_aux(u32 j, u64* aux_cm, u64 final_out[2]);
     void lde_and_commit(Committed& c, float* t_lde, float* t_hash, bool lde_done = false);
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev[8];
@@ -483,6 +490,131 @@ u64 mdn_session::grind(u32 bits) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// op-list compiler: validation, liveness, slot assignment (shared by constraint and lookup programs)
+// ---------------------------------------------------------------------------------------------
+struct Compiled { std::vector<u32> code; std::vector<u64> consts; u32 n_slots = 0; bool uses_sel = false; };
+// lookup == false: words = [MAIR, 1, n_nodes, n_constraints, n_consts | nodes | constraint node ids | consts];
+//                  a FOLD instruction (15) is placed right after the node it folds, in emission order.
+// lookup == true : words = [MLKP, 1, n_nodes, n_interactions, n_consts | nodes | {column, flag, mult, denom} | consts];
+//                  an EMIT instruction (17) is placed once its three operands are defined.
+static Compiled compile_oplist(u32 i, const mdn_air& a, u32 n_publics, const u32* w, u32 n_words, bool lookup, u32 lookup_cols) {
+    const char* what = lookup ? "lookup program" : "constraint program";
+    const u32 magic = lookup ? 0x504B4C4Du : 0x5249414Du, item = lookup ? 4u : 1u;
+    if (!w || n_words < 5 || w[0] != magic || w[1] != 1) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad %s header", i, what);
+    u32 nn = w[2], nc = w[3], nk = w[4];
+    if ((size_t)n_words != 5 + 3 * (size_t)nn + (size_t)item * nc + 2 * (size_t)nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad %s length", i, what);
+    Compiled out;
+    const u32* items = w + 5 + 3 * (size_t)nn;
+    for (u32 j = 0; j < nn; j++) {
+        u32 op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
+        if (op > 15) fail(MDN_ERR_INVALID_ARG, "AIR %u: unknown op %u", i, op);
+        // a LookupBuilder exposes the main window, periodic values, public values, challenges and constants only
+        if (lookup && (op == 1 || (op >= 4 && op <= 7) || op == 15)) fail(MDN_ERR_INVALID_ARG, "AIR %u: op %u is not available to a lookup program", i, op);
+        if (op == 15 && (x > 1 || y >= a.preprocessed_width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed column out of range", i);
+        if (op >= 5 && op <= 7) out.uses_sel = true;
+        if (op >= 10 && op <= 12 && (x >= j || y >= j)) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
+        if (op == 13 && x >= j) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
+        if (op == 0 && (x > 1 || y >= a.width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: main column out of range", i);
+        if (op == 1 && (x > 1 || y >= a.aux_width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: aux column out of range", i);
+        if (op == 2 && x >= n_publics) fail(MDN_ERR_INVALID_ARG, "AIR %u: public value out of range", i);
+        if (op == 3 && x >= a.num_randomness) fail(MDN_ERR_INVALID_ARG, "AIR %u: challenge out of range", i);
+        if (op == 4 && x >= a.num_aux_values) fail(MDN_ERR_INVALID_ARG, "AIR %u: aux value out of range", i);
+        if (op == 8 && x >= nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: constant out of range", i);
+        if (op == 9 && x + 1 >= nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: constant out of range", i);
+        if (op == 14 && x >= a.num_periodic_columns) fail(MDN_ERR_INVALID_ARG, "AIR %u: periodic column out of range", i);
+    }
+    // event stream: node definitions, each followed by the folds / emits that became ready
+    struct Ev { u32 kind; u32 node; };   // kind 0: define node; 1: fold node / emit interaction `node`
+    std::vector<Ev> evs; evs.reserve(nn + nc);
+    auto ready_at = [&](u32 kk) -> u32 {
+        if (!lookup) return items[kk];
+        const u32* it = items + 4 * (size_t)kk;
+        u32 m = std::max(it[2], it[3]);
+        return it[1] == 0xFFFFFFFFu ? m : std::max(m, it[1]);
+    };
+    for (u32 kk = 0; kk < nc; kk++) {
+        if (!lookup) { if (items[kk] >= nn) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint id", i); continue; }
+        const u32* it = items + 4 * (size_t)kk;
+        if (it[0] >= lookup_cols) fail(MDN_ERR_INVALID_ARG, "AIR %u: lookup column out of range", i);
+        if ((it[1] != 0xFFFFFFFFu && it[1] >= nn) || it[2] >= nn || it[3] >= nn) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad lookup interaction", i);
+    }
+    { u32 kk = 0;
+      for (u32 j = 0; j < nn; j++) {
+          evs.push_back({0, j});
+          while (kk < nc && ready_at(kk) <= j) { evs.push_back({1, lookup ? kk : items[kk]}); kk++; }
+      }
+      if (kk != nc) fail(MDN_ERR_INVALID_ARG, "AIR %u: %s with no nodes", i, what); }
+    std::vector<u32> last_use(nn, 0);
+    std::vector<uint8_t> is_ext(nn, 0);
+    for (u32 e = 0; e < evs.size(); e++) {
+        if (evs[e].kind) {
+            if (!lookup) { last_use[evs[e].node] = e; continue; }
+            const u32* it = items + 4 * (size_t)evs[e].node;
+            if (it[1] != 0xFFFFFFFFu) last_use[it[1]] = e;
+            last_use[it[2]] = e; last_use[it[3]] = e;
+            continue;
+        }
+        u32 j = evs[e].node, op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
+        last_use[j] = std::max(last_use[j], e);
+        if (op >= 10 && op <= 12) { last_use[x] = e; last_use[y] = e; is_ext[j] = is_ext[x] | is_ext[y]; }
+        else if (op == 13) { last_use[x] = e; is_ext[j] = is_ext[x]; }
+        else is_ext[j] = (op == 1 || op == 3 || op == 4 || op == 9);
+    }
+    if (lookup) for (u32 kk = 0; kk < nc; kk++) {
+        const u32* it = items + 4 * (size_t)kk;
+        if ((it[1] != 0xFFFFFFFFu && is_ext[it[1]]) || is_ext[it[2]]) fail(MDN_ERR_INVALID_ARG, "AIR %u: lookup flag and multiplicity must be base-field expressions", i);
+    }
+    std::vector<u32> slot_of(nn, 0), free_slots;
+    u32 n_slots = 0;
+    std::vector<u32>& code = out.code; code.reserve(4 * evs.size());
+    auto release = [&](u32 node, u32 e) { if (last_use[node] == e) free_slots.push_back(slot_of[node]); };
+    for (u32 e = 0; e < evs.size(); e++) {
+        if (evs[e].kind && !lookup) {
+            code.insert(code.end(), {15u | ((u32)is_ext[evs[e].node] << 8), 0u, slot_of[evs[e].node], 0u});
+            release(evs[e].node, e);
+            continue;
+        }
+        if (evs[e].kind) {
+            const u32* it = items + 4 * (size_t)evs[e].node;
+            u32 fs = it[1] == 0xFFFFFFFFu ? 0xffffu : slot_of[it[1]];
+            code.insert(code.end(), {17u, it[0], fs | (slot_of[it[2]] << 16), slot_of[it[3]]});
+            // a node may serve several operands of one interaction: release each distinct node once
+            u32 ops3[3] = {it[1], it[2], it[3]};
+            for (int q = 0; q < 3; q++) {
+                if (ops3[q] == 0xFFFFFFFFu) continue;
+                bool dup = false;
+                for (int q2 = 0; q2 < q; q2++) dup |= ops3[q2] == ops3[q];
+                if (!dup) release(ops3[q], e);
+            }
+            continue;
+        }
+        u32 j = evs[e].node, op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
+        u32 ox = x, oy = y;
+        if (op >= 10 && op <= 13) {
+            ox = slot_of[x]; oy = (op == 13) ? 0 : slot_of[y];
+            release(x, e);
+            if (op != 13 && y != x) release(y, e);
+        }
+        u32 dst;
+        if (!free_slots.empty()) { dst = free_slots.back(); free_slots.pop_back(); }
+        else dst = n_slots++;
+        slot_of[j] = dst;
+        code.insert(code.end(), {(op == 15 ? 16u : op) | ((u32)is_ext[j] << 8), dst, ox, oy});   // compiled 15 = FOLD, 16 = PREPROCESSED
+        if (last_use[j] == e) free_slots.push_back(dst);   // dead value
+    }
+    if (n_slots > 1024) fail(MDN_ERR_UNSUPPORTED, "AIR %u: %s needs %u live values (interpreter limit 1024)", i, what, n_slots);
+    out.n_slots = n_slots;
+    const u32* kw = items + (size_t)item * nc;
+    for (u32 j = 0; j < nk; j++) {
+        u64 v = (u64)kw[2 * j] | ((u64)kw[2 * j + 1] << 32);
+        if (v >= gl::P) fail(MDN_ERR_INVALID_ARG, "AIR %u: non-canonical constant", i);
+        out.consts.push_back(v);
+    }
+    return out;
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // prove_begin: validation, statement/shape binding, main commit, randomness  (mod.rs:240-349)
 // ---------------------------------------------------------------------------------------------
 void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces, const mdn_challenger* chal, u32 flags) {
@@ -514,81 +646,15 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         // parse + upload the constraint program
         AirHost& h = airs[i];
         h.desc = a;
-        const u32* w = a.program;
-        if (!w || a.program_words < 5 || w[0] != 0x5249414Du || w[1] != 1) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint program header", i);
-        u32 nn = w[2], nc = w[3], nk = w[4];
-        if ((size_t)a.program_words != 5 + 3 * (size_t)nn + nc + 2 * (size_t)nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint program length", i);
-        bool uses_sel = false;
-        for (u32 j = 0; j < nn; j++) {
-            u32 op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
-            if (op > 15) fail(MDN_ERR_INVALID_ARG, "AIR %u: unknown op %u", i, op);
-            if (op == 15 && (x > 1 || y >= a.preprocessed_width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed column out of range", i);
-            if (op >= 5 && op <= 7) uses_sel = true;
-            if (op >= 10 && op <= 12 && (x >= j || y >= j)) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
-            if (op == 13 && x >= j) fail(MDN_ERR_INVALID_ARG, "AIR %u: forward reference", i);
-            if (op == 0 && (x > 1 || y >= a.width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: main column out of range", i);
-            if (op == 1 && (x > 1 || y >= a.aux_width)) fail(MDN_ERR_INVALID_ARG, "AIR %u: aux column out of range", i);
-            if (op == 2 && x >= st->n_public_values) fail(MDN_ERR_INVALID_ARG, "AIR %u: public value out of range", i);
-            if (op == 3 && x >= a.num_randomness) fail(MDN_ERR_INVALID_ARG, "AIR %u: challenge out of range", i);
-            if (op == 4 && x >= a.num_aux_values) fail(MDN_ERR_INVALID_ARG, "AIR %u: aux value out of range", i);
-            if (op == 8 && x >= nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: constant out of range", i);
-            if (op == 9 && x + 1 >= nk) fail(MDN_ERR_INVALID_ARG, "AIR %u: constant out of range", i);
-        }
-        for (u32 j = 0; j < nc; j++) if (w[5 + 3 * nn + j] >= nn) fail(MDN_ERR_INVALID_ARG, "AIR %u: bad constraint id", i);
-        // ---- compile: event stream (node definitions + constraint folds in emission order), liveness,
-        //      slot assignment ----
-        struct Ev { u32 fold; u32 node; };
-        std::vector<Ev> evs; evs.reserve(nn + nc);
-        { u32 kk = 0;
-          for (u32 j = 0; j < nn; j++) {
-              evs.push_back({0, j});
-              while (kk < nc && w[5 + 3 * nn + kk] <= j) { evs.push_back({1, w[5 + 3 * nn + kk]}); kk++; }
-          } }
-        std::vector<u32> last_use(nn, 0);
-        std::vector<uint8_t> is_ext(nn, 0);
-        for (u32 e = 0; e < evs.size(); e++) {
-            if (evs[e].fold) { last_use[evs[e].node] = e; continue; }
-            u32 j = evs[e].node, op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
-            last_use[j] = std::max(last_use[j], e);
-            if (op >= 10 && op <= 12) { last_use[x] = e; last_use[y] = e; is_ext[j] = is_ext[x] | is_ext[y]; }
-            else if (op == 13) { last_use[x] = e; is_ext[j] = is_ext[x]; }
-            else is_ext[j] = (op == 1 || op == 3 || op == 4 || op == 9);
-            if (op == 14 && x >= a.num_periodic_columns) fail(MDN_ERR_INVALID_ARG, "AIR %u: periodic column out of range", i);
-        }
-        std::vector<u32> slot_of(nn, 0), free_slots;
-        u32 n_slots = 0;
-        std::vector<u32> code; code.reserve(4 * evs.size());
-        auto release = [&](u32 node, u32 e) { if (last_use[node] == e) free_slots.push_back(slot_of[node]); };
-        for (u32 e = 0; e < evs.size(); e++) {
-            if (evs[e].fold) {
-                code.insert(code.end(), {15u | ((u32)is_ext[evs[e].node] << 8), 0u, slot_of[evs[e].node], 0u});
-                release(evs[e].node, e);
-                continue;
-            }
-            u32 j = evs[e].node, op = w[5 + 3 * j], x = w[6 + 3 * j], y = w[7 + 3 * j];
-            u32 ox = x, oy = y;
-            if (op >= 10 && op <= 13) {
-                ox = slot_of[x]; oy = (op == 13) ? 0 : slot_of[y];
-                release(x, e);
-                if (op != 13 && y != x) release(y, e);
-            }
-            u32 dst;
-            if (!free_slots.empty()) { dst = free_slots.back(); free_slots.pop_back(); }
-            else dst = n_slots++;
-            slot_of[j] = dst;
-            code.insert(code.end(), {(op == 15 ? 16u : op) | ((u32)is_ext[j] << 8), dst, ox, oy});   // compiled 15 = FOLD, 16 = PREPROCESSED
-            if (last_use[j] == e) free_slots.push_back(dst);   // dead value
-        }
-        if (n_slots > 1024) fail(MDN_ERR_UNSUPPORTED, "AIR %u: constraint program needs %u live values (interpreter limit 1024)", i, n_slots);
+        Compiled cp = compile_oplist(i, a, st->n_public_values, a.program, a.program_words, false, 0);
+        bool uses_sel = cp.uses_sel;
+        u32 n_slots = cp.n_slots;
+        std::vector<u32>& code = cp.code;
+        u32 nk = (u32)cp.consts.size();
         std::vector<u64> hostp((code.size() + 1) / 2 + nk + 2, 0);
         memcpy(hostp.data(), code.data(), code.size() * sizeof(u32));
         size_t const_off = (code.size() + 1) / 2;
-        size_t words32 = 3 * (size_t)nn + nc;
-        for (u32 j = 0; j < nk; j++) {
-            u64 v = (u64)w[5 + words32 + 2 * j] | ((u64)w[5 + words32 + 2 * j + 1] << 32);
-            if (v >= gl::P) fail(MDN_ERR_INVALID_ARG, "AIR %u: non-canonical constant", i);
-            hostp[const_off + j] = v;
-        }
+        for (u32 j = 0; j < nk; j++) hostp[const_off + j] = cp.consts[j];
         // periodic columns: table[col][m] = P_col(s^(n/maxp) * w_{maxp*B}^m), m < maxp*B
         // (prover/periodic.rs:49-98; the column is interpolated over the size-maxp subgroup)
         size_t per_off = hostp.size();
@@ -628,6 +694,28 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         h.dev.periodic = a.num_periodic_columns ? h.program.p + per_off : nullptr;
         h.dev.n_instr = (u32)(code.size() / 4); h.dev.n_slots = std::max(1u, n_slots); h.dev.uses_selectors = uses_sel;
         h.dev.log_max_period = a.log_max_period; h.dev.n_periodic = a.num_periodic_columns;
+        // lowered LookupAir -> the aux trace of this AIR is built on the device (commit_aux)
+        h.has_lookup = a.lookup != nullptr;
+        if (h.has_lookup) {
+            const mdn_lookup& lk = *a.lookup;
+            if (lk.num_columns != a.aux_width || a.num_aux_values != 1) fail(MDN_ERR_INVALID_ARG, "AIR %u: a lookup program needs aux_width == num_columns and num_aux_values == 1", i);
+            if (lk.num_columns == 0 || lk.num_columns > mk::LOGUP_MAX_COLS) fail(MDN_ERR_UNSUPPORTED, "AIR %u: at most %u lookup columns", i, mk::LOGUP_MAX_COLS);
+            Compiled lc = compile_oplist(i, a, st->n_public_values, lk.program, lk.program_words, true, lk.num_columns);
+            size_t c_off = (lc.code.size() + 1) / 2, p_off = c_off + lc.consts.size() + 2;
+            size_t np = a.num_periodic_columns, mp = (size_t)1 << a.log_max_period;
+            std::vector<u64> hp(p_off + np * mp, 0);
+            memcpy(hp.data(), lc.code.data(), lc.code.size() * sizeof(u32));
+            for (size_t j = 0; j < lc.consts.size(); j++) hp[c_off + j] = lc.consts[j];
+            for (size_t q = 0; q < np * mp; q++) hp[p_off + q] = a.periodic_values[q];   // canonical: checked above
+            h.lookup_program.alloc(hp.size(), stream);
+            CUDA_OK(cudaMemcpyAsync(h.lookup_program.p, hp.data(), hp.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+            CUDA_OK(cudaStreamSynchronize(stream));
+            h.lookup_dev = mk::AirDev{};
+            h.lookup_dev.code = (const u32*)h.lookup_program.p; h.lookup_dev.consts = h.lookup_program.p + c_off;
+            h.lookup_dev.periodic = np ? h.lookup_program.p + p_off : nullptr;
+            h.lookup_dev.n_instr = (u32)(lc.code.size() / 4); h.lookup_dev.n_slots = std::max(1u, lc.n_slots);
+            h.lookup_dev.log_max_period = a.log_max_period; h.lookup_dev.n_periodic = a.num_periodic_columns;
+        }
     }
     // preprocessed presence / shape parity (ProverInstance::new, prover/mod.rs:139-153; validate_preprocessed,
     // preprocessed.rs:147-260): a bundle must be installed exactly when some AIR declares preprocessed columns,
@@ -701,12 +789,13 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
                 mk::launch_transpose_rm_to_cm(staging[j].p, main_c.mats[j].coef, 1u << main_c.mats[j].log_n, main_c.mats[j].width, (u32*)d_flag.p, stream);
             }
             if (j + 1 == k) CUDA_OK(cudaEventRecord(ev[1], stream));
+            keep_raw_main(j);
             lde_matrix(main_c.mats[j]);   // queued behind the copy of matrix j; overlaps the copy of matrix j+1
         }
     } else {
         for (u32 j = 0; j < k; j++) upload_matrix(traces[order[j]], true, main_c.mats[j].coef);
         CUDA_OK(cudaEventRecord(ev[1], stream));
-        for (u32 j = 0; j < k; j++) lde_matrix(main_c.mats[j]);
+        for (u32 j = 0; j < k; j++) { keep_raw_main(j); lde_matrix(main_c.mats[j]); }
     }
     staging.clear();
     check_input_flag("a main trace");
@@ -759,6 +848,43 @@ void mdn_session::set_preprocessed(const mdn_statement* st, const mdn_matrix* ma
     has_prep = true;
 }
 
+void mdn_session::keep_raw_main(u32 j) {
+    AirHost& h = airs[order[j]];
+    if (!h.has_lookup) return;
+    CommittedMat& m = main_c.mats[j];
+    size_t n = ((size_t)1 << m.log_n) * m.width;
+    h.raw_main.alloc(n, stream);
+    CUDA_OK(cudaMemcpyAsync(h.raw_main.p, m.coef, n * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
+}
+
+// build_logup_aux_trace (air/src/lookup/aux_builder.rs:49-97) for proof position j: fraction collection and
+// per-row sums on the trace domain, exclusive EF prefix sum into column 0, committed final = the grand total.
+void mdn_session::build_logup_aux(u32 j, u64* aux_cm, u64 final_out[2]) {
+    AirHost& h = airs[order[j]];
+    u32 ln = log_heights[order[j]];
+    size_t N = (size_t)1 << ln;
+    DevBuf totals, scratch, fin;
+    totals.alloc(2 * N, stream); scratch.alloc(2 * ((N + 2047) / 2048) + 2, stream); fin.alloc(2, stream);
+    mk::LogupArgs la;
+    la.main_cm = h.raw_main.p; la.log_n = ln; la.n_cols = h.desc.aux_width; la.prog = h.lookup_dev;
+    la.publics = d_publics.p; la.challenges = d_randomness.p; la.aux_cm = aux_cm; la.totals = totals.p; la.bad_flag = (u32*)d_flag.p;
+    {
+        ProfScope ps(prof, PC_CONSTRAINTS);
+        if (mk::launch_logup_rows(la, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "lookup program too large for the interpreter");
+        mk::launch_ef_exclusive_scan(totals.p, N, aux_cm, aux_cm + N, fin.p, scratch.p, stream);
+    }
+    CUDA_OK(cudaMemcpyAsync(final_out, fin.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    u32 flag = 0;
+    CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    h.raw_main.release();
+    if (flag) {
+        CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));
+        if (flag & 2) fail(MDN_ERR_INVALID_ARG, "AIR %u: LogUp denominator must be non-zero", order[j]);   // aux_builder.rs:240-243
+        fail(MDN_ERR_INVALID_ARG, "an aux trace contains a non-canonical field element (>= p)");
+    }
+}
+
 // aux traces (instance order, EF flattened to base), aux values; commit + observe (mod.rs:397-422)
 void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values, bool zero_aux) {
     if (!in_proof) fail(MDN_ERR_INVALID_ARG, "commit_aux called outside a proof");
@@ -773,6 +899,11 @@ void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values
     }
     aux_c.coef_buf.alloc(coef_total, stream);
     aux_c.lde_buf.alloc(lde_total, stream);
+    // device copies of the small per-proof vectors used by the lookup and constraint kernels
+    d_publics.alloc(std::max<size_t>(1, publics.size()), stream);
+    if (!publics.empty()) CUDA_OK(cudaMemcpyAsync(d_publics.p, publics.data(), publics.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    d_randomness.alloc(std::max<size_t>(1, 2 * randomness.size()), stream);
+    if (!randomness.empty()) CUDA_OK(cudaMemcpyAsync(d_randomness.p, randomness.data(), randomness.size() * sizeof(E2), cudaMemcpyHostToDevice, stream));
     size_t co = 0, lo = 0;
     std::vector<u64> flat_values;
     aux_values_p.assign(k, {}); aux_values_off.assign(k, 0);
@@ -781,9 +912,13 @@ void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values
         size_t N = (size_t)1 << log_heights[inst];
         u32 w = 2 * airs[inst].desc.aux_width;
         aux_c.mats.push_back(CommittedMat{aux_c.lde_buf.p + lo, aux_c.coef_buf.p + co, log_heights[inst], w});
-        if (w) {
+        u64 logup_final[2] = {0, 0};
+        const bool dev_aux = airs[inst].has_lookup;
+        if (dev_aux) build_logup_aux(j, aux_c.coef_buf.p + co, logup_final);
+        else if (w) {
             if (zero_aux) CUDA_OK(cudaMemsetAsync(aux_c.coef_buf.p + co, 0, N * w * sizeof(u64), stream));
             else {
+                if (!aux[inst].values) fail(MDN_ERR_INVALID_ARG, "aux trace %u is NULL", inst);
                 if (aux[inst].width != w || aux[inst].log_height != log_heights[inst]) fail(MDN_ERR_INVALID_ARG, "aux trace %u has the wrong shape", inst);
                 upload_matrix(aux[inst], false, aux_c.coef_buf.p + co);
             }
@@ -791,7 +926,7 @@ void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values
         u32 nav = airs[inst].desc.num_aux_values;
         aux_values_off[j] = flat_values.size();
         for (u32 v = 0; v < 2 * nav; v++) {
-            u64 x = zero_aux ? 0 : aux_values[inst][v];
+            u64 x = dev_aux ? logup_final[v] : (zero_aux ? 0 : aux_values[inst][v]);
             if (x >= gl::P) fail(MDN_ERR_INVALID_ARG, "non-canonical aux value");
             aux_values_p[j].push_back(x); flat_values.push_back(x);
         }
@@ -802,11 +937,6 @@ void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values
     tr.send_commitment(aux_c.root);
     memcpy(dbg_roots[1], aux_c.root, 32);
     for (auto& vs : aux_values_p) for (u64 v : vs) tr.send_field(v);
-    // device copies of the small per-proof vectors used by the constraint kernel
-    d_publics.alloc(std::max<size_t>(1, publics.size()), stream);
-    if (!publics.empty()) CUDA_OK(cudaMemcpyAsync(d_publics.p, publics.data(), publics.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
-    d_randomness.alloc(std::max<size_t>(1, 2 * randomness.size()), stream);
-    if (!randomness.empty()) CUDA_OK(cudaMemcpyAsync(d_randomness.p, randomness.data(), randomness.size() * sizeof(E2), cudaMemcpyHostToDevice, stream));
     d_aux_values.alloc(std::max<size_t>(1, flat_values.size()), stream);
     if (!flat_values.empty()) CUDA_OK(cudaMemcpyAsync(d_aux_values.p, flat_values.data(), flat_values.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -1310,6 +1440,7 @@ int mdn_prove(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces,
         std::vector<const u64*> val_ptrs(k);
         for (u32 i = 0; i < k; i++) {
             const mdn_air& a = st->airs[i];
+            if (a.lookup) { aux_mats[i] = mdn_matrix{nullptr, traces[i].log_height, 2 * a.aux_width}; val_ptrs[i] = nullptr; continue; }   // built on the device
             size_t N = (size_t)1 << traces[i].log_height;
             aux_bufs[i].assign(N * 2 * a.aux_width, 0);
             val_bufs[i].assign(2 * (size_t)a.num_aux_values + 1, 0);

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import air_program
-from .binding import Air, Challenger, Matrix, PcsParams, Statement, u32p, u64p
+from .binding import Air, Challenger, Lookup, Matrix, PcsParams, Statement, u32p, u64p
 
 P = 0xFFFFFFFF00000001
 MIDEN_WIDTHS = (51, 22, 16)        # core / chiplets / poseidon2 main widths
@@ -58,7 +58,7 @@ class Workload:
 
     def __init__(self, log_heights, widths=MIDEN_WIDTHS, aux_widths=MIDEN_AUX_WIDTHS, seed=SEED,
                  programs=None, num_randomness=2, public_values=(), log_quotient_degrees=None, traces=None,
-                 num_aux_values=None, periodic=None, preprocessed=None):
+                 num_aux_values=None, periodic=None, preprocessed=None, lookups=None):
         self.k = len(log_heights)
         self.log_heights = list(log_heights)
         self.widths = list(widths)[: self.k]
@@ -83,6 +83,15 @@ class Workload:
                 a.periodic_values = per.ctypes.data_as(u64p)
                 a.num_periodic_columns = per.shape[1]
                 a.log_max_period = int(per.shape[0]).bit_length() - 1
+        # lowered LookupAir per AIR: (num_columns, program words) or None -> aux trace built on the device
+        self._lookups = []
+        for i in range(self.k):
+            lk = lookups[i] if lookups is not None else None
+            if lk is not None:
+                prog = np.ascontiguousarray(lk[1], dtype=np.uint32)
+                st_ = Lookup(lk[0], len(prog), prog.ctypes.data_as(u32p))
+                self._lookups.append((st_, prog))
+                self._airs[i].lookup = C.pointer(st_)
         # BaseAir::preprocessed_trace per AIR (None = the AIR declares none); same height as the main trace
         self.preprocessed = None
         if preprocessed is not None and any(m is not None for m in preprocessed):

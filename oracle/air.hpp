@@ -74,6 +74,57 @@ struct AirProgram {
     }
 };
 
+// Lowering of `LookupAir::eval` (reference air/src/lookup/builder.rs): the node vocabulary of the constraint
+// op-list restricted to what a LookupBuilder exposes (main window, periodic values, public values, the two
+// challenges, constants, arithmetic), plus one record per interaction: the aux column it belongs to, its 0/1
+// flag (NONE = unconditional), its signed base-field multiplicity and its encoded extension-field
+// denominator -- `ProverGroup::insert` / `ProverBatch::insert` (air/src/lookup/prover.rs:338-362,421-444)
+// push exactly (multiplicity, denominator) when the flag is non-zero.
+struct LookupInteraction { uint32_t column, flag, multiplicity, denominator; };
+struct LookupProgram {
+    uint32_t num_columns = 0;
+    std::vector<AirNode> nodes;
+    std::vector<LookupInteraction> interactions;
+    std::vector<u64> consts;
+    static constexpr uint32_t MAGIC = 0x504B4C4Du;   // "MLKP"
+    static constexpr uint32_t NO_FLAG = 0xFFFFFFFFu;
+    bool present() const { return num_columns > 0; }
+
+    // words [MAGIC, 1, n_nodes, n_interactions, n_consts, nodes (3 each), interactions (4 each), consts (lo, hi)]
+    static LookupProgram parse(uint32_t num_columns, const uint32_t* w, size_t n_words) {
+        if (n_words < 5 || w[0] != MAGIC || w[1] != 1) throw std::runtime_error("lookup program: bad header");
+        size_t nn = w[2], ni = w[3], nk = w[4];
+        if (n_words != 5 + 3 * nn + 4 * ni + 2 * nk) throw std::runtime_error("lookup program: bad length");
+        LookupProgram p; p.num_columns = num_columns;
+        const uint32_t* q = w + 5;
+        std::vector<uint8_t> is_ext(nn);
+        for (size_t i = 0; i < nn; i++, q += 3) {
+            AirNode nd{q[0], q[1], q[2]};
+            switch (nd.op) {
+                case OP_MAIN: case OP_PUBLIC: case OP_CONST: case OP_PERIODIC: is_ext[i] = 0; break;
+                case OP_CHALLENGE: case OP_EXT_CONST: is_ext[i] = 1; break;
+                case OP_ADD: case OP_SUB: case OP_MUL:
+                    if (nd.a >= i || nd.b >= i) throw std::runtime_error("lookup program: forward reference");
+                    is_ext[i] = is_ext[nd.a] | is_ext[nd.b]; break;
+                case OP_NEG:
+                    if (nd.a >= i) throw std::runtime_error("lookup program: forward reference");
+                    is_ext[i] = is_ext[nd.a]; break;
+                default: throw std::runtime_error("lookup program: op not available to a LookupBuilder");
+            }
+            p.nodes.push_back(nd);
+        }
+        for (size_t i = 0; i < ni; i++, q += 4) {
+            LookupInteraction it{q[0], q[1], q[2], q[3]};
+            if (it.column >= num_columns) throw std::runtime_error("lookup program: column out of range");
+            if ((it.flag != NO_FLAG && (it.flag >= nn || is_ext[it.flag])) || it.multiplicity >= nn || is_ext[it.multiplicity] || it.denominator >= nn)
+                throw std::runtime_error("lookup program: bad interaction");
+            p.interactions.push_back(it);
+        }
+        for (size_t i = 0; i < nk; i++, q += 2) p.consts.push_back((u64)q[0] | ((u64)q[1] << 32));
+        return p;
+    }
+};
+
 // Everything a program can read at one evaluation point.
 struct AirPoint {
     const Fp* main_local; const Fp* main_next;

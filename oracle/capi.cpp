@@ -23,8 +23,10 @@ extern "C" {
 
 struct orc_pcs_params { uint32_t log_blowup, log_folding_arity, log_final_degree, folding_pow_bits, deep_pow_bits, num_queries, query_pow_bits; };
 struct orc_challenger { uint64_t sponge_state[12]; uint64_t input_buffer[8]; uint32_t input_len, output_len; };
+struct orc_lookup { uint32_t num_columns, program_words; const uint32_t* program; };
 struct orc_air { uint32_t width, aux_width, num_aux_values, num_randomness, log_quotient_degree, program_words; const uint32_t* program;
-                 const uint64_t* periodic_values; uint32_t num_periodic_columns, log_max_period, preprocessed_width; };
+                 const uint64_t* periodic_values; uint32_t num_periodic_columns, log_max_period, preprocessed_width;
+                 const struct orc_lookup* lookup; };
 struct orc_matrix { const uint64_t* values; uint32_t log_height, width; };
 struct orc_statement { const orc_air* airs; uint32_t n_airs; const uint64_t* public_values; uint32_t n_public_values; const uint64_t* observe_felts; uint32_t n_observe_felts; };
 typedef int (*orc_aux_builder)(void* ctx, uint32_t instance, const orc_matrix* main, const uint64_t* randomness, uint64_t* aux_out, uint64_t* aux_values);
@@ -125,6 +127,15 @@ static Statement to_statement(const orc_statement* st) {
         d.n_periodic = a.num_periodic_columns; d.log_max_period = a.log_max_period; d.preprocessed_width = a.preprocessed_width;
         for (size_t q = 0; q < ((size_t)a.num_periodic_columns << a.log_max_period); q++) d.periodic.push_back(Fp(a.periodic_values[q]));
         for (auto& nd : d.program.nodes) if (nd.op == OP_PERIODIC && nd.a >= d.n_periodic) throw std::runtime_error("air program: periodic column out of range");
+        if (a.lookup) {
+            d.lookup = LookupProgram::parse(a.lookup->num_columns, a.lookup->program, a.lookup->program_words);
+            for (auto& nd : d.lookup.nodes) {
+                if (nd.op == OP_PERIODIC && nd.a >= d.n_periodic) throw std::runtime_error("lookup program: periodic column out of range");
+                if (nd.op == OP_MAIN && (nd.a > 1 || nd.b >= d.width)) throw std::runtime_error("lookup program: main column out of range");
+                if (nd.op == OP_CHALLENGE && nd.a >= d.num_randomness) throw std::runtime_error("lookup program: challenge out of range");
+                if (nd.op == OP_PUBLIC && nd.a >= st->n_public_values) throw std::runtime_error("lookup program: public value out of range");
+            }
+        }
         s.airs.push_back(std::move(d));
     }
     for (uint32_t i = 0; i < st->n_public_values; i++) s.public_values.push_back(Fp(st->public_values[i]));

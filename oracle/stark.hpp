@@ -46,7 +46,8 @@ struct AirDesc {
     AirProgram program;
     // periodic_columns_matrix(): max_period x n_periodic, row-major (prover/periodic.rs:49-98)
     std::vector<Fp> periodic; size_t n_periodic = 0; unsigned log_max_period = 0;
-    size_t preprocessed_width = 0;       // BaseAir::preprocessed_width
+    size_t preprocessed_width = 0;
+    LookupProgram lookup;            // optional: aux trace built from the lowered LookupAir (build_logup_aux_trace)       // BaseAir::preprocessed_width
     // coefficients (ascending) of periodic column c over the size-max_period subgroup
     std::vector<std::vector<Fp>> periodic_coeffs() const {
         size_t mp = size_t(1) << log_max_period;
@@ -426,6 +427,64 @@ struct ProveDebug {
     OpenDebug open;
 };
 
+// `build_logup_aux_trace` (air/src/lookup/aux_builder.rs:49-97) on the lowered LookupAir, with the per-fraction
+// semantics of `accumulate_slow` (:215-268): f_c(r) = sum of m/d over the active interactions of column c at
+// row r; aux[r][c>0] = f_c(r); aux[r][0] = sum_{r'<r} sum_c f_c(r'); committed final = aux[N][0].
+inline void build_logup_aux(const AirDesc& air, const Matrix& main, const std::vector<Ef>& challenges,
+                            const std::vector<Fp>& publics, Matrix& aux, std::vector<Ef>& aux_values) {
+    const LookupProgram& lp = air.lookup;
+    size_t N = main.height, C = lp.num_columns;
+    if (air.aux_width != C || air.num_aux_values != 1) throw std::runtime_error("lookup: aux shape mismatch");
+    aux = Matrix(N, 2 * C);
+    std::vector<Ef> totals(N);
+    size_t maxp = size_t(1) << air.log_max_period;
+    std::string err;
+    #pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < N; r++) {
+        std::vector<Ef> val(lp.nodes.size());
+        const Fp* loc = main.row(r); const Fp* nxt = main.row((r + 1) % N);
+        for (size_t i = 0; i < lp.nodes.size(); i++) {
+            const AirNode& nd = lp.nodes[i];
+            Ef v;
+            switch (nd.op) {
+                case OP_MAIN: v = Ef((nd.a ? nxt : loc)[nd.b]); break;
+                case OP_PUBLIC: v = Ef(publics[nd.a]); break;
+                case OP_CHALLENGE: v = challenges[nd.a]; break;
+                case OP_CONST: v = Ef(Fp(lp.consts[nd.a])); break;
+                case OP_EXT_CONST: v = Ef(Fp(lp.consts[nd.a]), Fp(lp.consts[nd.a + 1])); break;
+                case OP_ADD: v = val[nd.a] + val[nd.b]; break;
+                case OP_SUB: v = val[nd.a] - val[nd.b]; break;
+                case OP_MUL: v = val[nd.a] * val[nd.b]; break;
+                case OP_NEG: v = -val[nd.a]; break;
+                case OP_PERIODIC: v = Ef(air.periodic[(r % maxp) * air.n_periodic + nd.a]); break;
+                default: break;
+            }
+            val[i] = v;
+        }
+        std::vector<Ef> f(C);
+        for (const LookupInteraction& it : lp.interactions) {
+            if (it.flag != LookupProgram::NO_FLAG && val[it.flag].is_zero()) continue;
+            Ef d = val[it.denominator];
+            if (d.is_zero()) {
+                #pragma omp critical
+                err = "LogUp denominator must be non-zero";
+                continue;
+            }
+            f[it.column] += ef_inv(d) * val[it.multiplicity].a;
+        }
+        Ef t;
+        for (size_t c = 0; c < C; c++) {
+            t += f[c];
+            if (c > 0) { aux.row(r)[2 * c] = f[c].a; aux.row(r)[2 * c + 1] = f[c].b; }
+        }
+        totals[r] = t;
+    }
+    if (!err.empty()) throw std::runtime_error(err);
+    Ef acc;
+    for (size_t r = 0; r < N; r++) { aux.row(r)[0] = acc.a; aux.row(r)[1] = acc.b; acc += totals[r]; }
+    aux_values.assign(1, acc);
+}
+
 inline Proof stark_prove(const PcsParams& params, const Statement& st, const std::vector<Matrix>& traces,
                          Challenger challenger, const AuxBuilder& build_aux, ProveDebug* dbg = nullptr) {
     size_t k = st.airs.size();
@@ -475,7 +534,8 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
         std::vector<Ef> r(randomness.begin(), randomness.begin() + st.airs[i].num_randomness);
         aux_i[i] = Matrix(traces[i].height, 2 * st.airs[i].aux_width);
         auxv_i[i].assign(st.airs[i].num_aux_values, Ef());
-        if (build_aux) build_aux(i, traces[i], r, aux_i[i], auxv_i[i]);
+        if (st.airs[i].lookup.present()) build_logup_aux(st.airs[i], traces[i], r, st.public_values, aux_i[i], auxv_i[i]);
+        else if (build_aux) build_aux(i, traces[i], r, aux_i[i], auxv_i[i]);
     }
     std::vector<Matrix> aux_p; std::vector<std::vector<Ef>> auxv_p;
     for (size_t j = 0; j < k; j++) { aux_p.push_back(aux_i[ord.proof_to_instance[j]]); auxv_p.push_back(auxv_i[ord.proof_to_instance[j]]); }

@@ -20,12 +20,16 @@ class Challenger(C.Structure):
                 ("input_len", C.c_uint32), ("output_len", C.c_uint32)]
 
 
+class Lookup(C.Structure):
+    _fields_ = [("num_columns", C.c_uint32), ("program_words", C.c_uint32), ("program", u32p)]
+
+
 class Air(C.Structure):
     _fields_ = [("width", C.c_uint32), ("aux_width", C.c_uint32), ("num_aux_values", C.c_uint32),
                 ("num_randomness", C.c_uint32), ("log_quotient_degree", C.c_uint32),
                 ("program_words", C.c_uint32), ("program", u32p),
                 ("periodic_values", u64p), ("num_periodic_columns", C.c_uint32), ("log_max_period", C.c_uint32),
-                ("preprocessed_width", C.c_uint32)]
+                ("preprocessed_width", C.c_uint32), ("lookup", C.POINTER(Lookup))]
 
 
 class Matrix(C.Structure):

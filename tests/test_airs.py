@@ -131,6 +131,98 @@ def preprocessed_workload(log_hs=(6, 8), with_prep=(True, True), lqd: int = 1):
                       log_quotient_degrees=[lqd] * k, num_aux_values=[0] * k, preprocessed=preps)
 
 
+def ef_inv(x):
+    n = (x[0] * x[0] - 7 * x[1] * x[1]) % P
+    ni = pow(n, P - 2, P)
+    return (x[0] * ni % P, (P - x[1]) * ni % P)
+
+
+def logup_workload(log_h: int, device: bool = True, lqd: int = 2, seed: int = 5):
+    """A LogUp AIR in the shape `build_logup_aux_trace` serves (air/src/lookup/aux_builder.rs): main columns
+    [x, y, tx, ty, f, m], one periodic selector p (period 4), 3 aux columns, max_message_width 2, 2 bus ids:
+      column 0 (accumulator): add(flag f, bus0 (x, y))
+      column 1              : insert(always, multiplicity -m, bus0 (tx, ty))
+      column 2              : batch(flag p) { add(bus1 (x)); remove(bus1 (tx)) }
+    Constraints tie the aux columns to those fractions, so the oracle verifier checks the built aux trace.
+    device=True ships the lowered LookupAir (aux built by the backend); device=False returns a host aux
+    builder computing the same trace independently with Python integers."""
+    import random
+    rng = random.Random(seed)
+    n = 1 << log_h
+    per = np.array([[1], [0], [0], [1]], dtype=np.uint64)
+    t = W.synthetic_trace(31, log_h, 6)
+    for r in range(n):
+        t[r, 4] = rng.randrange(2)
+        t[r, 5] = rng.randrange(4)
+    MW = 2
+
+    def chal(b):
+        return b.challenge(0), b.challenge(1)
+
+    def denoms(b):
+        x, y, tx, ty = (b.main(0, c) for c in range(4))
+        if isinstance(b, AP.LookupProgramBuilder):
+            return b.encode(0, MW, [x, y]), b.encode(0, MW, [tx, ty]), b.encode(1, MW, [x]), b.encode(1, MW, [tx])
+        al, be = chal(b)
+        g = be * be
+        return al + g + x + be * y, al + g + tx + be * ty, al + g * b.const(2) + x, al + g * b.const(2) + tx
+
+    # ---- lowered LookupAir
+    lb = AP.LookupProgramBuilder(3)
+    d0, d1, d2a, d2b = denoms(lb)
+    lb.insert(0, lb.main(0, 4), lb.const(1), d0)
+    lb.insert(1, None, -lb.main(0, 5), d1)
+    pflag = lb.periodic(0)
+    lb.insert(2, pflag, lb.const(1), d2a)
+    lb.insert(2, pflag, lb.const(P - 1), d2b)
+    # ---- constraints
+    b = AP.ProgramBuilder()
+    d0, d1, d2a, d2b = denoms(b)
+    f, m, p = b.main(0, 4), b.main(0, 5), b.periodic(0)
+    a0, a1, a2, a0n = b.aux(0, 0), b.aux(0, 1), b.aux(0, 2), b.aux(1, 0)
+    b.assert_zero(f * (f - b.const(1)))
+    b.assert_zero_ext(a1 * d1 + m)
+    b.assert_zero_ext(a2 * d2a * d2b - (d2b - d2a) * p)
+    b.assert_zero_ext(((a0n - a0 - a1 - a2) * d0 - f) * b.is_transition())
+    b.assert_zero_ext(a0 * b.is_first_row())
+    b.assert_zero_ext(((b.aux_value(0) - a0 - a1 - a2) * d0 - f) * b.is_last_row())
+    wl = W.Workload([log_h], widths=[6], aux_widths=[3], programs=[b.serialize()], traces=[t],
+                    log_quotient_degrees=[lqd], periodic=[per], num_aux_values=[1],
+                    lookups=[(3, lb.serialize())] if device else None)
+
+    def build_aux(ctx, instance, main, randomness, aux_out, aux_values):
+        al = (randomness[0], randomness[1]); be = (randomness[2], randomness[3])
+        g = ef_mul(be, be); g2 = ((2 * g[0]) % P, (2 * g[1]) % P)
+        w = main.contents.width
+        v = main.contents.values
+
+        def enc(prefix, e0, e1=None):
+            d = ((al[0] + prefix[0] + e0) % P, (al[1] + prefix[1]) % P)
+            if e1 is not None:
+                d = ((d[0] + be[0] * e1) % P, (d[1] + be[1] * e1) % P)
+            return d
+
+        acc = (0, 0)
+        for r in range(n):
+            x, y, tx, ty, fl, mm = (int(v[r * w + c]) for c in range(6))
+            pp = int(per[r % 4, 0])
+            f0 = ef_inv(enc(g, x, y)) if fl else (0, 0)
+            i1 = ef_inv(enc(g, tx, ty))
+            f1 = ((P - mm) * i1[0] % P, (P - mm) * i1[1] % P)
+            f2 = (0, 0)
+            if pp:
+                ia, ib = ef_inv(enc(g2, x)), ef_inv(enc(g2, tx))
+                f2 = ((ia[0] - ib[0]) % P, (ia[1] - ib[1]) % P)
+            row = [acc, f1, f2]
+            for c in range(3):
+                aux_out[r * 6 + 2 * c], aux_out[r * 6 + 2 * c + 1] = row[c]
+            acc = tuple((acc[q] + f0[q] + f1[q] + f2[q]) % P for q in range(2))
+        aux_values[0], aux_values[1] = acc
+        return 0
+
+    return wl, (None if device else build_aux)
+
+
 def big_program_workload(log_h: int, n_terms: int = 300, seed: int = 3, lqd: int = 3):
     """A program with thousands of nodes whose constraints vanish identically (E - E' with E, E' built
     separately), exercising the liveness-based slot allocation of the constraint interpreter."""

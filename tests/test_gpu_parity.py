@@ -228,6 +228,58 @@ def test_prove_preprocessed_columns(log_hs, with_prep):
         s.prove(wl.statement, wl.matrices, ch)
 
 
+@pytest.mark.parametrize("log_h", [5, 13])
+def test_prove_logup_aux_built_on_device(sess_fast, log_h):
+    # mdn_air.lookup: fraction collection, per-row sums and the EF prefix sum run on the device; the proof is
+    # bit-exact against the oracle and against a host aux builder using Python integers (small case)
+    import test_airs
+    params = W.fast_pcs_params()
+    wl_dev, _ = test_airs.logup_workload(log_h, device=True)
+    h1, f1, c1 = _compare_proofs(sess_fast, params, wl_dev)
+    if log_h <= 8:
+        wl_host, builder = test_airs.logup_workload(log_h, device=False)
+        ch = W.initial_challenger(params, prod_observe)
+        h2, f2, c2 = sess_fast.prove(wl_host.statement, wl_host.matrices, ch, B.AUX_BUILDER(builder))
+        assert h1 == h2 and np.array_equal(f1, f2) and np.array_equal(c1, c2)
+
+
+def test_logup_mixed_with_host_built_aux(sess_fast):
+    # one AIR with a lowered LookupAir (device aux) next to the fib/product AIR whose aux comes from the host callback
+    import test_airs
+    params = W.fast_pcs_params()
+    wl_l, _ = test_airs.logup_workload(6, device=True)
+    wl_f, fib_builder = test_airs.fib_product_workload([7])
+    progs = [wl_l.programs[0], wl_f.programs[0]]
+    wl = W.Workload([6, 7], widths=[6, 3], aux_widths=[3, 1], programs=progs, traces=[wl_l.traces[0], wl_f.traces[0]],
+                    public_values=[int(v) for v in wl_f.public_values], log_quotient_degrees=[2, 1], num_aux_values=[1, 1],
+                    periodic=[np.array([[1], [0], [0], [1]], dtype=np.uint64), None],
+                    lookups=[(3, wl_l._lookups[0][1]), None])
+
+    def builder(ctx, instance, main, randomness, aux_out, aux_values):
+        assert instance == 1            # the lookup AIR never reaches the host callback
+        return fib_builder(ctx, 0, main, randomness, aux_out, aux_values)
+
+    _compare_proofs(sess_fast, params, wl, builder)
+
+
+def test_logup_zero_denominator_is_an_error(sess_fast):
+    import test_airs
+    AP = test_airs.AP
+    lb = AP.LookupProgramBuilder(1)
+    lb.insert(0, None, lb.const(1), lb.main(0, 0) + lb.challenge(0) - lb.challenge(0))
+    b = AP.ProgramBuilder()
+    b.assert_zero(b.main(0, 0) - b.main(0, 0))
+    t = W.synthetic_trace(3, 5, 2)
+    t[7, 0] = 0
+    wl = W.Workload([5], widths=[2], aux_widths=[1], programs=[b.serialize()], traces=[t], log_quotient_degrees=[1],
+                    num_aux_values=[1], lookups=[(1, lb.serialize())])
+    ch = W.initial_challenger(W.fast_pcs_params(), prod_observe)
+    with pytest.raises(B.ProverError, match="denominator"):
+        sess_fast.prove(wl.statement, wl.matrices, ch)
+    # the session stays usable
+    _compare_proofs(sess_fast, W.fast_pcs_params(), W.Workload([5], widths=(9,), aux_widths=(1,)))
+
+
 def test_prove_big_constraint_program(sess_fast):
     # ~2.4k nodes per constraint pair: far above the old 256-node interpreter limit
     import test_airs
