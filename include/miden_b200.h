@@ -242,9 +242,21 @@ typedef enum {
     MDN_INFO_DEEP_EVALS = 5,       /* L EF values, bit-reversed order */
     MDN_INFO_FRI_ROOTS = 6,        /* 4 u64 per round */
     MDN_INFO_QUERY_INDICES = 7,    /* num_queries u64 */
+    MDN_INFO_JIT = 8,              /* per AIR (proof order) of the last proof: 1 = NVRTC kernel, 0 = interpreter */
 } mdn_info;
 /* QUOTIENT_ACC / DEEP_EVALS are only recorded (extra device->host copies) after mdn_set_debug(s, 1). */
 int mdn_set_debug(mdn_session* s, int enable);
+
+/* ---- run-time specialisation of the constraint evaluator -------------------------------------------
+ * AIR programs with at least `min_nodes` nodes (default 256; 0 = never) are lowered to straight-line CUDA,
+ * compiled once per program with NVRTC for sm_100a and cached; smaller ones (and all of them when libnvrtc
+ * is absent) run on the op-list interpreter.  Both produce identical values. */
+int mdn_session_set_jit(mdn_session* s, uint32_t min_nodes);
+/* "nvrtc <version>" or why it is unavailable, plus the reason the last JIT attempt was dropped (compile error,
+ * or the first-use comparison against the interpreter failed -- the interpreter's result is then kept). */
+const char* mdn_jit_status(mdn_session* s);
+/* Codegen + NVRTC only, no device needed: cubin size (> 0) or a negative mdn_status with *err set. */
+long long mdn_jit_compile_check(const uint32_t* program, uint32_t program_words, const char** err);
 /* Copies at most cap u64 into out; returns the number of u64 available (or <0). */
 long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap);
 

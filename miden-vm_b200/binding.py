@@ -69,10 +69,20 @@ EXPORTS = [
     "mdn_prove_commit_aux", "mdn_prove_finish", "mdn_proof_serialize", "mdn_coset_lde_batch",
     "mdn_lmcs_commit", "mdn_poseidon2_permute", "mdn_get_info", "mdn_get_timings",
     "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug", "mdn_session_set_shard",
-    "mdn_session_set_preprocessed",
+    "mdn_session_set_preprocessed", "mdn_session_set_jit", "mdn_jit_compile_check", "mdn_jit_status",
 ]
 
 _lib = None
+
+
+def jit_compile_check(program: np.ndarray) -> int:
+    """Lower + NVRTC-compile a constraint program without touching a device; returns the cubin size."""
+    err = C.c_char_p()
+    prog = np.ascontiguousarray(program, dtype=np.uint32)
+    n = lib().mdn_jit_compile_check(prog.ctypes.data_as(u32p), len(prog), C.byref(err))
+    if n < 0:
+        raise ProverError(n, (err.value or b"").decode())
+    return n
 
 
 class BackendMissing(RuntimeError):
@@ -106,6 +116,11 @@ def lib():
         L.mdn_set_debug.argtypes = [C.c_void_p, C.c_int]
         L.mdn_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHER, C.c_void_p]
         L.mdn_session_set_preprocessed.argtypes = [C.c_void_p, C.POINTER(Statement), C.POINTER(Matrix), u64p]
+        L.mdn_session_set_jit.argtypes = [C.c_void_p, C.c_uint32]
+        L.mdn_jit_status.restype = C.c_char_p
+        L.mdn_jit_status.argtypes = [C.c_void_p]
+        L.mdn_jit_compile_check.restype = C.c_longlong
+        L.mdn_jit_compile_check.argtypes = [u32p, C.c_uint32, C.POINTER(C.c_char_p)]
         L.mdn_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.mdn_challenger_observe.argtypes = [C.POINTER(Challenger), u64p, C.c_size_t]
         L.mdn_challenger_sample.restype = C.c_uint64
@@ -155,6 +170,13 @@ class Session:
         """Hash-shard every proof of this session over `world` ranks (mdn_session_set_shard)."""
         self._allgather_cb = allgather_cb      # keep the ctypes trampoline alive
         self._check(lib().mdn_session_set_shard(self._h, rank, world, allgather_cb, None))
+
+    def set_jit(self, min_nodes: int):
+        """Node threshold above which constraint programs are NVRTC-compiled (0 = interpreter only)."""
+        self._check(lib().mdn_session_set_jit(self._h, min_nodes))
+
+    def jit_status(self) -> str:
+        return lib().mdn_jit_status(self._h).decode()
 
     def set_preprocessed(self, statement: Statement, preprocessed):
         """`Preprocessed::build(statement, config)` on the device; returns the commitment (u64[4]).

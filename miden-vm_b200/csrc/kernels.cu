@@ -11,6 +11,7 @@ namespace mk {
 
 static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return g_launches; }
+void count_launch() { ++g_launches; }
 void reset_launch_count() { g_launches = 0; }
 #define COUNT_LAUNCH() (++g_launches)
 
@@ -830,6 +831,15 @@ __global__ void __launch_bounds__(128) k_grind(const u64* __restrict__ st12, u32
 void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
     u64 mask = (1ull << bits) - 1;
     k_grind<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_state12, in_len, mask, start, count, d_result);
+    COUNT_LAUNCH();
+}
+
+__global__ void k_compare(const u64* __restrict__ a, const u64* __restrict__ b, size_t n, u32* flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) atomicOr(flag, 4u);
+}
+void launch_compare(const u64* a, const u64* b, size_t n, u32* flag, cudaStream_t st) {
+    k_compare<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, n, flag);
     COUNT_LAUNCH();
 }
 

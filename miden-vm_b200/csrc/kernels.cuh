@@ -156,6 +156,8 @@ void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, u64*
 void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result /* init ~0 */,
                   cudaStream_t st);
 
+// sets *flag |= 4 when a[i] != b[i] for some i < n (self-check of the NVRTC constraint kernels)
+void launch_compare(const u64* a, const u64* b, size_t n, u32* flag, cudaStream_t st);
 void launch_gather(const u64* const* d_ptrs, u64* d_out, size_t n, cudaStream_t st);
 
 // test/export helper: LDE (coset-major columns) -> row-major with bit-reversed rows
@@ -163,6 +165,7 @@ void launch_export_lde_bitrev_rm(const u64* lde, u32 log_n, u32 log_blowup, u32 
 
 void upload_constants();   // Poseidon2 round constants -> __constant__
 unsigned long long launch_count();
+void count_launch();   // for kernels launched outside kernels.cu (the NVRTC constraint kernels)
 void reset_launch_count();
 
 }  // namespace mk

@@ -7,6 +7,7 @@
 #include "../../include/miden_b200.h"
 #include "host_transcript.hpp"
 #include "kernels.cuh"
+#include "jit.hpp"
 
 #include <cstdarg>
 #include <cstdio>
@@ -108,6 +109,9 @@ struct AirHost {
     bool has_lookup = false;
     DevBuf lookup_program, raw_main;
     mk::AirDev lookup_dev;
+    // NVRTC-specialised constraint kernel (jit.hpp) for large programs; NULL = interpreter
+    std::shared_ptr<jit::Kernel> jit;
+    u32 n_constraints = 0;
 };
 
 }  // namespace
@@ -138,6 +142,11 @@ struct mdn_session {
     Committed main_c, aux_c, quot_c;
     // Preprocessed bundle (mdn_session_set_preprocessed): persists across proofs like the reference's borrowed
     // `Preprocessed` (preprocessed.rs:49-61).  prep_air[q] = instance of committed preprocessed trace q.
+    // constraint JIT: programs with at least jit_min_nodes nodes are compiled with NVRTC (0 = never)
+    u32 jit_min_nodes = 256;
+    std::map<u64, std::shared_ptr<jit::Kernel>> jit_kernels;   // loaded modules by program hash
+    std::vector<u64> jit_used;       // per AIR of the last proof: 1 = JIT kernel, 0 = interpreter
+    std::string jit_note;            // why the JIT was not used, if it was wanted
     Committed prep_c; bool has_prep = false;
     std::vector<u32> prep_air, prep_log_h;
     void set_preprocessed(const mdn_statement* st, const mdn_matrix* mats);
@@ -694,6 +703,21 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         h.dev.periodic = a.num_periodic_columns ? h.program.p + per_off : nullptr;
         h.dev.n_instr = (u32)(code.size() / 4); h.dev.n_slots = std::max(1u, n_slots); h.dev.uses_selectors = uses_sel;
         h.dev.log_max_period = a.log_max_period; h.dev.n_periodic = a.num_periodic_columns;
+        // large programs: straight-line kernel compiled once per AIR (jit.hpp); the interpreter stays the fallback
+        h.jit.reset(); h.n_constraints = a.program[3];
+        if (jit_min_nodes && a.program[2] >= jit_min_nodes) {
+            try {
+                u64 key = jit::fnv1a(a.program, a.program_words) ^ ((u64)a.program_words << 40);
+                auto it = jit_kernels.find(key);
+                if (it == jit_kernels.end()) {
+                    const std::vector<char>& cubin = jit::cubin_for(a.program, a.program_words, nullptr);
+                    auto kn = std::make_shared<jit::Kernel>();
+                    kn->load(cubin);
+                    it = jit_kernels.emplace(key, kn).first;
+                }
+                h.jit = it->second;
+            } catch (const std::exception& e) { jit_note = e.what(); }
+        }
         // lowered LookupAir -> the aux trace of this AIR is built on the device (commit_aux)
         h.has_lookup = a.lookup != nullptr;
         if (h.has_lookup) {
@@ -955,6 +979,8 @@ void mdn_session::finish() {
     E2 alpha = tr.ch.sample_ext(), beta = tr.ch.sample_ext();
     // 4. constraint evaluation + beta accumulation, ascending height (mod.rs:445-537)
     DevBuf acc_pp[2];
+    std::vector<DevBuf> jit_apow;   // alive until the constraint kernels have run
+    jit_used.clear();
     int acc_cur = -1;
     u32 acc_prev_log = 0;
     for (u32 j = 0; j < k; j++) {
@@ -974,7 +1000,50 @@ void mdn_session::finish() {
         ca.acc_in = acc_cur < 0 ? nullptr : acc_pp[acc_cur].p; ca.acc_in_log_n = acc_prev_log; ca.acc_out = acc_pp[nxt].p;
         ca.T = &ntt(ln).T;
         ProfScope ps(prof, PC_CONSTRAINTS);
-        if (mk::launch_constraints(ca, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "constraint program too large for the interpreter");
+        if (air.jit && air.jit->checked < 0) air.jit.reset();   // failed its self-check earlier in this session
+        jit_used.push_back(air.jit ? 1 : 0);
+        if (air.jit) {
+            // alpha^(K-1-k) for the K constraints in emission order
+            u32 K = air.n_constraints;
+            std::vector<E2> apow(std::max(1u, K));
+            { E2 x = gl::e2(1, 0); for (u32 q = K; q-- > 0;) { apow[q] = x; x = gl::e2_mul(x, alpha); } }
+            jit_apow.emplace_back(); jit_apow.back().alloc(2 * (size_t)std::max(1u, K), stream);
+            CUDA_OK(cudaMemcpyAsync(jit_apow.back().p, apow.data(), apow.size() * sizeof(E2), cudaMemcpyHostToDevice, stream));
+            CUDA_OK(cudaStreamSynchronize(stream));   // apow is a stack vector
+            jit::JitArgs ja{};
+            ja.main_lde = ca.main_lde; ja.aux_lde = ca.aux_lde; ja.prep_lde = ca.prep_lde;
+            ja.publics = ca.publics; ja.challenges = ca.challenges; ja.aux_values = ca.aux_values;
+            ja.periodic = air.dev.periodic; ja.apow = jit_apow.back().p;
+            ja.acc_in = ca.acc_in; ja.acc_out = ca.acc_out; ja.w_hi = ca.T->w_hi; ja.w_lo = ca.T->w_lo;
+            ja.shift = gl::lde_shift(ln + lb); ja.w_l = gl::two_adic_generator(ln + lb); ja.w_h_inv = gl::inv(gl::two_adic_generator(ln));
+            { u64 s_pow_n = gl::exp_pow2(ja.shift, ln), w_b = gl::two_adic_generator(lb), x = 1;   // Z_H on coset t (domain.rs:742-749)
+              for (u32 t = 0; t < B; t++) { ja.zh[t] = gl::sub(gl::mul(s_pow_n, x), 1); ja.inv_zh[t] = gl::inv(ja.zh[t]); x = gl::mul(x, w_b); } }
+            ja.beta_a = beta.a; ja.beta_b = beta.b;
+            ja.log_n = ln; ja.log_b = lb; ja.acc_in_log_n = ca.acc_in_log_n; ja.lo_bits = ca.T->lo_bits; ja.log_max_period = air.dev.log_max_period;
+            size_t Lj = (size_t)1 << (ln + lb);
+            try { air.jit->launch(ja, (unsigned)((Lj + 127) / 128), 128, stream); }
+            catch (const std::exception& e) { fail(MDN_ERR_CUDA, "%s", e.what()); }
+            mk::count_launch();
+            if (air.jit->checked == 0) {
+                // first use of this compiled kernel in the session: the interpreter evaluates the same points and
+                // the two accumulators must agree word for word; on disagreement (a compiler defect) the interpreter's
+                // result is kept, the kernel is retired and the reason is recorded
+                DevBuf chk; chk.alloc(2 * Lj, stream);
+                mk::ConstraintArgs cb = ca; cb.acc_out = chk.p;
+                if (mk::launch_constraints(cb, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "constraint program too large for the interpreter");
+                mk::launch_compare(chk.p, ca.acc_out, 2 * Lj, (u32*)d_flag.p, stream);
+                u32 flag = 0;
+                CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
+                CUDA_OK(cudaStreamSynchronize(stream));
+                if (flag) {
+                    CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));
+                    CUDA_OK(cudaMemcpyAsync(ca.acc_out, chk.p, 2 * Lj * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
+                    CUDA_OK(cudaStreamSynchronize(stream));
+                    air.jit->checked = -1; jit_used.back() = 0;
+                    jit_note = "NVRTC kernel disagreed with the interpreter on its first use; interpreter kept";
+                } else air.jit->checked = 1;
+            }
+        } else if (mk::launch_constraints(ca, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "constraint program too large for the interpreter");
         acc_cur = nxt; acc_prev_log = ln;
     }
     DevBuf acc = std::move(acc_pp[acc_cur]);
@@ -1378,6 +1447,8 @@ void mdn_session_destroy(mdn_session* s) {
     s->prep_c = Committed();
     s->d_publics.release(); s->d_randomness.release(); s->d_aux_values.release(); s->d_flag.release();
     s->ntt_plans.clear(); s->premul_plans.clear();
+    for (auto& a : s->airs) a.jit.reset();
+    s->jit_kernels.clear();
     cudaStreamSynchronize(s->stream);
     for (auto& evn : s->ev) cudaEventDestroy(evn);
     for (auto& evn : s->copy_ev) cudaEventDestroy(evn);
@@ -1564,6 +1635,7 @@ long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap)
         case MDN_INFO_DEEP_EVALS: v = s->dbg_deep; break;
         case MDN_INFO_FRI_ROOTS: v = s->dbg_fri_roots; break;
         case MDN_INFO_QUERY_INDICES: v = s->dbg_queries; break;
+        case MDN_INFO_JIT: v = s->jit_used; break;
         default: return -1;
     }
     if (out) for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
@@ -1587,6 +1659,36 @@ int mdn_session_set_preprocessed(mdn_session* s, const mdn_statement* st, const 
     } catch (const MdnError& e) { s->error = e.what(); s->prep_c = Committed(); s->has_prep = false; return e.code; }
     catch (const std::exception& e) { s->error = e.what(); s->prep_c = Committed(); s->has_prep = false; return MDN_ERR_INVALID_ARG; }
     return MDN_OK;
+}
+
+const char* mdn_jit_status(mdn_session* s) {
+    static thread_local std::string msg;
+    jit::Nvrtc& n = jit::nvrtc();
+    msg = n.ok() ? "nvrtc " + std::to_string(n.version / 100) + "." + std::to_string(n.version % 100) : "nvrtc unavailable (" + n.why + ")";
+    if (s && !s->jit_note.empty()) msg += "; " + s->jit_note;
+    return msg.c_str();
+}
+
+int mdn_session_set_jit(mdn_session* s, uint32_t min_nodes) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    s->jit_min_nodes = min_nodes;
+    return MDN_OK;
+}
+
+// Codegen + NVRTC only (no device needed): returns the cubin size, or a negative status with the compiler log
+// in *err (static buffer).  Lets CPU-only CI check that an AIR lowers and compiles.
+long long mdn_jit_compile_check(const uint32_t* program, uint32_t program_words, const char** err) {
+    static thread_local std::string msg;
+    try {
+        if (!program || program_words < 5 || program[0] != 0x5249414Du || program[1] != 1 ||
+            (size_t)program_words != 5 + 3 * (size_t)program[2] + program[3] + 2 * (size_t)program[4]) { msg = "bad constraint program"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
+        for (u32 j = 0; j < program[2]; j++) {
+            u32 op = program[5 + 3 * j], x = program[6 + 3 * j], y = program[7 + 3 * j];
+            if (op > 15 || (op >= 10 && op <= 12 && (x >= j || y >= j)) || (op == 13 && x >= j) || ((op == 8) && x >= program[4]) || (op == 9 && x + 1 >= program[4])) { msg = "malformed node"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
+        }
+        for (u32 q = 0; q < program[3]; q++) if (program[5 + 3 * (size_t)program[2] + q] >= program[2]) { msg = "bad constraint id"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
+        return (long long)jit::cubin_for(program, program_words, nullptr).size();
+    } catch (const std::exception& e) { msg = e.what(); if (err) *err = msg.c_str(); return MDN_ERR_UNSUPPORTED; }
 }
 
 int mdn_set_debug(mdn_session* s, int enable) {

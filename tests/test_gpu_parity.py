@@ -280,6 +280,59 @@ def test_logup_zero_denominator_is_an_error(sess_fast):
     _compare_proofs(sess_fast, W.fast_pcs_params(), W.Workload([5], widths=(9,), aux_widths=(1,)))
 
 
+def _jit_session(params, min_nodes):
+    s = B.Session(params, device=0)
+    B.lib().mdn_set_debug(s.handle, 1)
+    s.set_jit(min_nodes)
+    return s
+
+
+@pytest.mark.parametrize("case", ["fib_aux_selectors", "periodic", "logup", "mixed_degrees", "big_program", "preprocessed"])
+def test_jit_constraint_kernels_match_oracle(case):
+    # every AIR forced through the NVRTC-specialised kernel (threshold 1 node): proofs stay bit-exact
+    import test_airs
+    params = W.fast_pcs_params()
+    s = _jit_session(params, 1)
+    builder = None
+    if case == "fib_aux_selectors":
+        wl, builder = test_airs.fib_product_workload([6, 4])
+    elif case == "periodic":
+        wl = test_airs.periodic_workload(6, lqd=3)
+    elif case == "logup":
+        wl, _ = test_airs.logup_workload(7, device=True)
+    elif case == "mixed_degrees":
+        wl = W.Workload([5, 7, 6], widths=(9, 9, 9), aux_widths=(1, 1, 1), log_quotient_degrees=[3, 1, 2],
+                        programs=[AP_degree(9), AP_degree(3), AP_degree(5)])
+    elif case == "big_program":
+        wl = test_airs.big_program_workload(5, n_terms=300)        # 10 k nodes: 21 chunk functions
+    else:
+        wl = test_airs.preprocessed_workload((6, 8), (True, True))
+        s.set_preprocessed(wl.statement, wl.preprocessed_matrices)
+    _compare_proofs(s, params, wl, builder)
+    assert list(s.info(8)) == [1] * wl.k, "the JIT kernel was not used"
+    # and the interpreter on the same session gives the same bytes
+    s.set_jit(0)
+    _compare_proofs(s, params, wl, builder)
+    assert list(s.info(8)) == [0] * wl.k
+
+
+def test_jit_self_check_catches_a_miscompiling_nvrtc():
+    import subprocess, sys, os
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "run_jit_old_nvrtc.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SELF-CHECK OK" in r.stdout or "NOTE" in r.stdout or "SKIP" in r.stdout, r.stdout
+
+
+def AP_degree(d):
+    b = H.pkg.air_program.ProgramBuilder()
+    acc = b.const(1)
+    for j in range(d):
+        acc = acc * b.main(0, j)
+    b.assert_zero(acc)
+    return b.serialize()
+
+
 def test_prove_big_constraint_program(sess_fast):
     # ~2.4k nodes per constraint pair: far above the old 256-node interpreter limit
     import test_airs

@@ -17,7 +17,12 @@ sess = B.Session(params, 0)
 for n_terms in (50, 150, 400):
     wl = test_airs.big_program_workload(18, n_terms=n_terms)
     nodes = int(wl.programs[0][2])
-    for _ in range(2):
+    for mode, thr in (("interpreter", 0), ("nvrtc", 1)):
+        sess.set_jit(thr)
+        t0 = time.time()
         sess.prove(wl.statement, wl.matrices, ch)
-    t = sess.timings()
-    print(f"nodes={nodes} constraints_ms={t.kernel_ms[4]:.2f} total_ms={t.total:.1f} (2^18 rows x 12 cols, 2^21 points)")
+        first = time.time() - t0
+        sess.prove(wl.statement, wl.matrices, ch)
+        t = sess.timings()
+        print(f"nodes={nodes} {mode:11s} constraints_ms={t.kernel_ms[4]:.2f} total_ms={t.total:.1f} first_call_s={first:.1f} "
+              f"jit={list(sess.info(8))} (2^18 rows x 12 cols, 2^21 points)", flush=True)
