@@ -621,28 +621,38 @@ void launch_ef_exclusive_scan(const u64* totals, size_t n, u64* acc0, u64* acc1,
 // OOD evaluation: dot products of coefficient columns with y^(bitrev(p))
 // =============================================================================================
 struct PowTable { E2 sq[24]; };   // sq[i] = y^(2^i)
-__global__ void k_pow_bitrev(PowTable tab, u32 n, u64* __restrict__ wvec) {
+// wvec[p] = y^(bitrev_n(p)) = A[p >> h] * B[p & (2^h - 1)]: the two half tables (2^(n-h) and 2^h entries, built
+// by k_pow_tables with at most n/2 multiplications per entry) replace the per-element product over up to n
+// squares (was 4.8 ms of the 2^20 proof for 18 vectors; now one extension multiplication per element).
+__global__ void k_pow_tables(PowTable tab, u32 n, u32 h, u64* __restrict__ A, u64* __restrict__ B) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 na = 1u << (n - h), nb = 1u << h;
+    if (i >= na + nb) return;
+    bool is_a = i < na;
+    u32 idx = is_a ? i : i - na, bits = is_a ? n - h : h, off = is_a ? h : 0;
+    E2 w = gl::e2(1, 0);
+    for (u32 b = 0; b < bits; b++)
+        if ((idx >> b) & 1) w = gl::e2_mul(w, tab.sq[n - 1 - (off + b)]);   // bit (off + b) of p <-> exponent bit n-1-(off+b)
+    u64* dst = is_a ? A : B;
+    reinterpret_cast<ulonglong2*>(dst)[idx] = make_ulonglong2(w.a, w.b);
+}
+__global__ void k_pow_bitrev(const u64* __restrict__ A, const u64* __restrict__ B, u32 n, u32 h, u64* __restrict__ wvec) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= ((size_t)1 << n)) return;
-    // exponent bitrev_n(p): bit (n-1-i) of the exponent is bit i of p
-    E2 w = gl::e2(1, 0);
-    bool first = true;
-    for (u32 i = 0; i < n; i++) {
-        if ((p >> i) & 1) {
-            E2 f = tab.sq[n - 1 - i];
-            w = first ? f : gl::e2_mul(w, f);
-            first = false;
-        }
-    }
+    ulonglong2 a = reinterpret_cast<const ulonglong2*>(A)[p >> h], b = reinterpret_cast<const ulonglong2*>(B)[p & ((1u << h) - 1)];
+    E2 w = gl::e2_mul(gl::e2(a.x, a.y), gl::e2(b.x, b.y));
     reinterpret_cast<ulonglong2*>(wvec)[p] = make_ulonglong2(w.a, w.b);
 }
-void launch_pow_bitrev(E2 y, u32 n, u64* wvec, cudaStream_t st) {
+void launch_pow_bitrev(E2 y, u32 n, u64* wvec, u64* scratch, cudaStream_t st) {
     size_t N = (size_t)1 << n;
     PowTable tab;
     E2 x = y;
     for (u32 i = 0; i < 24; i++) { tab.sq[i] = x; x = gl::e2_sqr(x); }
-    k_pow_bitrev<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(tab, n, wvec);
-    COUNT_LAUNCH();
+    u32 h = n / 2, na = 1u << (n - h), nb = 1u << h;
+    u64* A = scratch; u64* B = scratch + 2 * (size_t)na;
+    k_pow_tables<<<(na + nb + 127) / 128, 128, 0, st>>>(tab, n, h, A, B);
+    k_pow_bitrev<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(A, B, n, h, wvec);
+    COUNT_LAUNCH(); COUNT_LAUNCH();
 }
 
 static constexpr int OOD_COLS = 8;

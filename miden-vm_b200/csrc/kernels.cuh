@@ -127,8 +127,8 @@ static constexpr u32 LOGUP_MAX_COLS = 16;
 // ---------------------------------------------------------------------------------------------
 // DEEP / FRI / misc
 // ---------------------------------------------------------------------------------------------
-// wvec[p] = y^(bitrev_n(p)) for p < 2^n  (EF interleaved)
-void launch_pow_bitrev(E2 y, u32 n, u64* wvec, cudaStream_t st);
+// wvec[p] = y^(bitrev_n(p)) for p < 2^n  (EF interleaved); scratch: 2 * (2^(n - n/2) + 2^(n/2)) u64
+void launch_pow_bitrev(E2 y, u32 n, u64* wvec, u64* scratch, cudaStream_t st);
 // partial dot products: out[(col * n_chunks + chunk) * 4 + {0,1}] (point 0), {2,3} (point 1)
 void launch_ood_dot(const u64* coef, size_t col_stride, u32 n_cols, u32 n, const u64* w0, const u64* w1,
                     u64* partial, u32 n_chunks, cudaStream_t st);

@@ -1130,8 +1130,10 @@ void mdn_session::finish() {
         auto make_w = [&](u32 ln, E2 y0, E2 y1) {
             keep.emplace_back(); keep.back().alloc((size_t)2 << ln, stream); u64* a = keep.back().p;
             keep.emplace_back(); keep.back().alloc((size_t)2 << ln, stream); u64* b = keep.back().p;
-            mk::launch_pow_bitrev(y0, ln, a, stream);
-            mk::launch_pow_bitrev(y1, ln, b, stream);
+            size_t tw = 2 * (((size_t)1 << (ln - ln / 2)) + ((size_t)1 << (ln / 2)));
+            keep.emplace_back(); keep.back().alloc(2 * tw, stream); u64* sc = keep.back().p;
+            mk::launch_pow_bitrev(y0, ln, a, sc, stream);
+            mk::launch_pow_bitrev(y1, ln, b, sc + tw, stream);
             return std::make_pair(a, b);
         };
         size_t col_off = 0;

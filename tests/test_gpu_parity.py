@@ -370,6 +370,61 @@ def test_full_size_2_20_verifies():
     s.close()
 
 
+def test_config5_shape_2_22_with_preprocessed_verifies():
+    """BASELINE config 5 shape (tallest trace 2^22, mixed heights, a preprocessed tree, full FRI with the
+    production parameters): the proof must be accepted by the oracle verifier.  Narrower than the Miden widths so
+    the host-side trace generation stays in seconds; the maximum supported height and the 11+11 NTT split are what
+    is exercised."""
+    import test_airs
+    params = W.miden_pcs_params()
+    s = B.Session(params, 0)
+    lhs = (22, 18, 20)
+    base = test_airs.preprocessed_workload((6, 6, 6), (True, False, True))       # programs only
+    traces, preps = [], []
+    for i, lh in enumerate(lhs):
+        n = 1 << lh
+        t = W.synthetic_trace(50 + i, lh, 3)
+        if i != 1:
+            pm = W.synthetic_trace(60 + i, lh, 2)
+            t[:, 0] = _mulmod(pm[:, 0], t[:, 1])
+            t[:, 2] = _addmod(np.roll(pm[:, 1], -1), t[:, 1])
+            preps.append(pm)
+        else:
+            t[:, 0] = _mulmod(t[:, 1], t[:, 2])
+            preps.append(None)
+        traces.append(t)
+    wl = W.Workload(list(lhs), widths=[3, 3, 3], aux_widths=[0, 0, 0], programs=base.programs, traces=traces,
+                    log_quotient_degrees=[1, 1, 1], num_aux_values=[0, 0, 0], preprocessed=preps)
+    commitment = s.set_preprocessed(wl.statement, wl.preprocessed_matrices)
+    ch = W.initial_challenger(params, prod_observe)
+    proof = s.prove(wl.statement, wl.matrices, ch)
+    rc, err = H.oracle_verify(params, wl, ch, *proof, prep_commitment=commitment)
+    assert rc == 0, err
+    s.close()
+
+
+def _mulmod(a, b):
+    """Vectorised Goldilocks product of two uint64 arrays (Python-int object arrays would take minutes at 2^22)."""
+    P = int(W.P)
+    a = a.astype(np.uint64); b = b.astype(np.uint64)
+    a0, a1 = a & np.uint64(0xFFFFFFFF), a >> np.uint64(32)
+    b0, b1 = b & np.uint64(0xFFFFFFFF), b >> np.uint64(32)
+    # 128-bit product limbs via float-free 32x32 partials
+    p00 = a0 * b0; p01 = a0 * b1; p10 = a1 * b0; p11 = a1 * b1
+    mid = (p00 >> np.uint64(32)) + (p01 & np.uint64(0xFFFFFFFF)) + (p10 & np.uint64(0xFFFFFFFF))
+    lo = (p00 & np.uint64(0xFFFFFFFF)) | ((mid & np.uint64(0xFFFFFFFF)) << np.uint64(32))
+    hi = p11 + (p01 >> np.uint64(32)) + (p10 >> np.uint64(32)) + (mid >> np.uint64(32))
+    # reduce: lo - hh + hl * (2^32 - 1)   (2^64 = 2^32 - 1, 2^96 = -1 mod p); one pass of Python ints for the final mod
+    hh, hl = hi >> np.uint64(32), hi & np.uint64(0xFFFFFFFF)
+    res = (lo.astype(object) - hh.astype(object) + hl.astype(object) * 0xFFFFFFFF) % P
+    return res.astype(np.uint64)
+
+
+def _addmod(a, b):
+    res = (a.astype(object) + b.astype(object)) % int(W.P)
+    return res.astype(np.uint64)
+
+
 def test_large_height_2_21_commit_root(lib, sess, oracle):
     """Heights above 2^20 (n1 = 10, n2 = 11 NTT split; BASELINE config 5 is 2^22): LMCS root of a narrow
     2^21-row matrix against the oracle."""
