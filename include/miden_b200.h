@@ -243,6 +243,7 @@ typedef enum {
     MDN_INFO_FRI_ROOTS = 6,        /* 4 u64 per round */
     MDN_INFO_QUERY_INDICES = 7,    /* num_queries u64 */
     MDN_INFO_JIT = 8,              /* per AIR (proof order) of the last proof: 1 = NVRTC kernel, 0 = interpreter */
+    MDN_INFO_POOL = 9,             /* cudaMallocAsync pool reserved now / high, used now / high (bytes); proof arena capacity (bytes), slabs, driver allocations so far, live blocks */
 } mdn_info;
 /* QUOTIENT_ACC / DEEP_EVALS are only recorded (extra device->host copies) after mdn_set_debug(s, 1). */
 int mdn_set_debug(mdn_session* s, int enable);

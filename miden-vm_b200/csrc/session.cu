@@ -41,18 +41,71 @@ struct MdnError : std::runtime_error {
 
 std::string g_create_error;
 
-// stream-ordered device buffer
+// Proof-lifetime device memory.  Every buffer a proof allocates is gone when the proof ends, and a prover proves
+// the same shapes over and over, so the session owns slabs obtained once with cudaMalloc and hands out blocks by
+// bumping (plus size-keyed reuse of blocks released mid-proof); at the end of a proof the bump pointers go back
+// to zero.  After the first proof of a shape no allocation reaches the driver.  The stream-ordered pool this
+// replaces had to re-map physical memory whenever its free space was fragmented when a 1 GB request arrived --
+// a driver call that stalled 100-200 ms under a loaded neighbour (profiles/r1_summary.md "step-time outliers").
+// Blocks are used on the session's stream only (the copy stream is ordered behind it by events), so handing a
+// released block to the next request is safe in stream order.
+struct Arena {
+    struct Slab { char* base; size_t size, used; };
+    std::vector<Slab> slabs;
+    std::multimap<size_t, char*> free_blocks;
+    size_t live = 0, grow_events = 0;
+    static size_t round_up(size_t b) { return (b + 511) & ~(size_t)511; }
+    void* alloc(size_t bytes) {
+        bytes = round_up(bytes);
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 4) { void* p = it->second; free_blocks.erase(it); live++; return p; }
+        for (Slab& sl : slabs) if (sl.size - sl.used >= bytes) { void* p = sl.base + sl.used; sl.used += bytes; live++; return p; }
+        size_t sz = std::max(bytes, (size_t)1 << 30);
+        char* base = nullptr;
+        CUDA_OK(cudaMalloc((void**)&base, sz));
+        slabs.push_back(Slab{base, sz, bytes});
+        grow_events++; live++;
+        return base;
+    }
+    void free(void* p, size_t bytes) { free_blocks.emplace(round_up(bytes), (char*)p); live--; }
+    // end of a proof: everything must have been released; several slabs are merged into one of the total size
+    void reset() {
+        if (live) return;
+        free_blocks.clear();
+        for (Slab& sl : slabs) sl.used = 0;
+        if (slabs.size() > 1) {
+            size_t total = 0;
+            for (Slab& sl : slabs) total += sl.size;
+            for (Slab& sl : slabs) cudaFree(sl.base);
+            slabs.clear();
+            char* base = nullptr;
+            if (cudaMalloc((void**)&base, total) == cudaSuccess) slabs.push_back(Slab{base, total, 0});
+            else cudaGetLastError();   // the next proof grows again
+        }
+    }
+    void destroy() { for (Slab& sl : slabs) cudaFree(sl.base); slabs.clear(); free_blocks.clear(); live = 0; }
+};
+thread_local Arena* tl_arena = nullptr;   // set while an API call works on a proof
+struct ArenaScope { Arena* prev; explicit ArenaScope(Arena* a) : prev(tl_arena) { tl_arena = a; } ~ArenaScope() { tl_arena = prev; } };
+
+// device buffer: from the proof arena when one is active, else stream-ordered (persistent tables, tools)
 struct DevBuf {
-    u64* p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
+    u64* p = nullptr; size_t n = 0; cudaStream_t st = nullptr; Arena* owner = nullptr;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept { p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; return *this; }
+    DevBuf(DevBuf&& o) noexcept { p = o.p; n = o.n; st = o.st; owner = o.owner; o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; st = o.st; owner = o.owner; o.p = nullptr; o.n = 0; return *this; }
     void alloc(size_t count, cudaStream_t s) {
-        release(); st = s; n = count;
-        if (count) CUDA_OK(cudaMallocAsync((void**)&p, count * sizeof(u64), s));
+        release(); st = s; n = count; owner = tl_arena;
+        if (!count) return;
+        if (owner) p = (u64*)owner->alloc(count * sizeof(u64));
+        else CUDA_OK(cudaMallocAsync((void**)&p, count * sizeof(u64), s));
     }
-    void release() { if (p) { cudaFreeAsync(p, st); p = nullptr; n = 0; } }
+    void release() {
+        if (!p) return;
+        if (owner) owner->free(p, n * sizeof(u64)); else cudaFreeAsync(p, st);
+        p = nullptr; n = 0;
+    }
     ~DevBuf() { release(); }
 };
 
@@ -130,6 +183,8 @@ struct mdn_session {
     std::map<std::pair<u32, u32>, std::unique_ptr<PremulPlan>> premul_plans;   // (n, kind)
 
     // ---- per-proof state ----
+    Arena arena;
+    void release_proof_memory();
     bool in_proof = false;
     std::vector<AirHost> airs;              // instance order
     std::vector<u32> log_heights;           // instance order
@@ -227,7 +282,7 @@ NttPlan& mdn_session::ntt(u32 n) {
     size_t o_hi = push(powers(gl::exp_pow2(w, lo_bits), (size_t)1 << (n - lo_bits)));
     size_t o_ilo = push(powers(wi, (size_t)1 << lo_bits));
     size_t o_ihi = push(powers(gl::exp_pow2(wi, lo_bits), (size_t)1 << (n - lo_bits)));
-    plan->store.alloc(host.size(), stream);
+    { ArenaScope persistent(nullptr); plan->store.alloc(host.size(), stream); }
     CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     u64* b = plan->store.p;
@@ -251,7 +306,7 @@ std::unique_ptr<PremulPlan> make_premul(const std::vector<u64>& bases, u32 n, cu
         for (size_t j1 = 0; j1 < N1; j1++) { host[bases.size() * N2 + b * N1 + j1] = x; x = gl::mul(x, g); }
     }
     auto plan = std::make_unique<PremulPlan>();
-    plan->store.alloc(host.size(), stream);
+    { ArenaScope persistent(nullptr); plan->store.alloc(host.size(), stream); }
     CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     plan->P.tab_a = plan->store.p;
@@ -296,10 +351,18 @@ PremulPlan& mdn_session::premul_quotient(u32 n, u32 log_d) {
 
 void mdn_session::reset_proof() {
     in_proof = false;
-    airs.clear(); log_heights.clear(); order.clear(); publics.clear(); randomness.clear();
-    main_c = Committed(); aux_c = Committed(); quot_c = Committed();
+    log_heights.clear(); order.clear(); publics.clear(); randomness.clear();
     aux_values_p.clear(); aux_values_off.clear();
     tr = Transcript();
+    release_proof_memory();
+}
+
+// Called when no proof-lifetime buffer of a caller's frame is alive any more (API wrappers, error paths).
+void mdn_session::release_proof_memory() {
+    main_c = Committed(); aux_c = Committed(); quot_c = Committed();
+    airs.clear();
+    d_publics.release(); d_randomness.release(); d_aux_values.release();
+    arena.reset();
 }
 
 void mdn_session::check_input_flag(const char* what) {
@@ -632,7 +695,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     memset(&timings, 0, sizeof timings);
     mk::reset_launch_count();
     prof.st = stream; prof.reset(); leaf_bytes = ntt_bytes = 0; perms = 0;
-    if (!d_flag.p) { d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
+    if (!d_flag.p) { ArenaScope persistent(nullptr); d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
     if (!st || !traces || !chal) fail(MDN_ERR_INVALID_ARG, "null argument");
     if (st->n_airs == 0 || st->n_airs > 256) fail(MDN_ERR_INVALID_ARG, "AIR count must be in 1..=256");
     if (params.log_folding_arity < 1 || params.log_folding_arity > 3) fail(MDN_ERR_INVALID_ARG, "invalid folding arity: log_arity %u (must be 1, 2, or 3)", params.log_folding_arity);
@@ -843,7 +906,7 @@ void mdn_session::set_preprocessed(const mdn_statement* st, const mdn_matrix* ma
     if (!st) fail(MDN_ERR_INVALID_ARG, "null argument");
     u32 lb = params.log_blowup;
     if (lb == 0 || lb > 4) fail(MDN_ERR_UNSUPPORTED, "log_blowup must be in 1..=4");
-    if (!d_flag.p) { d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
+    if (!d_flag.p) { ArenaScope persistent(nullptr); d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
     std::vector<u32> ids;
     for (u32 i = 0; i < st->n_airs; i++) {
         if (mats[i].width != st->airs[i].preprocessed_width) fail(MDN_ERR_INVALID_ARG, "AIR %u: preprocessed matrix width %u does not match the declared %u", i, mats[i].width, st->airs[i].preprocessed_width);
@@ -1398,9 +1461,7 @@ void mdn_session::finish() {
     timings.kernel_launches = mk::launch_count();
     prof.resolve(timings.kernel_ms, timings.kernel_regions);
     timings.leaf_hash_bytes = leaf_bytes; timings.ntt_bytes = ntt_bytes; timings.permutations = perms;
-    // release per-proof device memory (returns to the stream-ordered pool)
-    main_c = Committed(); aux_c = Committed(); quot_c = Committed();
-    in_proof = false;
+    in_proof = false;   // the API wrapper returns the proof's device memory to the arena once this frame is gone
 }
 
 // =============================================================================================
@@ -1452,6 +1513,7 @@ void mdn_session_destroy(mdn_session* s) {
     for (auto& a : s->airs) a.jit.reset();
     s->jit_kernels.clear();
     cudaStreamSynchronize(s->stream);
+    s->arena.destroy();
     for (auto& evn : s->ev) cudaEventDestroy(evn);
     for (auto& evn : s->copy_ev) cudaEventDestroy(evn);
     for (int b = 0; b < 2; b++) if (s->bounce[b]) { cudaFreeHost(s->bounce[b]); cudaEventDestroy(s->bounce_ev[b]); }
@@ -1472,6 +1534,7 @@ int mdn_prove_begin(mdn_session* s, const mdn_statement* st, const mdn_matrix* t
                     uint32_t flags, uint64_t main_root[4], uint64_t* randomness_out) {
     if (!s) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
+    ArenaScope proof_memory(&s->arena);
     CUDA_OK(cudaSetDevice(s->device));
     s->prove_begin(st, traces, challenger, flags);
     if (main_root) memcpy(main_root, s->main_c.root, 32);
@@ -1482,6 +1545,7 @@ int mdn_prove_begin(mdn_session* s, const mdn_statement* st, const mdn_matrix* t
 int mdn_prove_commit_aux(mdn_session* s, const mdn_matrix* aux, const uint64_t* const* aux_values, uint64_t aux_root[4]) {
     if (!s) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
+    ArenaScope proof_memory(&s->arena);
     CUDA_OK(cudaSetDevice(s->device));
     s->commit_aux(aux, aux_values, aux == nullptr);
     if (aux_root) memcpy(aux_root, s->aux_c.root, 32);
@@ -1491,9 +1555,11 @@ int mdn_prove_commit_aux(mdn_session* s, const mdn_matrix* aux, const uint64_t* 
 int mdn_prove_finish(mdn_session* s, mdn_proof* out) {
     if (!s || !out) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
+    ArenaScope proof_memory(&s->arena);
     CUDA_OK(cudaSetDevice(s->device));
     s->finish();
     fill_proof(s, out);
+    s->release_proof_memory();
     API_CATCH(s)
 }
 
@@ -1501,6 +1567,7 @@ int mdn_prove(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces,
               mdn_aux_builder build_aux, void* aux_ctx, uint32_t flags, mdn_proof* out) {
     if (!s || !out) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
+    ArenaScope proof_memory(&s->arena);
     CUDA_OK(cudaSetDevice(s->device));
     s->prove_begin(st, traces, challenger, flags);
     if (!build_aux) {
@@ -1529,6 +1596,7 @@ int mdn_prove(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces,
     }
     s->finish();
     fill_proof(s, out);
+    s->release_proof_memory();
     API_CATCH(s)
 }
 
@@ -1638,6 +1706,18 @@ long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap)
         case MDN_INFO_FRI_ROOTS: v = s->dbg_fri_roots; break;
         case MDN_INFO_QUERY_INDICES: v = s->dbg_queries; break;
         case MDN_INFO_JIT: v = s->jit_used; break;
+        case MDN_INFO_POOL: {
+            cudaMemPool_t pool; uint64_t a[4] = {0, 0, 0, 0};
+            if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess) {
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &a[0]);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &a[1]);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &a[2]);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &a[3]);
+            }
+            v.assign(a, a + 4);
+            { size_t cap = 0; for (auto& sl : s->arena.slabs) cap += sl.size; v.push_back(cap); v.push_back(s->arena.slabs.size()); v.push_back(s->arena.grow_events); v.push_back(s->arena.live); }
+            break;
+        }
         default: return -1;
     }
     if (out) for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
