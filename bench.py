@@ -250,10 +250,13 @@ def main():
         leaf_bytes = tim_v.leaf_hash_bytes / max(1, tim_v.kernel_regions[2])
         achieved = leaf_bytes / (leaf_ms * 1e-3) / 1e9 if leaf_ms > 0 else 0.0
         ntt_gbs = tim_v.ntt_bytes / (km[1] * 1e-3) / 1e9 if km[1] > 0 else 0.0
-        traffic = None
+        traffic, traffic_note = None, None
         tf = os.path.join(ROOT, "profiles", "leaf_sponge_traffic.json")
         if os.path.exists(tf):
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            tj = json.load(open(tf))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = (f"ncu --set full capture of the main-tree launch: {traffic / 1e9:.2f} GB DRAM for "
+                            f"{tj.get('algorithmic_bytes_per_launch', 0) / 1e9:.2f} GB algorithmic; `achieved` averages the three leaf-sponge launches of a proof")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_v / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if hash_sharded else "weak", "vs_baseline": None,
@@ -273,7 +276,7 @@ def main():
             "gpu_launches": int(tim_v.kernel_launches) * args.steps * 2 + int(tim_v.kernel_launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon2 leaf sponge, main trace)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_kind} copy bandwidth",
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_kind} copy bandwidth",
                          "note": "integer-ALU bound by construction (~16k instructions per permutation per 64 input bytes); HBM fraction is low on purpose",
                          "permutations_per_s": tim_v.permutations / ((km[2] + km[3]) * 1e-3) if km[2] + km[3] > 0 else None},
             "kernels_ms_per_step": dict(zip(names, km)),

@@ -1209,7 +1209,7 @@ void mdn_session::finish() {
                 if (!cm.width) continue;
                 u32 ln = cm.log_n, lr = log_max_n - ln;
                 size_t Nm = (size_t)1 << ln;
-                u32 n_chunks = (u32)std::max<size_t>(1, std::min<size_t>(Nm / 1024, 1024));
+                u32 n_chunks = (u32)std::max<size_t>(1, std::min<size_t>(Nm / 4096, 256));   // k_ood_reduce walks the chunks serially
                 if (g != gq) {
                     auto it = weights.find(ln);
                     if (it == weights.end()) it = weights.emplace(ln, make_w(ln, gl::e2_exp_pow2(z, lr), gl::e2_exp_pow2(z_next, lr))).first;
