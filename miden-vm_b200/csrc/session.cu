@@ -866,18 +866,24 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         for (u32 j = 0; j < k; j++) staging[j].alloc(((size_t)1 << main_c.mats[j].log_n) * main_c.mats[j].width, stream);
         CUDA_OK(cudaEventRecord(copy_ev[7], stream));
         CUDA_OK(cudaStreamWaitEvent(copy_stream, copy_ev[7], 0));
-        for (u32 j = 0; j < k; j++) {
+        // smallest matrix first: only its copy is exposed, every later copy hides behind the LDE of its predecessors
+        // (the committed order of the matrices does not depend on the order in which they are prepared)
+        std::vector<u32> by_size(k);
+        for (u32 j = 0; j < k; j++) by_size[j] = j;
+        std::stable_sort(by_size.begin(), by_size.end(), [&](u32 a, u32 b) { return staging[a].n < staging[b].n; });
+        for (u32 q = 0; q < k; q++) {
+            u32 j = by_size[q];
             const mdn_matrix& m = traces[order[j]];
             host_to_device(staging[j].p, m.values, staging[j].n);
-            CUDA_OK(cudaEventRecord(copy_ev[j % 7], copy_stream));
-            CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[j % 7], 0));
+            CUDA_OK(cudaEventRecord(copy_ev[q % 7], copy_stream));
+            CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[q % 7], 0));
             {
                 ProfScope ps(prof, PC_TRANSPOSE);
                 mk::launch_transpose_rm_to_cm(staging[j].p, main_c.mats[j].coef, 1u << main_c.mats[j].log_n, main_c.mats[j].width, (u32*)d_flag.p, stream);
             }
-            if (j + 1 == k) CUDA_OK(cudaEventRecord(ev[1], stream));
+            if (q + 1 == k) CUDA_OK(cudaEventRecord(ev[1], stream));
             keep_raw_main(j);
-            lde_matrix(main_c.mats[j]);   // queued behind the copy of matrix j; overlaps the copy of matrix j+1
+            lde_matrix(main_c.mats[j]);   // queued behind the copy of this matrix; overlaps the copy of the next one
         }
     } else {
         for (u32 j = 0; j < k; j++) upload_matrix(traces[order[j]], true, main_c.mats[j].coef);
