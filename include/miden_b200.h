@@ -247,6 +247,10 @@ typedef enum {
 } mdn_info;
 /* QUOTIENT_ACC / DEEP_EVALS are only recorded (extra device->host copies) after mdn_set_debug(s, 1). */
 int mdn_set_debug(mdn_session* s, int enable);
+/* Layout self-description for binding authors: { sizeof pcs_params, challenger, lookup, air; offsetof air.program,
+ * .periodic_values, .preprocessed_width, .lookup; sizeof matrix, statement, proof, timings; offsetof
+ * timings.kernel_ms, .permutations }.  Returns the number of entries. */
+size_t mdn_abi_layout(uint32_t* out, size_t cap);
 
 /* ---- run-time specialisation of the constraint evaluator -------------------------------------------
  * AIR programs with at least `min_nodes` nodes (default 256; 0 = never) are lowered to straight-line CUDA,

@@ -69,7 +69,7 @@ EXPORTS = [
     "mdn_prove_commit_aux", "mdn_prove_finish", "mdn_proof_serialize", "mdn_coset_lde_batch",
     "mdn_lmcs_commit", "mdn_poseidon2_permute", "mdn_get_info", "mdn_get_timings",
     "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug", "mdn_session_set_shard",
-    "mdn_session_set_preprocessed", "mdn_session_set_jit", "mdn_jit_compile_check", "mdn_jit_status",
+    "mdn_session_set_preprocessed", "mdn_session_set_jit", "mdn_jit_compile_check", "mdn_jit_status", "mdn_abi_layout",
 ]
 
 _lib = None
@@ -116,6 +116,8 @@ def lib():
         L.mdn_set_debug.argtypes = [C.c_void_p, C.c_int]
         L.mdn_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHER, C.c_void_p]
         L.mdn_session_set_preprocessed.argtypes = [C.c_void_p, C.POINTER(Statement), C.POINTER(Matrix), u64p]
+        L.mdn_abi_layout.restype = C.c_size_t
+        L.mdn_abi_layout.argtypes = [u32p, C.c_size_t]
         L.mdn_session_set_jit.argtypes = [C.c_void_p, C.c_uint32]
         L.mdn_jit_status.restype = C.c_char_p
         L.mdn_jit_status.argtypes = [C.c_void_p]

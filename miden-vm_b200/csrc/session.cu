@@ -8,6 +8,7 @@
 #include "host_transcript.hpp"
 #include "kernels.cuh"
 #include "jit.hpp"
+#include <cstddef>
 
 #include <cstdarg>
 #include <cstdio>
@@ -1777,6 +1778,18 @@ long long mdn_jit_compile_check(const uint32_t* program, uint32_t program_words,
         for (u32 q = 0; q < program[3]; q++) if (program[5 + 3 * (size_t)program[2] + q] >= program[2]) { msg = "bad constraint id"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
         return (long long)jit::cubin_for(program, program_words, nullptr).size();
     } catch (const std::exception& e) { msg = e.what(); if (err) *err = msg.c_str(); return MDN_ERR_UNSUPPORTED; }
+}
+
+// sizeof / offsetof of every struct of the boundary, so a binding (ctypes, Rust #[repr(C)]) can assert its layout
+size_t mdn_abi_layout(uint32_t* out, size_t cap) {
+    const uint32_t v[] = {
+        (uint32_t)sizeof(mdn_pcs_params), (uint32_t)sizeof(mdn_challenger), (uint32_t)sizeof(mdn_lookup), (uint32_t)sizeof(mdn_air),
+        (uint32_t)offsetof(mdn_air, program), (uint32_t)offsetof(mdn_air, periodic_values), (uint32_t)offsetof(mdn_air, preprocessed_width),
+        (uint32_t)offsetof(mdn_air, lookup), (uint32_t)sizeof(mdn_matrix), (uint32_t)sizeof(mdn_statement), (uint32_t)sizeof(mdn_proof),
+        (uint32_t)sizeof(mdn_timings), (uint32_t)offsetof(mdn_timings, kernel_ms), (uint32_t)offsetof(mdn_timings, permutations)};
+    size_t n = sizeof v / sizeof v[0];
+    if (out) for (size_t i = 0; i < n && i < cap; i++) out[i] = v[i];
+    return n;
 }
 
 int mdn_set_debug(mdn_session* s, int enable) {

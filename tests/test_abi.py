@@ -31,6 +31,21 @@ def test_library_builds_and_exports_every_symbol():
         assert hasattr(lib, name), f"{name} not exported by libmiden_b200.so"
 
 
+def test_ctypes_struct_layouts_match_the_library():
+    import numpy as np
+    lib = B.lib()
+    n = lib.mdn_abi_layout(None, 0)
+    v = np.zeros(n, dtype=np.uint32)
+    lib.mdn_abi_layout(v.ctypes.data_as(B.u32p), n)
+    A, T = B.Air, B.Timings
+    expect = [C.sizeof(B.PcsParams), C.sizeof(B.Challenger), C.sizeof(B.Lookup), C.sizeof(A), A.program.offset, A.periodic_values.offset,
+              A.preprocessed_width.offset, A.lookup.offset, C.sizeof(B.Matrix), C.sizeof(B.Statement), C.sizeof(B.Proof), C.sizeof(T),
+              T.kernel_ms.offset, T.permutations.offset]
+    assert list(v) == expect
+    import oracle_binding as ob      # the oracle's C API mirrors the same structs
+    assert C.sizeof(ob.Air) == C.sizeof(A) and ob.Air.lookup.offset == A.lookup.offset
+
+
 def test_session_create_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
