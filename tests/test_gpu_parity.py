@@ -469,6 +469,33 @@ def test_error_paths(lib, sess):
     wl = W.Workload([5], widths=(9,), aux_widths=(1,), log_quotient_degrees=[4])   # > log_blowup: DomainError
     with pytest.raises(B.ProverError):
         sess.prove(wl.statement, wl.matrices, ch)
+    # height above the supported maximum (2^22): rejected before any upload
+    big = np.zeros((1 << 23, 1), dtype=np.uint64)
+    wl = W.Workload([23], widths=(1,), aux_widths=(0,), traces=[big], programs=[AP_degree(1)], log_quotient_degrees=[1], num_aux_values=[0])
+    with pytest.raises(B.ProverError, match="2\\^22"):
+        sess.prove(wl.statement, wl.matrices, ch)
+    # malformed constraint programs
+    good = W.Workload([5], widths=(9,), aux_widths=(1,))
+    for mutate in (lambda p: p.__setitem__(0, 0x12345678),            # magic
+                   lambda p: p.__setitem__(5, 99),                    # unknown op
+                   lambda p: p.__setitem__(6, 1000),                  # constant index out of range (node 0 is CONST)
+                   lambda p: p.__setitem__(2, int(p[2]) + 1)):        # node count / length mismatch
+        wl = W.Workload([5], widths=(9,), aux_widths=(1,))
+        mutate(wl.programs[0])
+        with pytest.raises(B.ProverError):
+            sess.prove(wl.statement, wl.matrices, ch)
+    # no AIRs at all
+    empty = B.Statement(None, 0, None, 0, None, 0)
+    with pytest.raises(B.ProverError):
+        sess.prove(empty, good.matrices, ch)
+    # a lookup program whose column count disagrees with aux_width
+    import test_airs
+    wl, _ = test_airs.logup_workload(5)
+    wl._airs[0].aux_width = 2
+    with pytest.raises(B.ProverError):
+        sess.prove(wl.statement, wl.matrices, ch)
+    # the session is still usable afterwards
+    _compare_proofs(sess, W.miden_pcs_params(), good)
 
 
 def test_gpu_matches_committed_golden_proofs():
