@@ -185,6 +185,7 @@ struct mdn_session {
 
     // ---- per-proof state ----
     Arena arena;
+    bool use_arena = getenv("MDN_NO_ARENA") == nullptr;   // off: every buffer is its own allocation (compute-sanitizer memcheck)
     void release_proof_memory();
     bool in_proof = false;
     std::vector<AirHost> airs;              // instance order
@@ -1541,7 +1542,7 @@ int mdn_prove_begin(mdn_session* s, const mdn_statement* st, const mdn_matrix* t
                     uint32_t flags, uint64_t main_root[4], uint64_t* randomness_out) {
     if (!s) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
-    ArenaScope proof_memory(&s->arena);
+    ArenaScope proof_memory(s->use_arena ? &s->arena : nullptr);
     CUDA_OK(cudaSetDevice(s->device));
     s->prove_begin(st, traces, challenger, flags);
     if (main_root) memcpy(main_root, s->main_c.root, 32);
@@ -1552,7 +1553,7 @@ int mdn_prove_begin(mdn_session* s, const mdn_statement* st, const mdn_matrix* t
 int mdn_prove_commit_aux(mdn_session* s, const mdn_matrix* aux, const uint64_t* const* aux_values, uint64_t aux_root[4]) {
     if (!s) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
-    ArenaScope proof_memory(&s->arena);
+    ArenaScope proof_memory(s->use_arena ? &s->arena : nullptr);
     CUDA_OK(cudaSetDevice(s->device));
     s->commit_aux(aux, aux_values, aux == nullptr);
     if (aux_root) memcpy(aux_root, s->aux_c.root, 32);
@@ -1562,7 +1563,7 @@ int mdn_prove_commit_aux(mdn_session* s, const mdn_matrix* aux, const uint64_t* 
 int mdn_prove_finish(mdn_session* s, mdn_proof* out) {
     if (!s || !out) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
-    ArenaScope proof_memory(&s->arena);
+    ArenaScope proof_memory(s->use_arena ? &s->arena : nullptr);
     CUDA_OK(cudaSetDevice(s->device));
     s->finish();
     fill_proof(s, out);
@@ -1574,7 +1575,7 @@ int mdn_prove(mdn_session* s, const mdn_statement* st, const mdn_matrix* traces,
               mdn_aux_builder build_aux, void* aux_ctx, uint32_t flags, mdn_proof* out) {
     if (!s || !out) return MDN_ERR_INVALID_ARG;
     API_TRY(s)
-    ArenaScope proof_memory(&s->arena);
+    ArenaScope proof_memory(s->use_arena ? &s->arena : nullptr);
     CUDA_OK(cudaSetDevice(s->device));
     s->prove_begin(st, traces, challenger, flags);
     if (!build_aux) {
