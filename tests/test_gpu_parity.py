@@ -192,6 +192,28 @@ def test_prove_other_fri_arities(log_arity):
         s.close()
 
 
+@pytest.mark.parametrize("pcs,lhs", [((3, 2, 7, 4, 12, 27, 16), [3]),        # 2^6-point LDE < final degree * blowup: zero FRI rounds
+                                     ((3, 2, 7, 4, 12, 27, 16), [4, 6]),     # still zero rounds, two heights
+                                     ((3, 2, 7, 4, 12, 27, 16), [7]),        # exactly at the boundary
+                                     ((1, 1, 0, 0, 0, 3, 0), [2]),           # 4-row trace, blowup 2, no proof-of-work at all
+                                     ((2, 3, 1, 1, 1, 4, 2), [3, 5])])       # arity 8 on tiny domains
+def test_prove_edge_configurations(pcs, lhs):
+    import test_airs
+    params = B.PcsParams(*pcs)
+    s = B.Session(params, device=0)
+    B.lib().mdn_set_debug(s.handle, 1)
+    builder = None
+    if params.log_blowup >= 3:
+        wl = W.Workload(lhs, widths=(9,) * len(lhs), aux_widths=(1,) * len(lhs))
+    elif len(lhs) == 1:
+        wl, builder = test_airs.fib_product_workload(lhs, lqd=1)
+    else:
+        wl = W.Workload(lhs, widths=(9,) * len(lhs), aux_widths=(1,) * len(lhs), log_quotient_degrees=[params.log_blowup] * len(lhs),
+                        programs=[AP_degree(1 + (1 << params.log_blowup)) for _ in lhs])
+    _compare_proofs(s, params, wl, builder)
+    s.close()
+
+
 def test_prove_periodic_columns(sess_fast):
     import test_airs
     _compare_proofs(sess_fast, W.fast_pcs_params(), test_airs.periodic_workload(6, lqd=3))
