@@ -43,6 +43,20 @@ void orc_poseidon2_permute(uint64_t* st, size_t n) {
     }
 }
 
+// n states through the AVX-512 path (8 at a time; the tail and machines without AVX-512 use the scalar code).
+// Returns 1 when the vector path ran.
+int orc_poseidon2_permute_x8(uint64_t* st, size_t n) {
+    std::vector<State> s(n);
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < 12; k++) s[i][k] = Fp(st[12 * i + k]);
+    size_t i = 0; int used = 0;
+#if ORC_HAVE_X8
+    if (x8_available()) { for (; i + 8 <= n; i += 8) poseidon2_permute_x8(&s[i]); used = n >= 8; }
+#endif
+    for (; i < n; i++) poseidon2_permute(s[i]);
+    for (size_t j = 0; j < n; j++) for (int k = 0; k < 12; k++) st[12 * j + k] = s[j][k].v;
+    return used;
+}
+
 uint64_t orc_fp_mul(uint64_t a, uint64_t b) { return (Fp(a) * Fp(b)).v; }
 uint64_t orc_fp_inv(uint64_t a) { return fp_inv(Fp(a)).v; }
 uint64_t orc_two_adic_generator(uint32_t bits) { return two_adic_generator(bits).v; }

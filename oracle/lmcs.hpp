@@ -10,6 +10,7 @@
 #pragma once
 #include "ntt.hpp"
 #include "transcript.hpp"
+#include "poseidon2_x8.hpp"
 #include <algorithm>
 #include <map>
 
@@ -43,8 +44,16 @@ struct LmcsTree {
                 for (size_t i = active; i-- > 0;)
                     for (size_t k = 0; k < f; k++) states[i * f + k] = states[i];
             }
+#if ORC_HAVE_X8
+            if (h >= 8 && x8_available()) {   // 8 leaves per AVX-512 permutation
 #pragma omp parallel for schedule(static) if (h > 256)
-            for (size_t r = 0; r < h; r++) sponge_absorb(states[r], m.row(r), m.width);
+                for (size_t r8 = 0; r8 < h / 8; r8++) sponge_absorb_x8(&states[8 * r8], m.row(8 * r8), m.width, m.width);
+            } else
+#endif
+            {
+#pragma omp parallel for schedule(static) if (h > 256)
+                for (size_t r = 0; r < h; r++) sponge_absorb(states[r], m.row(r), m.width);
+            }
             active = h;
         }
         unsigned lg = log2_strict(H);
@@ -55,8 +64,16 @@ struct LmcsTree {
         for (unsigned d = lg; d-- > 0;) {
             const std::vector<Digest>& prev = t.layers[d + 1];
             std::vector<Digest> next(prev.size() / 2);
+#if ORC_HAVE_X8
+            if (next.size() >= 8 && x8_available()) {
 #pragma omp parallel for schedule(static) if (next.size() > 256)
-            for (size_t i = 0; i < next.size(); i++) next[i] = compress2(prev[2 * i], prev[2 * i + 1]);
+                for (size_t i8 = 0; i8 < next.size() / 8; i8++) compress2_x8(&prev[16 * i8], &next[8 * i8]);
+            } else
+#endif
+            {
+#pragma omp parallel for schedule(static) if (next.size() > 256)
+                for (size_t i = 0; i < next.size(); i++) next[i] = compress2(prev[2 * i], prev[2 * i + 1]);
+            }
             t.layers[d] = std::move(next);
         }
         return t;

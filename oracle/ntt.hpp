@@ -6,6 +6,7 @@
 // reference's NaiveDft differentials, e.g. crates/lifted-stark/src/prover/quotient.rs:254-265).
 #pragma once
 #include "field.hpp"
+#include "poseidon2_x8.hpp"
 #include <cstring>
 
 namespace orc {
@@ -35,7 +36,9 @@ inline void bit_reverse_rows(Matrix& m) {
 
 // In-place decimation-in-frequency transform on rows: natural-order input, BIT-REVERSED output.
 // out[bitrev(k)] = sum_j in[j] * root^(j k), root a primitive height-th root of unity.
-inline void dif_rows(Matrix& m, Fp root) {
+// Reference form (one pass over the whole row-major matrix per stage); kept for small inputs and as the
+// definition the column-wise routine below is tested against.
+inline void dif_rows_rowmajor(Matrix& m, Fp root) {
     size_t n = m.height, w = m.width;
     if (n <= 1) return;
     unsigned lg = log2_strict(n);
@@ -45,7 +48,6 @@ inline void dif_rows(Matrix& m, Fp root) {
     for (unsigned s = 0; s < lg; s++) {
         size_t half = n >> (s + 1);           // butterfly span
         size_t nblocks = size_t(1) << s;
-#pragma omp parallel for schedule(static) if (n * w > (1u << 16))
         for (size_t bj = 0; bj < nblocks * half; bj++) {
             size_t b = bj / half, j = bj % half;
             Fp t = tw[j << s];
@@ -58,6 +60,70 @@ inline void dif_rows(Matrix& m, Fp root) {
             }
         }
     }
+}
+
+// One column (contiguous, length n): the same DIF.  stage_tw[s] holds the `half = n >> (s+1)` twiddles of stage
+// s contiguously, so the inner loop is unit-stride in data and twiddles (and runs 8 butterflies per AVX-512 step).
+#if ORC_HAVE_X8
+ORC_X8_FN inline void dif_stage_x8(Fp* x, Fp* y, const Fp* t, size_t half) {
+    for (size_t j = 0; j < half; j += 8) {
+        __m512i a = _mm512_loadu_si512((const void*)(x + j)), d = _mm512_loadu_si512((const void*)(y + j));
+        __m512i tw = _mm512_loadu_si512((const void*)(t + j));
+        _mm512_storeu_si512((void*)(x + j), x8::add(a, d));
+        _mm512_storeu_si512((void*)(y + j), x8::mul(x8::sub(a, d), tw));
+    }
+}
+#endif
+inline void dif_column(Fp* col, size_t n, const std::vector<std::vector<Fp>>& stage_tw, bool vec) {
+    unsigned lg = log2_strict(n);
+    for (unsigned s = 0; s < lg; s++) {
+        size_t half = n >> (s + 1), nblocks = size_t(1) << s;
+        const Fp* t = stage_tw[s].data();
+        for (size_t b = 0; b < nblocks; b++) {
+            Fp* x = col + b * 2 * half; Fp* y = x + half;
+#if ORC_HAVE_X8
+            if (vec && half >= 8) { dif_stage_x8(x, y, t, half); continue; }
+#endif
+            for (size_t j = 0; j < half; j++) {
+                Fp a = x[j], d = y[j];
+                x[j] = a + d;
+                y[j] = (a - d) * t[j];
+            }
+        }
+    }
+}
+
+// Matrix form: transpose to columns, one cache-resident transform per column (threads over columns), transpose
+// back.  Same result as dif_rows_rowmajor (exact field arithmetic); tests/test_oracle.py checks both against the
+// naive DFT.
+inline void dif_rows(Matrix& m, Fp root) {
+    size_t n = m.height, w = m.width;
+    if (n <= 1 || w == 0) return;
+    if (n * w < (size_t(1) << 12)) { dif_rows_rowmajor(m, root); return; }
+    unsigned lg = log2_strict(n);
+    std::vector<std::vector<Fp>> stage_tw(lg);
+    {
+        std::vector<Fp> tw(n / 2);
+        tw[0] = Fp::raw(1);
+        for (size_t i = 1; i < n / 2; i++) tw[i] = tw[i - 1] * root;
+        for (unsigned s = 0; s < lg; s++) {
+            size_t half = n >> (s + 1);
+            stage_tw[s].resize(half);
+            for (size_t j = 0; j < half; j++) stage_tw[s][j] = tw[j << s];
+        }
+    }
+    const bool vec = x8_available();
+    std::vector<Fp> cols(n * w);
+#pragma omp parallel for schedule(static)
+    for (size_t r0 = 0; r0 < n; r0 += 64)
+        for (size_t c = 0; c < w; c++)
+            for (size_t r = r0; r < std::min(n, r0 + 64); r++) cols[c * n + r] = m.v[r * w + c];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c = 0; c < w; c++) dif_column(cols.data() + c * n, n, stage_tw, vec);
+#pragma omp parallel for schedule(static)
+    for (size_t r0 = 0; r0 < n; r0 += 64)
+        for (size_t c = 0; c < w; c++)
+            for (size_t r = r0; r < std::min(n, r0 + 64); r++) m.v[r * w + c] = cols[c * n + r];
 }
 
 // Forward DFT, natural in -> natural out:  out[k] = sum_j in[j] * omega_n^(j k).

@@ -29,6 +29,25 @@ def test_poseidon2_permutation_kat(oracle):
     assert [int(x) for x in st] == [int(x, 16) for x in kat["output_hex"]]
 
 
+def test_poseidon2_x8_matches_scalar(oracle):
+    # the AVX-512 packing used by the tree builder (oracle/poseidon2_x8.hpp) against the scalar definition,
+    # including 0, p-1 and a ragged tail that falls back to the scalar code
+    oracle.orc_poseidon2_permute_x8.argtypes = [ob.u64p, C.c_size_t]
+    oracle.orc_poseidon2_permute_x8.restype = C.c_int
+    rng = np.random.default_rng(7)
+    P = 0xFFFFFFFF00000001
+    n = 8 * 25 + 3
+    a = rng.integers(0, 2**63, size=12 * n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=12 * n, dtype=np.uint64)
+    a = np.where(a >= np.uint64(P), a - np.uint64(P), a).astype(np.uint64)
+    a[:12] = 0
+    a[12:24] = P - 1
+    a[24:36] = np.arange(12)
+    b, c = a.copy(), a.copy()
+    oracle.orc_poseidon2_permute(ob.ptr(b), n)
+    oracle.orc_poseidon2_permute_x8(ob.ptr(c), n)
+    assert np.array_equal(b, c)
+
+
 def test_field_constants(oracle):
     # constants.masm:5 ROOT_UNITY; random_coin.masm:426-440 (g = 7, TWO_ADICITY = 32)
     kat = json.load(open(os.path.join(GOLDEN, "field_constants.json")))
