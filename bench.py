@@ -137,8 +137,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log-height", type=int, default=20)
-    ap.add_argument("--ref-log-height", type=int, default=16)
-    ap.add_argument("--cpu-log-height", type=int, default=16)
+    ap.add_argument("--ref-log-height", type=int, default=18)
+    ap.add_argument("--cpu-log-height", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharding", choices=["proof", "hash"], default="proof",
                     help="N>1: 'proof' = one independent proof per GPU (throughput, default); 'hash' = ONE proof whose "
