@@ -143,7 +143,6 @@ struct Tree {
     DevBuf nodes;   // heap layout: layer d at ((1<<d)-1)*4, 4 u64 per digest
     u32 depth = 0;
     u64* layer(u32 d) { return nodes.p + (((size_t)1 << d) - 1) * 4; }
-    const u64* layer(u32 d) const { return nodes.p + (((size_t)1 << d) - 1) * 4; }
 };
 
 struct CommittedMat { u64* lde; u64* coef; u32 log_n, width; };
@@ -227,7 +226,7 @@ struct mdn_session {
     NttPlan& ntt(u32 n);
     PremulPlan& premul_trace(u32 n);
     PremulPlan& premul_quotient(u32 n, u32 log_d);
-    void build_tree(Committed& c, bool aligned_unused);
+    void build_tree(Committed& c);
     void lde_matrix(CommittedMat& m);
     void keep_raw_main(u32 j);
     void build_logup_aux(u32 j, u64* aux_cm, u64 final_out[2]);
@@ -455,7 +454,7 @@ void mdn_session::lde_and_commit(Committed& c, float* t_lde, float* t_hash, bool
     CUDA_OK(cudaEventRecord(e0, stream));
     if (!lde_done) for (auto& m : c.mats) lde_matrix(m);
     CUDA_OK(cudaEventRecord(e1, stream));
-    build_tree(c, true);
+    build_tree(c);
     CUDA_OK(cudaEventRecord(e2, stream));
     CUDA_OK(cudaEventSynchronize(e2));
     float a = 0, b = 0;
@@ -465,7 +464,7 @@ void mdn_session::lde_and_commit(Committed& c, float* t_lde, float* t_hash, bool
 }
 
 // leaf sponge states per height group (ascending), then the compression layers
-void mdn_session::build_tree(Committed& c, bool) {
+void mdn_session::build_tree(Committed& c) {
     u32 lb = params.log_blowup;
     u32 log_n_max = 0;
     for (auto& m : c.mats) log_n_max = std::max(log_n_max, m.log_n);
@@ -1161,7 +1160,7 @@ void mdn_session::finish() {
         u32 per = 2 * B;   // items per chunk t
         for (u32 t = 0; t < D; t++) mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)t * per, per, plan.T, pm.P, stream);
         prof.end(rq);
-        build_tree(quot_c, true);
+        build_tree(quot_c);
         tr.send_commitment(quot_c.root);
         memcpy(dbg_roots[2], quot_c.root, 32);
     }
