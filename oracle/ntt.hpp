@@ -8,6 +8,11 @@
 #include "field.hpp"
 #include "poseidon2_x8.hpp"
 #include <cstring>
+#include <memory>
+#include <new>
+#include <cstdio>
+#include <cstdlib>
+#include <omp.h>
 
 namespace orc {
 
@@ -74,21 +79,34 @@ ORC_X8_FN inline void dif_stage_x8(Fp* x, Fp* y, const Fp* t, size_t half) {
     }
 }
 #endif
-inline void dif_column(Fp* col, size_t n, const std::vector<std::vector<Fp>>& stage_tw, bool vec) {
-    unsigned lg = log2_strict(n);
-    for (unsigned s = 0; s < lg; s++) {
-        size_t half = n >> (s + 1), nblocks = size_t(1) << s;
-        const Fp* t = stage_tw[s].data();
-        for (size_t b = 0; b < nblocks; b++) {
-            Fp* x = col + b * 2 * half; Fp* y = x + half;
+inline void dif_column_stage(Fp* x, Fp* y, const Fp* t, size_t half, bool vec) {
 #if ORC_HAVE_X8
-            if (vec && half >= 8) { dif_stage_x8(x, y, t, half); continue; }
+    if (vec && half >= 8) { dif_stage_x8(x, y, t, half); return; }
 #endif
-            for (size_t j = 0; j < half; j++) {
-                Fp a = x[j], d = y[j];
-                x[j] = a + d;
-                y[j] = (a - d) * t[j];
-            }
+    (void)vec;
+    for (size_t j = 0; j < half; j++) {
+        Fp a = x[j], d = y[j];
+        x[j] = a + d;
+        y[j] = (a - d) * t[j];
+    }
+}
+// After s stages a DIF splits into 2^s independent transforms of size n >> s, so the stages that span more than
+// BLOCK elements stream the whole column and everything below runs block by block while the block sits in cache
+// (7 passes over a 2^21-element column instead of 21).
+inline void dif_column(Fp* col, size_t n, const std::vector<std::vector<Fp>>& stage_tw, bool vec) {
+    const size_t BLOCK = size_t(1) << 14;             // 128 KiB of field elements
+    unsigned lg = log2_strict(n), s_split = 0;
+    while ((n >> s_split) > BLOCK) s_split++;
+    for (unsigned s = 0; s < s_split; s++) {
+        size_t half = n >> (s + 1), nblocks = size_t(1) << s;
+        for (size_t b = 0; b < nblocks; b++) dif_column_stage(col + b * 2 * half, col + b * 2 * half + half, stage_tw[s].data(), half, vec);
+    }
+    size_t bsz = n >> s_split;
+    for (size_t blk = 0; blk < n / bsz; blk++) {
+        Fp* base = col + blk * bsz;
+        for (unsigned s = s_split; s < lg; s++) {
+            size_t half = n >> (s + 1), nsub = bsz / (2 * half);
+            for (size_t b = 0; b < nsub; b++) dif_column_stage(base + b * 2 * half, base + b * 2 * half + half, stage_tw[s].data(), half, vec);
         }
     }
 }
@@ -104,26 +122,38 @@ inline void dif_rows(Matrix& m, Fp root) {
     std::vector<std::vector<Fp>> stage_tw(lg);
     {
         std::vector<Fp> tw(n / 2);
-        tw[0] = Fp::raw(1);
-        for (size_t i = 1; i < n / 2; i++) tw[i] = tw[i - 1] * root;
+        const size_t CH = 4096;
+#pragma omp parallel for schedule(static)
+        for (size_t i0 = 0; i0 < n / 2; i0 += CH) {
+            Fp x = fp_pow(root, i0);
+            for (size_t i = i0; i < std::min(n / 2, i0 + CH); i++) { tw[i] = x; x = x * root; }
+        }
         for (unsigned s = 0; s < lg; s++) {
             size_t half = n >> (s + 1);
             stage_tw[s].resize(half);
+#pragma omp parallel for schedule(static) if (half > 4096)
             for (size_t j = 0; j < half; j++) stage_tw[s][j] = tw[j << s];
         }
     }
     const bool vec = x8_available();
-    std::vector<Fp> cols(n * w);
+    double t0 = omp_get_wtime();
+    // uninitialised scratch: every page is first touched by the thread that fills it
+    std::unique_ptr<Fp, void (*)(void*)> cols_mem((Fp*)malloc(n * w * sizeof(Fp)), free);
+    if (!cols_mem) throw std::bad_alloc();
+    Fp* cols = cols_mem.get();
 #pragma omp parallel for schedule(static)
     for (size_t r0 = 0; r0 < n; r0 += 64)
         for (size_t c = 0; c < w; c++)
             for (size_t r = r0; r < std::min(n, r0 + 64); r++) cols[c * n + r] = m.v[r * w + c];
+    double t1 = omp_get_wtime();
 #pragma omp parallel for schedule(dynamic, 1)
-    for (size_t c = 0; c < w; c++) dif_column(cols.data() + c * n, n, stage_tw, vec);
+    for (size_t c = 0; c < w; c++) dif_column(cols + c * n, n, stage_tw, vec);
+    double t2 = omp_get_wtime();
 #pragma omp parallel for schedule(static)
     for (size_t r0 = 0; r0 < n; r0 += 64)
         for (size_t c = 0; c < w; c++)
             for (size_t r = r0; r < std::min(n, r0 + 64); r++) m.v[r * w + c] = cols[c * n + r];
+    if (getenv("ORC_PROFILE_NTT")) fprintf(stderr, "[dif_rows %zux%zu] tw+alloc+transpose %.0f ms, columns %.0f ms, transpose back %.0f ms\n", n, w, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (omp_get_wtime() - t2) * 1e3);
 }
 
 // Forward DFT, natural in -> natural out:  out[k] = sum_j in[j] * omega_n^(j k).
@@ -150,10 +180,13 @@ inline Matrix coset_lde_bitrev(const Matrix& evals, unsigned added_bits, Fp shif
     idft_rows(c);
     size_t n = c.height, w = c.width, big = n << added_bits;
     Matrix out(big, w);
-    Fp sp = Fp::raw(1);
-    for (size_t k = 0; k < n; k++) {
-        for (size_t j = 0; j < w; j++) out.row(k)[j] = c.row(k)[j] * sp;
-        sp = sp * shift;
+#pragma omp parallel for schedule(static)
+    for (size_t k0 = 0; k0 < n; k0 += 1024) {
+        Fp sp = fp_pow(shift, k0);
+        for (size_t k = k0; k < std::min(n, k0 + 1024); k++) {
+            for (size_t j = 0; j < w; j++) out.row(k)[j] = c.row(k)[j] * sp;
+            sp = sp * shift;
+        }
     }
     dif_rows(out, two_adic_generator(log2_strict(big)));   // leaves rows bit-reversed
     return out;
