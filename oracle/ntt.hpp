@@ -28,13 +28,18 @@ struct Matrix {
 
 inline void bit_reverse_rows(Matrix& m) {
     unsigned lg = log2_strict(m.height);
-    std::vector<Fp> tmp(m.width);
-    for (size_t i = 0; i < m.height; i++) {
-        size_t j = reverse_bits64(i, lg);
-        if (i < j) {
-            memcpy(tmp.data(), m.row(i), m.width * sizeof(Fp));
-            memcpy(m.row(i), m.row(j), m.width * sizeof(Fp));
-            memcpy(m.row(j), tmp.data(), m.width * sizeof(Fp));
+    // each unordered pair (i, bitrev(i)) is swapped by the iteration with the smaller index only
+#pragma omp parallel if (m.height * m.width > (size_t(1) << 16))
+    {
+        std::vector<Fp> tmp(m.width);
+#pragma omp for schedule(static)
+        for (size_t i = 0; i < m.height; i++) {
+            size_t j = reverse_bits64(i, lg);
+            if (i < j) {
+                memcpy(tmp.data(), m.row(i), m.width * sizeof(Fp));
+                memcpy(m.row(i), m.row(j), m.width * sizeof(Fp));
+                memcpy(m.row(j), tmp.data(), m.width * sizeof(Fp));
+            }
         }
     }
 }

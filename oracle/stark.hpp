@@ -322,11 +322,23 @@ inline void pcs_open(const PcsParams& params, unsigned log_max_n, Ef z, Ef z_nex
             widths.push_back(w); aligned_widths.push_back(aw);
             for (int p = 0; p < 2; p++) {
                 Ef x = ef_exp_pow2(pts[p], lr);
-                std::vector<Ef> acc(w);
-                for (size_t k = cm.height; k-- > 0;) {
-                    const Fp* row = cm.row(k);
-                    for (size_t c = 0; c < w; c++) acc[c] = acc[c] * x + row[c];
+                // Horner in row chunks (threads), recombined with x^(chunk start): sum_k row_k x^k
+                const size_t CH = 4096, nch = (cm.height + CH - 1) / CH;
+                std::vector<std::vector<Ef>> part(nch, std::vector<Ef>(w));
+#pragma omp parallel for schedule(static) if (nch > 1)
+                for (size_t t = 0; t < nch; t++) {
+                    std::vector<Ef>& a = part[t];
+                    size_t k1 = std::min(cm.height, (t + 1) * CH);
+                    for (size_t k = k1; k-- > t * CH;) {
+                        const Fp* row = cm.row(k);
+                        for (size_t c = 0; c < w; c++) a[c] = a[c] * x + row[c];
+                    }
                 }
+                std::vector<Ef> acc(w);
+                Ef xch = ef_one();
+                for (size_t i = 0; i < CH && i < cm.height; i++) xch = xch * x;   // x^CH
+                for (size_t t = nch; t-- > 0;)
+                    for (size_t c = 0; c < w; c++) acc[c] = acc[c] * xch + part[t][c];
                 for (size_t c = 0; c < w; c++) flat[p].push_back(acc[c]);
                 for (size_t c = w; c < aw; c++) flat[p].push_back(Ef());
             }
