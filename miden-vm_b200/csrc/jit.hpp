@@ -36,6 +36,15 @@ struct JitArgs {
     uint32_t log_n, log_b, acc_in_log_n, lo_bits, log_max_period, pad;
 };
 
+// Arguments of the generated LogUp row kernel (same member names as JitArgs where the leaf code is shared).
+struct LookupJitArgs {
+    const uint64_t* main_lde;      // raw main trace, column-major [col][row]
+    const uint64_t* publics; const uint64_t* challenges; const uint64_t* periodic;   // periodic: raw row-major matrix
+    uint64_t* aux_cm; uint64_t* totals;
+    uint32_t* bad_flag;
+    uint32_t log_n, n_periodic, log_max_period, pad;
+};
+
 static const char PRELUDE[] = R"CUDA(
 typedef unsigned long long u64;
 typedef unsigned int u32;
@@ -88,6 +97,13 @@ __device__ __forceinline__ E2 eaddf(E2 x, u64 s) { return mk(fadd(x.a, s), x.b);
 __device__ __forceinline__ E2 esubf(E2 x, u64 s) { return mk(fsub(x.a, s), x.b); }      // x - s
 __device__ __forceinline__ E2 efsub(u64 s, E2 x) { return mk(fsub(s, x.a), fneg(x.b)); } // s - x
 __device__ __forceinline__ E2 ldapow(const u64* __restrict__ p, u32 k) { return mk(p[2 * k], p[2 * k + 1]); }
+__device__ E2 einv(E2 x) { u64 n = fsub(fmul(x.a, x.a), fmul7(fmul(x.b, x.b))); u64 ni = finv(n); return mk(fmul(x.a, ni), fneg(fmul(x.b, ni))); }
+struct LookupJitArgs {
+    const u64* main_lde; const u64* publics; const u64* challenges; const u64* periodic;
+    u64* aux_cm; u64* totals;
+    u32* bad_flag;
+    u32 log_n, n_periodic, log_max_period, pad;
+};
 )CUDA";
 
 // ---------------------------------------------------------------------------------------------
@@ -104,10 +120,22 @@ struct GenInfo { uint32_t n_constraints = 0; bool uses_sel = false; uint32_t n_c
 // whose slots are assigned by chunk-granular liveness.
 inline uint32_t chunk_nodes() { const char* e = getenv("MDN_JIT_CHUNK"); uint32_t v = e ? (uint32_t)atoi(e) : 0; return v ? v : 512; }
 
-inline std::string generate(const uint32_t* w, GenInfo* info) {
+// lookup == true: `w` is a lowered LookupAir ("MLKP": 4-word interactions instead of constraint ids) and the
+// kernel is the row kernel of build_logup_aux_trace (one (V, U) rational per aux column, see k_logup_rows).
+inline std::string generate(const uint32_t* w, GenInfo* info, bool lookup = false, uint32_t n_cols = 0) {
     const uint32_t nn = w[2], nc = w[3];
     const uint32_t* cons = w + 5 + 3 * (size_t)nn;
-    const uint32_t* kw = cons + nc;
+    const uint32_t* kw = cons + (lookup ? 4 : 1) * (size_t)nc;
+    const uint32_t NOFLAG = 0xFFFFFFFFu;
+    // operand nodes of item k (constraint: the node itself; interaction: flag?, multiplicity, denominator)
+    auto item_ops = [&](uint32_t k, uint32_t out[3]) -> int {
+        if (!lookup) { out[0] = cons[k]; return 1; }
+        const uint32_t* it = cons + 4 * (size_t)k;
+        int n = 0;
+        if (it[1] != NOFLAG) out[n++] = it[1];
+        out[n++] = it[2]; out[n++] = it[3];
+        return n;
+    };
     std::vector<uint8_t> ext(nn, 0), used(nn, 0), leaf(nn, 0);
     bool uses_sel = false;
     auto OP = [&](uint32_t j) { return w[5 + 3 * j]; };
@@ -120,7 +148,7 @@ inline std::string generate(const uint32_t* w, GenInfo* info) {
         else { ext[j] = (op == 1 || op == 3 || op == 4 || op == 9); leaf[j] = 1; }
         if (op >= 5 && op <= 7) uses_sel = true;
     }
-    for (uint32_t k = 0; k < nc; k++) used[cons[k]] = 1;
+    for (uint32_t k = 0; k < nc; k++) { uint32_t o[3]; int n = item_ops(k, o); for (int q = 0; q < n; q++) used[o[q]] = 1; }
     for (uint32_t j = nn; j-- > 0;) {
         if (!used[j] || leaf[j]) continue;
         used[X(j)] = 1;
@@ -137,6 +165,13 @@ inline std::string generate(const uint32_t* w, GenInfo* info) {
         last_chunk[j] = std::max(last_chunk[j], chunk_of[j]);
         uint32_t ops[2] = {X(j), OP(j) == 13 ? X(j) : Y(j)};
         for (uint32_t o : ops) if (chunk_of[o] != NONE) last_chunk[o] = std::max(last_chunk[o], chunk_of[j]);
+    }
+    // every item (constraint fold / interaction) runs in the last chunk that defines one of its operands
+    std::vector<uint32_t> item_chunk(nc, 0);
+    for (uint32_t k = 0; k < nc; k++) {
+        uint32_t o[3]; int n = item_ops(k, o);
+        for (int q = 0; q < n; q++) if (chunk_of[o[q]] != NONE) item_chunk[k] = std::max(item_chunk[k], chunk_of[o[q]]);
+        for (int q = 0; q < n; q++) if (chunk_of[o[q]] != NONE) last_chunk[o[q]] = std::max(last_chunk[o[q]], item_chunk[k]);
     }
     // slots for values that cross a chunk boundary
     std::vector<uint32_t> slot(nn, NONE);
@@ -192,15 +227,17 @@ inline std::string generate(const uint32_t* w, GenInfo* info) {
     // constraint folds: in the chunk of their node (leaf constraints: chunk 0); weights alpha^(K-1-k) make the
     // order irrelevant
     std::vector<std::vector<uint32_t>> folds(n_chunks);
-    for (uint32_t k = 0; k < nc; k++) folds[chunk_of[cons[k]] == NONE ? 0 : chunk_of[cons[k]]].push_back(k);
+    for (uint32_t k = 0; k < nc; k++) folds[item_chunk[k]].push_back(k);
 
     std::string s;
     s.reserve(80 * (size_t)nn + 16384);
     s += PRELUDE;
+    s += lookup ? "typedef LookupJitArgs KArgs;\n" : "typedef JitArgs KArgs;\n";
     s += "struct Ctx { size_t L, pos, pn, per_idx, per_stride; u64 is_first, is_last, is_trans; };\n";
     std::vector<uint8_t> seen(nn, 0);
     for (uint32_t c = 0; c < n_chunks; c++) {
-        snprintf(buf, sizeof buf, "__device__ __noinline__ void chunk%u(const JitArgs& a, const Ctx& c, u64* __restrict__ Sb, E2* __restrict__ Se, E2& acc) {\n", c);
+        if (lookup) snprintf(buf, sizeof buf, "__device__ __noinline__ void chunk%u(const KArgs& a, const Ctx& c, u64* __restrict__ Sb, E2* __restrict__ Se, E2* __restrict__ V, E2* __restrict__ U) {\n", c);
+        else snprintf(buf, sizeof buf, "__device__ __noinline__ void chunk%u(const KArgs& a, const Ctx& c, u64* __restrict__ Sb, E2* __restrict__ Se, E2& acc) {\n", c);
         s += buf;
         s += "  const size_t L = c.L, pos = c.pos, pn = c.pn, per_idx = c.per_idx, per_stride = c.per_stride;\n"
              "  (void)L; (void)pos; (void)pn; (void)per_idx; (void)per_stride; (void)Sb; (void)Se;\n";
@@ -212,7 +249,7 @@ inline std::string generate(const uint32_t* w, GenInfo* info) {
             uint32_t ops[2] = {X(j), OP(j) == 13 ? X(j) : Y(j)};
             for (uint32_t o : ops) if (leaf[o] || chunk_of[o] != c) want(o);
         }
-        for (uint32_t k : folds[c]) if (leaf[cons[k]]) want(cons[k]);
+        for (uint32_t k : folds[c]) { uint32_t o[3]; int n = item_ops(k, o); for (int q = 0; q < n; q++) if (leaf[o[q]] || chunk_of[o[q]] != c) want(o[q]); }
         for (uint32_t o : need) {
             if (leaf[o]) s += leaf_def(o);
             else { snprintf(buf, sizeof buf, "  const %s %s = %s[%u];\n", ext[o] ? "E2" : "u64", nm(o).c_str(), ext[o] ? "Se" : "Sb", slot[o]); s += buf; }
@@ -220,12 +257,48 @@ inline std::string generate(const uint32_t* w, GenInfo* info) {
         }
         for (uint32_t j = 0; j < nn; j++) if (chunk_of[j] == c) s += arith_def(j);
         for (uint32_t k : folds[c]) {
-            uint32_t cn = cons[k];
-            snprintf(buf, sizeof buf, "  acc = eadd(acc, %s(ldapow(a.apow, %u), %s));\n", ext[cn] ? "emul" : "emulf", k, nm(cn).c_str());
+            if (!lookup) {
+                uint32_t cn = cons[k];
+                snprintf(buf, sizeof buf, "  acc = eadd(acc, %s(ldapow(a.apow, %u), %s));\n", ext[cn] ? "emul" : "emulf", k, nm(cn).c_str());
+                s += buf;
+                continue;
+            }
+            // ProverGroup::insert (air/src/lookup/prover.rs:338-362): push (multiplicity, denominator) unless the flag is zero
+            const uint32_t* it = cons + 4 * (size_t)k;
+            std::string den = ext[it[3]] ? nm(it[3]) : "mk(" + nm(it[3]) + ", 0ull)";
+            std::string cond = it[1] == NOFLAG ? "true" : nm(it[1]) + " != 0ull";
+            s += "  if (" + cond + ") { const E2 d = " + den + "; if ((d.a | d.b) == 0ull) *a.bad_flag = 2u; else { ";
+            snprintf(buf, sizeof buf, "V[%u] = eadd(emul(V[%u], d), emulf(U[%u], %s)); U[%u] = emul(U[%u], d); } }\n", it[0], it[0], it[0], nm(it[2]).c_str(), it[0], it[0]);
             s += buf;
         }
         for (uint32_t j : defined[c]) { snprintf(buf, sizeof buf, "  %s[%u] = %s;\n", ext[j] ? "Se" : "Sb", slot[j], nm(j).c_str()); s += buf; }
         s += "}\n";
+    }
+    if (lookup) {
+        s += "extern \"C\" __global__ void __launch_bounds__(128) k_jit(const KArgs a) {\n"
+             "  Ctx c;\n"
+             "  c.L = (size_t)1 << a.log_n;\n"
+             "  c.pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;\n"
+             "  if (c.pos >= c.L) return;\n"
+             "  c.pn = (c.pos + 1) & (c.L - 1);\n"
+             "  c.per_idx = (c.pos & (((size_t)1 << a.log_max_period) - 1)) * a.n_periodic;\n"
+             "  c.per_stride = 1;\n"
+             "  c.is_first = c.is_last = c.is_trans = 0ull;\n";
+        snprintf(buf, sizeof buf, "  u64 Sb[%u]; E2 Se[%u];\n  E2 V[%u], U[%u];\n  for (int i = 0; i < %u; i++) { V[i] = mk(0ull, 0ull); U[i] = mk(1ull, 0ull); }\n",
+                 std::max(1u, nb), std::max(1u, ne), std::max(1u, n_cols), std::max(1u, n_cols), n_cols);
+        s += buf;
+        for (uint32_t c = 0; c < n_chunks; c++) { snprintf(buf, sizeof buf, "  chunk%u(a, c, Sb, Se, V, U);\n", c); s += buf; }
+        snprintf(buf, sizeof buf, "  E2 t = mk(0ull, 0ull);\n  for (u32 i = 0; i < %uu; i++) {\n", n_cols);
+        s += buf;
+        s += "    E2 f = V[i];\n"
+             "    if (!(U[i].a == 1ull && U[i].b == 0ull)) f = emul(V[i], einv(U[i]));\n"
+             "    t = eadd(t, f);\n"
+             "    if (i > 0) { a.aux_cm[(size_t)(2 * i) * c.L + c.pos] = f.a; a.aux_cm[(size_t)(2 * i + 1) * c.L + c.pos] = f.b; }\n"
+             "  }\n"
+             "  a.totals[2 * c.pos] = t.a; a.totals[2 * c.pos + 1] = t.b;\n"
+             "}\n";
+        if (info) { info->n_constraints = nc; info->uses_sel = false; info->n_chunks = n_chunks; info->spill_base = nb; info->spill_ext = ne; }
+        return s;
     }
     s += "extern \"C\" __global__ void __launch_bounds__(128) k_jit(const JitArgs a) {\n"
          "  Ctx c;\n"
@@ -385,7 +458,8 @@ struct Kernel {
         rc = d.ModuleGetFunction(&func, module, "k_jit");
         if (rc) throw std::runtime_error("cuModuleGetFunction: " + cu_err(rc));
     }
-    void launch(const JitArgs& a, unsigned blocks, unsigned threads, cudaStream_t st) const {
+    template <class Args>
+    void launch(const Args& a, unsigned blocks, unsigned threads, cudaStream_t st) const {
         void* params[] = {(void*)&a};
         int rc = driver().LaunchKernel(func, blocks, 1, 1, threads, 1, 1, 0, (void*)st, params, nullptr);
         if (rc) throw std::runtime_error("cuLaunchKernel: " + cu_err(rc));
@@ -398,15 +472,15 @@ inline uint64_t fnv1a(const uint32_t* w, size_t n) {
     for (size_t i = 0; i < n; i++) { h ^= w[i]; h *= 1099511628211ull; }
     return h;
 }
-inline const std::vector<char>& cubin_for(const uint32_t* w, size_t n_words, GenInfo* info) {
+inline const std::vector<char>& cubin_for(const uint32_t* w, size_t n_words, GenInfo* info, bool lookup = false, uint32_t n_cols = 0) {
     static std::mutex mu;
     static std::map<uint64_t, std::pair<std::vector<char>, GenInfo>> cache;
-    uint64_t key = fnv1a(w, n_words) ^ (uint64_t)n_words << 40 ^ (uint64_t)chunk_nodes() << 20;
+    uint64_t key = fnv1a(w, n_words) ^ (uint64_t)n_words << 40 ^ (uint64_t)chunk_nodes() << 20 ^ (uint64_t)n_cols << 8 ^ (uint64_t)lookup;
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
         GenInfo gi;
-        std::string src = generate(w, &gi);
+        std::string src = generate(w, &gi, lookup, n_cols);
         if (const char* dump = getenv("MDN_JIT_DUMP")) { if (FILE* f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); } }
         it = cache.emplace(key, std::make_pair(compile(src), gi)).first;
         if (const char* dump = getenv("MDN_JIT_DUMP_CUBIN")) { if (FILE* f = fopen(dump, "wb")) { fwrite(it->second.first.data(), 1, it->second.first.size(), f); fclose(f); } }

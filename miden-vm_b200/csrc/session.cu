@@ -163,7 +163,7 @@ struct AirHost {
     DevBuf lookup_program, raw_main;
     mk::AirDev lookup_dev;
     // NVRTC-specialised constraint kernel (jit.hpp) for large programs; NULL = interpreter
-    std::shared_ptr<jit::Kernel> jit;
+    std::shared_ptr<jit::Kernel> jit, lookup_jit;
     u32 n_constraints = 0;
 };
 
@@ -803,6 +803,20 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
             h.lookup_dev.periodic = np ? h.lookup_program.p + p_off : nullptr;
             h.lookup_dev.n_instr = (u32)(lc.code.size() / 4); h.lookup_dev.n_slots = std::max(1u, lc.n_slots);
             h.lookup_dev.log_max_period = a.log_max_period; h.lookup_dev.n_periodic = a.num_periodic_columns;
+            h.lookup_jit.reset();
+            if (jit_min_nodes && lk.program[2] >= jit_min_nodes) {
+                try {
+                    u64 key = jit::fnv1a(lk.program, lk.program_words) ^ ((u64)lk.program_words << 40) ^ 0x4C4B5550ull;
+                    auto it = jit_kernels.find(key);
+                    if (it == jit_kernels.end()) {
+                        const std::vector<char>& cubin = jit::cubin_for(lk.program, lk.program_words, nullptr, true, lk.num_columns);
+                        auto kn = std::make_shared<jit::Kernel>();
+                        kn->load(cubin);
+                        it = jit_kernels.emplace(key, kn).first;
+                    }
+                    h.lookup_jit = it->second;
+                } catch (const std::exception& e) { jit_note = e.what(); }
+            }
         }
     }
     // preprocessed presence / shape parity (ProverInstance::new, prover/mod.rs:139-153; validate_preprocessed,
@@ -964,7 +978,38 @@ void mdn_session::build_logup_aux(u32 j, u64* aux_cm, u64 final_out[2]) {
     la.publics = d_publics.p; la.challenges = d_randomness.p; la.aux_cm = aux_cm; la.totals = totals.p; la.bad_flag = (u32*)d_flag.p;
     {
         ProfScope ps(prof, PC_CONSTRAINTS);
-        if (mk::launch_logup_rows(la, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "lookup program too large for the interpreter");
+        if (h.lookup_jit && h.lookup_jit->checked < 0) h.lookup_jit.reset();
+        if (h.lookup_jit) {
+            jit::LookupJitArgs ja{};
+            ja.main_lde = la.main_cm; ja.publics = la.publics; ja.challenges = la.challenges;
+            ja.periodic = h.lookup_dev.periodic; ja.aux_cm = aux_cm; ja.totals = totals.p; ja.bad_flag = la.bad_flag;
+            ja.log_n = ln; ja.n_periodic = h.lookup_dev.n_periodic; ja.log_max_period = h.lookup_dev.log_max_period;
+            try { h.lookup_jit->launch(ja, (unsigned)((N + 127) / 128), 128, stream); }
+            catch (const std::exception& e) { fail(MDN_ERR_CUDA, "%s", e.what()); }
+            mk::count_launch();
+            if (h.lookup_jit->checked == 0) {
+                // first use: the interpreter builds the same rows into scratch buffers; fraction columns and row totals
+                // must agree word for word, otherwise the interpreter's result is kept and the kernel is retired
+                DevBuf aux2, tot2;
+                u32 C = h.desc.aux_width;
+                aux2.alloc(2 * (size_t)C * N, stream); tot2.alloc(2 * N, stream);
+                mk::LogupArgs lb2 = la; lb2.aux_cm = aux2.p; lb2.totals = tot2.p;
+                if (mk::launch_logup_rows(lb2, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "lookup program too large for the interpreter");
+                if (C > 1) mk::launch_compare(aux2.p + 2 * N, aux_cm + 2 * N, 2 * (size_t)(C - 1) * N, (u32*)d_flag.p, stream);
+                mk::launch_compare(tot2.p, totals.p, 2 * N, (u32*)d_flag.p, stream);
+                u32 flag = 0;
+                CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
+                CUDA_OK(cudaStreamSynchronize(stream));
+                if (flag & 4) {
+                    CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));   // NB: drops a concurrent zero-denominator report; the re-run below raises it again
+                    if (C > 1) CUDA_OK(cudaMemcpyAsync(aux_cm + 2 * N, aux2.p + 2 * N, 2 * (size_t)(C - 1) * N * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
+                    CUDA_OK(cudaMemcpyAsync(totals.p, tot2.p, 2 * N * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
+                    CUDA_OK(cudaStreamSynchronize(stream));
+                    h.lookup_jit->checked = -1;
+                    jit_note = "NVRTC lookup kernel disagreed with the interpreter on its first use; interpreter kept";
+                } else h.lookup_jit->checked = 1;
+            }
+        } else if (mk::launch_logup_rows(la, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "lookup program too large for the interpreter");
         mk::launch_ef_exclusive_scan(totals.p, N, aux_cm, aux_cm + N, fin.p, scratch.p, stream);
     }
     CUDA_OK(cudaMemcpyAsync(final_out, fin.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
@@ -1769,11 +1814,21 @@ int mdn_session_set_jit(mdn_session* s, uint32_t min_nodes) {
 long long mdn_jit_compile_check(const uint32_t* program, uint32_t program_words, const char** err) {
     static thread_local std::string msg;
     try {
-        if (!program || program_words < 5 || program[0] != 0x5249414Du || program[1] != 1 ||
-            (size_t)program_words != 5 + 3 * (size_t)program[2] + program[3] + 2 * (size_t)program[4]) { msg = "bad constraint program"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
+        const bool lookup = program && program_words >= 5 && program[0] == 0x504B4C4Du;
+        if (!program || program_words < 5 || (program[0] != 0x5249414Du && !lookup) || program[1] != 1 ||
+            (size_t)program_words != 5 + 3 * (size_t)program[2] + (lookup ? 4 : 1) * (size_t)program[3] + 2 * (size_t)program[4]) { msg = "bad program"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
         for (u32 j = 0; j < program[2]; j++) {
             u32 op = program[5 + 3 * j], x = program[6 + 3 * j], y = program[7 + 3 * j];
             if (op > 15 || (op >= 10 && op <= 12 && (x >= j || y >= j)) || (op == 13 && x >= j) || ((op == 8) && x >= program[4]) || (op == 9 && x + 1 >= program[4])) { msg = "malformed node"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
+        }
+        if (lookup) {
+            u32 n_cols = 0;
+            for (u32 q = 0; q < program[3]; q++) {
+                const u32* it = program + 5 + 3 * (size_t)program[2] + 4 * (size_t)q;
+                if ((it[1] != 0xFFFFFFFFu && it[1] >= program[2]) || it[2] >= program[2] || it[3] >= program[2] || it[0] >= 16) { msg = "bad interaction"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
+                n_cols = std::max(n_cols, it[0] + 1);
+            }
+            return (long long)jit::cubin_for(program, program_words, nullptr, true, n_cols).size();
         }
         for (u32 q = 0; q < program[3]; q++) if (program[5 + 3 * (size_t)program[2] + q] >= program[2]) { msg = "bad constraint id"; if (err) *err = msg.c_str(); return MDN_ERR_INVALID_ARG; }
         return (long long)jit::cubin_for(program, program_words, nullptr).size();

@@ -332,6 +332,7 @@ def test_jit_constraint_kernels_match_oracle(case):
         s.set_preprocessed(wl.statement, wl.preprocessed_matrices)
     _compare_proofs(s, params, wl, builder)
     assert list(s.info(8)) == [1] * wl.k, "the JIT kernel was not used"
+    assert "disagreed" not in s.jit_status() and "nvrtc 1" in s.jit_status(), s.jit_status()   # incl. the generated LogUp row kernel
     # and the interpreter on the same session gives the same bytes
     s.set_jit(0)
     _compare_proofs(s, params, wl, builder)

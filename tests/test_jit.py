@@ -26,6 +26,7 @@ def test_jit_compiles_every_leaf_kind():
     _check(test_airs.preprocessed_workload().programs[0])       # preprocessed window
     wl, _ = test_airs.logup_workload(5)
     _check(wl.programs[0])                                      # mixed base/extension arithmetic
+    _check(wl._lookups[0][1])                                   # lowered LookupAir -> generated row kernel
 
 
 def test_jit_chunks_large_programs():
