@@ -339,6 +339,21 @@ def test_jit_constraint_kernels_match_oracle(case):
     assert list(s.info(8)) == [0] * wl.k
 
 
+def test_jit_kernels_with_tiny_chunks(monkeypatch):
+    # 5-node chunk functions force cross-chunk spills in both generated kernels (constraints and LogUp rows)
+    import test_airs
+    monkeypatch.setenv("MDN_JIT_CHUNK", "5")
+    params = W.fast_pcs_params()
+    s = _jit_session(params, 1)
+    wl, _ = test_airs.logup_workload(7, device=True)
+    _compare_proofs(s, params, wl)
+    assert list(s.info(8)) == [1] and "disagreed" not in s.jit_status(), s.jit_status()
+    wl, builder = test_airs.fib_product_workload([6, 4])
+    _compare_proofs(s, params, wl, builder)
+    assert "disagreed" not in s.jit_status(), s.jit_status()
+    s.close()
+
+
 def test_jit_self_check_catches_a_miscompiling_nvrtc():
     import subprocess, sys, os
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "run_jit_old_nvrtc.py")],
