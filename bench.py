@@ -273,7 +273,7 @@ def main():
                                      "per-step times are listed so a neighbour-induced stall is visible"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": proof_bytes,
                     "ms_per_step": total_e / args.steps * 1e3, "per_step_ms": [round(x * 1e3, 2) for x in steps_e], "api": "mdn_prove (include/miden_b200.h) with pinned host RowMajorMatrix buffers"},
-            "gpu_launches": int(tim_v.kernel_launches) * args.steps * 2 + int(tim_v.kernel_launches),
+            "gpu_launches": (int(tim_v.kernel_launches) + int(tim_e.kernel_launches)) * args.steps,   # kernels of the K value steps + K e2e steps
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon2 leaf sponge, main trace)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_kind} copy bandwidth",
