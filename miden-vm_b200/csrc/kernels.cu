@@ -4,7 +4,11 @@
 // permutations held entirely in registers, (c) streaming reductions over LDE columns.
 #include "kernels.cuh"
 #include "poseidon2.cuh"
-#include "poseidon2_fast.cuh"
+#ifdef MDN_ARITH_V2
+#include "poseidon2_fast2.cuh"    // second-generation lazy arithmetic (host-checked by tests/cpp/test_arith_v2.cpp)
+#else
+#include "poseidon2_fast.cuh"     // first-generation lazy arithmetic (r1b..r1k measurements)
+#endif
 #include <cstdio>
 
 namespace mk {

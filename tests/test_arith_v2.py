@@ -1,0 +1,18 @@
+"""The second-generation device arithmetic (miden-vm_b200/csrc/poseidon2_fast2.cuh) is written as
+__host__ __device__ code whose only device-specific parts are five carry-flag primitives.  This test
+compiles THAT header for the CPU (tests/cpp/test_arith_v2.cpp) and checks multiplication, the wide
+accumulators, exact division by 2^k, both linear layers and the whole permutation against 128-bit integer
+arithmetic, the canonical p2::permute and the reference KAT (poseidon2/test.rs:7-39), on canonical and
+non-canonical representatives.  The GPU side of the same header is covered by the -m gpu parity tests
+when the library is built with -DMDN_ARITH_V2."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "tests", "cpp")
+
+
+def test_arith_v2_on_host():
+    subprocess.check_call(["make", "-s", "-C", CPP, "test_arith_v2"])
+    r = subprocess.run([os.path.join(CPP, "test_arith_v2")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ARITH_V2_OK" in r.stdout, r.stdout + r.stderr
