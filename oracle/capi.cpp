@@ -62,6 +62,20 @@ uint64_t orc_fp_inv(uint64_t a) { return fp_inv(Fp(a)).v; }
 uint64_t orc_two_adic_generator(uint32_t bits) { return two_adic_generator(bits).v; }
 uint64_t orc_lde_shift(uint32_t log_lde) { return lde_shift(log_lde).v; }
 
+// One FRI fold of a physical (bit-reversed) row of 2^log_arity extension values, as the commit phase and
+// the verifier apply it (pcs/fri/fold/arity{2,4,8}.rs).  row = 2 * 2^log_arity felts, beta/out = 2 felts.
+// Exposed for tests/test_anchors.py, which compares it with the VM's own restatement of the arity-4 fold
+// (processor/src/execution/operations/fri_ops/mod.rs:48-240).
+int orc_fri_fold_row(uint32_t log_arity, const uint64_t* row, uint64_t s_inv, const uint64_t* beta, uint64_t* out) {
+    try {
+        Ef ev[8];
+        for (unsigned j = 0; j < (1u << log_arity); j++) ev[j] = Ef(Fp(row[2 * j]), Fp(row[2 * j + 1]));
+        Ef r = fold_row(log_arity, ev, Fp(s_inv), Ef(Fp(beta[0]), Fp(beta[1])));
+        out[0] = r.a.v; out[1] = r.b.v;
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 static Matrix to_matrix(const orc_matrix& m) {
     Matrix r(size_t(1) << m.log_height, m.width);
     for (size_t i = 0; i < r.v.size(); i++) r.v[i] = Fp(m.values[i]);

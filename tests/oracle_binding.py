@@ -70,6 +70,8 @@ def lib():
         L.orc_two_adic_generator.restype = C.c_uint64; L.orc_two_adic_generator.argtypes = [C.c_uint32]
         L.orc_lde_shift.restype = C.c_uint64; L.orc_lde_shift.argtypes = [C.c_uint32]
         L.orc_poseidon2_permute.argtypes = [u64p, C.c_size_t]
+        L.orc_fri_fold_row.restype = C.c_int
+        L.orc_fri_fold_row.argtypes = [C.c_uint32, u64p, C.c_uint64, u64p, u64p]
         L.orc_naive_dft.argtypes = [u64p, C.c_uint32, u64p]
         L.orc_dft.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_int, u64p]
         L.orc_coset_lde_batch.argtypes = [C.POINTER(Matrix), C.c_uint32, C.c_uint64, u64p]
