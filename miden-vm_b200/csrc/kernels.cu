@@ -4,10 +4,16 @@
 // permutations held entirely in registers, (c) streaming reductions over LDE columns.
 #include "kernels.cuh"
 #include "poseidon2.cuh"
+#if defined(MDN_NTT_V2) && !defined(MDN_ARITH_V2)
+#define MDN_ARITH_V2 1
+#endif
 #ifdef MDN_ARITH_V2
 #include "poseidon2_fast2.cuh"    // second-generation lazy arithmetic (host-checked by tests/cpp/test_arith_v2.cpp)
 #else
 #include "poseidon2_fast.cuh"     // first-generation lazy arithmetic (r1b..r1k measurements)
+#endif
+#ifdef MDN_NTT_V2
+#include "ntt2.cuh"
 #endif
 #include <cstdio>
 
@@ -72,6 +78,7 @@ __device__ __forceinline__ u64 w_pow(const u64* __restrict__ hi, const u64* __re
     return gl::mul(hi[e >> lo_bits], lo[e & ((1ull << lo_bits) - 1)]);
 }
 
+#ifndef MDN_NTT_V2
 // ---------------------------------------------------------------------------------------------
 // Register-tiled radix-2 stages over a shared-memory tile.
 //   tile element (idx, cc), idx < 2^m, cc < 2^log_cols, lives at off(idx, cc); contiguous tiles
@@ -275,6 +282,53 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
         COUNT_LAUNCH();
     }
 }
+
+#else   // MDN_NTT_V2: block functions of ntt2.cuh (host-checked by tests/cpp/test_ntt_v2.cpp) ------------------------
+__global__ void __launch_bounds__(NTT_THREADS) k_intt_strided(u64* cols, size_t col_stride, NttTables T, u32 log_c) {
+    extern __shared__ u64 sm[];
+    ntt2::intt_strided_block(blockIdx.x, blockIdx.y, sm, cols, col_stride, T, log_c);
+}
+__global__ void __launch_bounds__(NTT_THREADS) k_intt_contig(u64* cols, size_t col_stride, NttTables T) {
+    extern __shared__ u64 sm[];
+    ntt2::intt_contig_block(blockIdx.x, blockIdx.y, sm, cols, col_stride, T);
+}
+void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, cudaStream_t st) {
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+    if (T.n1 > 0) {
+        u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
+        u32 C = 1u << log_c;
+        size_t smem = ntt2::smem_words_strided(T.n1, log_c) * sizeof(u64);
+        cudaFuncSetAttribute(k_intt_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_intt_strided<<<dim3(N2 / C, n_cols), ntt_threads(T.n1, log_c), smem, st>>>(cols, col_stride, T, log_c);
+        COUNT_LAUNCH();
+    }
+    size_t smem = ntt2::smem_words_contig_inv(T.n2) * sizeof(u64);
+    k_intt_contig<<<dim3(N1, n_cols), ntt_threads(T.n2, 0), smem, st>>>(cols, col_stride, T);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_contig(const FwdItem* __restrict__ items, NttTables T, PremulTables Pm) {
+    extern __shared__ u64 sm[];
+    ntt2::fwd_contig_block(blockIdx.x, blockIdx.y, sm, items, T, Pm);
+}
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_strided(const FwdItem* __restrict__ items, NttTables T, u32 log_c) {
+    extern __shared__ u64 sm[];
+    ntt2::fwd_strided_block(blockIdx.x, blockIdx.y, sm, items, T, log_c);
+}
+void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, const PremulTables& Pm, cudaStream_t st) {
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+    size_t smem = ntt2::smem_words_contig_fwd(T.n2) * sizeof(u64);
+    k_fwd_contig<<<dim3(N1, n_items), ntt_threads(T.n2, 0), smem, st>>>(d_items, T, Pm);
+    COUNT_LAUNCH();
+    if (T.n1 > 0) {
+        u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
+        u32 C = 1u << log_c;
+        size_t smem2 = ntt2::smem_words_strided(T.n1, log_c) * sizeof(u64);
+        cudaFuncSetAttribute(k_fwd_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        k_fwd_strided<<<dim3(N2 / C, n_items), ntt_threads(T.n1, log_c), smem2, st>>>(d_items, T, log_c);
+        COUNT_LAUNCH();
+    }
+}
+#endif  // MDN_NTT_V2
 
 // =============================================================================================
 // Poseidon2 hashing

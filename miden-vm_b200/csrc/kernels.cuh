@@ -34,9 +34,12 @@ struct NttTables {
 };
 // Pre-multiplication tables for a coset base g: premul(j) = g^j / N with j = j2*N1 + j1:
 //   tab_a[j2] = (g^N1)^j2 (j2 < N2),  tab_b[j1] = g^j1 / N (j1 < N1).  One pair per base.
+//   tab_c[(1 << s) - 1 + j] = (g^N1)^(N2 / 2^(s+1)) * w_{2^(s+1)}^j: per-stage twiddles of the contiguous pass with
+//   the coset shift folded in (second-generation kernels, ntt2.cuh); built by ntt_tables.hpp.
 struct PremulTables {
     const u64* tab_a;   // n_bases x N2
     const u64* tab_b;   // n_bases x N1
+    const u64* tab_c;   // n_bases x N2 (N2 - 1 used)
 };
 
 // d_bad_flag (optional): set to 1 if any value is not a canonical field element (>= p)

@@ -18,6 +18,7 @@
 // representatives (value mod p, not necessarily < p); callers canonicalise what they store.
 #pragma once
 #include "gl.cuh"
+#include "poseidon2.cuh"
 
 namespace glf {
 using gl::u64;

@@ -7,6 +7,7 @@
 #include "../../include/miden_b200.h"
 #include "host_transcript.hpp"
 #include "kernels.cuh"
+#include "ntt_tables.hpp"
 #include "jit.hpp"
 #include <cstddef>
 
@@ -248,19 +249,9 @@ struct mdn_session {
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// table construction (host, tiny) -------------------------------------------------------------
+// table construction (host, tiny): ntt_tables.hpp ------------------------------------------------
 // ---------------------------------------------------------------------------------------------
-void split_n(u32 n, u32& n1, u32& n2) {
-    if (n <= 11) { n1 = 0; n2 = n; }
-    else { n1 = n / 2; n2 = n - n1; }
-}
-
-std::vector<u64> powers(u64 base, size_t count) {
-    std::vector<u64> v(count);
-    u64 x = 1;
-    for (size_t i = 0; i < count; i++) { v[i] = x; x = gl::mul(x, base); }
-    return v;
-}
+using ntt_tables::split_n;
 
 }  // namespace
 
@@ -269,25 +260,11 @@ NttPlan& mdn_session::ntt(u32 n) {
     if (it != ntt_plans.end()) return *it->second;
     if (n > 22) fail(MDN_ERR_UNSUPPORTED, "trace height 2^%u exceeds the supported 2^22", n);
     auto plan = std::make_unique<NttPlan>();
-    u32 n1, n2; split_n(n, n1, n2);
-    u32 lo_bits = (n + 1) / 2;
-    u64 w = gl::two_adic_generator(n), wi = gl::inv(w);
-    std::vector<u64> host;
-    auto push = [&](const std::vector<u64>& v) { size_t off = host.size(); host.insert(host.end(), v.begin(), v.end()); return off; };
-    u64 w1 = gl::two_adic_generator(n1), w2 = gl::two_adic_generator(n2);
-    size_t o_tw1 = push(powers(w1, n1 ? (size_t)1 << (n1 - 1) : 1));
-    size_t o_tw2 = push(powers(w2, n2 ? (size_t)1 << (n2 - 1) : 1));
-    size_t o_twi1 = push(powers(gl::inv(w1), n1 ? (size_t)1 << (n1 - 1) : 1));
-    size_t o_twi2 = push(powers(gl::inv(w2), n2 ? (size_t)1 << (n2 - 1) : 1));
-    size_t o_lo = push(powers(w, (size_t)1 << lo_bits));
-    size_t o_hi = push(powers(gl::exp_pow2(w, lo_bits), (size_t)1 << (n - lo_bits)));
-    size_t o_ilo = push(powers(wi, (size_t)1 << lo_bits));
-    size_t o_ihi = push(powers(gl::exp_pow2(wi, lo_bits), (size_t)1 << (n - lo_bits)));
-    { ArenaScope persistent(nullptr); plan->store.alloc(host.size(), stream); }
-    CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    ntt_tables::NttHost host = ntt_tables::build_ntt(n);
+    { ArenaScope persistent(nullptr); plan->store.alloc(host.data.size(), stream); }
+    CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data.data(), host.data.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
-    u64* b = plan->store.p;
-    plan->T = mk::NttTables{n, n1, n2, lo_bits, b + o_tw1, b + o_tw2, b + o_twi1, b + o_twi2, b + o_lo, b + o_hi, b + o_ilo, b + o_ihi};
+    plan->T = host.view(plan->store.p);
     auto& ref = *plan;
     ntt_plans[n] = std::move(plan);
     return ref;
@@ -295,23 +272,12 @@ NttPlan& mdn_session::ntt(u32 n) {
 
 namespace {
 std::unique_ptr<PremulPlan> make_premul(const std::vector<u64>& bases, u32 n, cudaStream_t stream) {
-    u32 n1, n2; split_n(n, n1, n2);
-    size_t N1 = (size_t)1 << n1, N2 = (size_t)1 << n2;
-    u64 n_inv = gl::inv((u64)1 << n);
-    std::vector<u64> host(bases.size() * (N1 + N2));
-    for (size_t b = 0; b < bases.size(); b++) {
-        u64 g = bases[b], gN1 = gl::exp_pow2(g, n1);
-        u64 x = 1;
-        for (size_t j2 = 0; j2 < N2; j2++) { host[b * N2 + j2] = x; x = gl::mul(x, gN1); }
-        x = n_inv;
-        for (size_t j1 = 0; j1 < N1; j1++) { host[bases.size() * N2 + b * N1 + j1] = x; x = gl::mul(x, g); }
-    }
+    ntt_tables::PremulHost host = ntt_tables::build_premul(bases, n);
     auto plan = std::make_unique<PremulPlan>();
-    { ArenaScope persistent(nullptr); plan->store.alloc(host.size(), stream); }
-    CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    { ArenaScope persistent(nullptr); plan->store.alloc(host.data.size(), stream); }
+    CUDA_OK(cudaMemcpyAsync(plan->store.p, host.data.data(), host.data.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
-    plan->P.tab_a = plan->store.p;
-    plan->P.tab_b = plan->store.p + bases.size() * N2;
+    plan->P = host.view(plan->store.p);
     plan->n_bases = (u32)bases.size();
     return plan;
 }
