@@ -96,6 +96,11 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise BackendMissing(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
         L = C.CDLL(LIB_PATH)
+        if hasattr(L, "mdn_emulated_build") and os.environ.get("MDN_ALLOW_EMULATOR") != "1":
+            # tests/emu builds the kernels for the CPU (one fiber per CUDA thread) so that host logic can be tested
+            # without a GPU; it is test infrastructure and must never stand in for the product
+            raise BackendMissing(f"{LIB_PATH} is the CPU kernel emulator of tests/emu, not the CUDA backend "
+                                 "(there is no CPU fallback; only tests/test_emulated.py may load it)")
         L.mdn_last_error.restype = C.c_char_p
         L.mdn_last_error.argtypes = [C.c_void_p]
         L.mdn_session_create.argtypes = [C.POINTER(PcsParams), C.c_int, C.POINTER(C.c_void_p)]

@@ -25,7 +25,7 @@ namespace ntt2 {
 using gl::u64;
 using gl::u32;
 
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(MDN_EMULATED)   // MDN_EMULATED: tests/emu runs one fiber per CUDA thread
 #define NTT2_FOR(i, n) for (u32 i = threadIdx.x; i < (u32)(n); i += blockDim.x)
 #define NTT2_SYNC() __syncthreads()
 #else
