@@ -23,8 +23,16 @@ W, B = pkg.workload, pkg.binding
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # On the CPU kernel emulator (tests/test_emulated.py) the same host logic runs over gloo: every rank uses
+    # "device" 0 of its own process and the all-gather callback moves host buffers.
+    emulated = os.environ.get("MDN_ALLOW_EMULATOR") == "1"
+    if emulated:
+        dist.init_process_group("gloo")
+        local, dev_name = 0, "cpu"
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dev_name = f"cuda:{local}"
     lib = B.lib()
 
     def observe(c, felts):
@@ -43,11 +51,13 @@ def main():
         ref = single.prove(wl.statement, wl.matrices, ch, cb)
         single.close()
         sh = B.Session(params, local)
-        sh.set_shard(rank, world, pkg.parallel.make_allgather_callback(f"cuda:{local}"))
+        sh.set_shard(rank, world, pkg.parallel.make_allgather_callback(dev_name))
         got = sh.prove(wl.statement, wl.matrices, ch, cb)
         assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]), \
             f"rank {rank}: sharded proof differs from the single-GPU proof"
         sh.close()
+    if rank == 0:
+        print(f"SHARDED_OK world={world} backend={'gloo/emulator' if emulated else 'nccl'}")
     # timing at full size (optional)
     if os.environ.get("SHARD_BENCH"):
         params = W.miden_pcs_params()

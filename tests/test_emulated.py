@@ -43,3 +43,19 @@ def test_gpu_parity_suite_on_the_emulator():
                        env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
     tail = r.stdout[-3000:] + r.stderr[-1000:]
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_hash_sharded_proof_over_gloo_on_the_emulator(world):
+    """One proof hash-sharded over `world` ranks (mdn_session_set_shard: leaf ranges + all-gather of sub-roots and
+    of the sibling digests the openings need) is byte-identical to the unsharded proof -- the product's N>1 host
+    logic, here with one emulated device per process and gloo as the transport (NCCL on the GPU box:
+    test_hash_sharded_proof_matches_single_gpu)."""
+    lib = _build("-DMDN_ARITH_V2 -DMDN_NTT_V2")
+    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1", SHARD_LOG_H="9", OMP_NUM_THREADS="1")
+    env.pop("SHARD_BENCH", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29711 + world),
+                        os.path.join(ROOT, "tests", "run_sharded.py")],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and f"SHARDED_OK world={world}" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
