@@ -108,7 +108,9 @@ GL_HD W wsum(u64 a, u64 b) {
 // w - x for wide w >= x (the caller adds a multiple of p to w beforehand)
 GL_HD void wsub(W& w, W x) {
 #ifdef __CUDA_ARCH__
-    asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u32 %1, %1, %3;" : "+l"(w.lo), "+r"(w.hi) : "l"(x.lo), "r"(x.hi));
+    u64 lo; u32 hi;     // the asm template is the one the first generation's wsub ran with on the B200
+    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, %4, %5;" : "=l"(lo), "=r"(hi) : "l"(w.lo), "l"(x.lo), "r"(w.hi), "r"(x.hi));
+    w.lo = lo; w.hi = hi;
 #else
     u32 b = w.lo < x.lo ? 1u : 0u; w.lo -= x.lo; w.hi = w.hi - x.hi - b;
 #endif
