@@ -4,16 +4,19 @@
 // permutations held entirely in registers, (c) streaming reductions over LDE columns.
 #include "kernels.cuh"
 #include "poseidon2.cuh"
-#if defined(MDN_NTT_V2) && !defined(MDN_ARITH_V2)
+// Second-generation field arithmetic and NTT are the default since r1l (accepted on the B200 by tools/ab_check.py,
+// profiles/ab_r1l_*.json); -DMDN_GEN1 builds the first generation (libmiden_b200_gen1.so, the A/B baseline).
+#ifndef MDN_GEN1
 #define MDN_ARITH_V2 1
+#define MDN_NTT_V2 1
 #endif
 #ifdef MDN_ARITH_V2
-#include "poseidon2_fast2.cuh"    // second-generation lazy arithmetic (host-checked by tests/cpp/test_arith_v2.cpp)
+#include "poseidon2_fast2.cuh"    // host-checked by tests/cpp/test_arith_v2.cpp
 #else
-#include "poseidon2_fast.cuh"     // first-generation lazy arithmetic (r1b..r1k measurements)
+#include "poseidon2_fast.cuh"     // r1b..r1k measurements
 #endif
 #ifdef MDN_NTT_V2
-#include "ntt2.cuh"
+#include "ntt2.cuh"               // host-checked by tests/cpp/test_ntt_v2.cpp
 #endif
 #include <cstdio>
 

@@ -1,5 +1,5 @@
-// Second-generation NTT block functions (built into the library with -DMDN_NTT_V2, which implies
-// -DMDN_ARITH_V2).  Same data layout, index conventions and results as the first generation in
+// Second-generation NTT block functions: the product's NTT since r1l (-DMDN_GEN1 builds the first
+// generation of kernels.cu instead).  Same data layout, index conventions and results as the first generation in
 // kernels.cu (DESIGN.md "NTT index conventions"; reference: Radix2DitParallel::coset_lde_batch at
 // crates/lifted-stark/src/prover/commit.rs:173, quotient.rs:186-209), fewer instructions per point:
 //

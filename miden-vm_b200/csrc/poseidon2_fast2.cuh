@@ -1,6 +1,6 @@
 // Second-generation lazy-reduction Goldilocks arithmetic + Poseidon2 (width 12) for the sm_100a
-// integer pipes.  Same interface and same function values as poseidon2_fast.cuh (which it replaces
-// when MDN_ARITH_V2 is defined: libmiden_b200_v2.so); reference: crates/crypto/src/hash/algebraic_sponge/poseidon2/
+// integer pipes: the product's arithmetic since r1l.  Same interface and same function values as
+// poseidon2_fast.cuh (the first generation, still built as libmiden_b200_gen1.so with -DMDN_GEN1); reference: crates/crypto/src/hash/algebraic_sponge/poseidon2/
 // mod.rs:226-319 (layer structure), constants.rs:18-31 (internal diagonal).
 //
 // What changed against v1 (SASS instructions per permutation 17.0 k -> see profiles/r1_summary.md):
@@ -49,7 +49,9 @@ GL_HD void subb64(u64 a, u64 b, u64& r, u32& m) {
 // a * (2^32 - 1) as a 64-bit product.  The explicit mul.wide keeps ptxas fusing it with the following add.cc
 // into one IMAD.WIDE.U32 with carry-out (a plain C product of a limb of the 128-bit multiply does not fuse).
 GL_HD u64 mul_eps(u32 a) {
-#ifdef __CUDA_ARCH__
+#ifdef P2_EPS_ALU           // tuning switch: (a << 32) - a on the ALU pipe instead of an IMAD.WIDE on the FMA pipe
+    return ((u64)a << 32) - (u64)a;
+#elif defined(__CUDA_ARCH__)
     u64 m;
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(m) : "r"(a), "r"(0xFFFFFFFFu));
     return m;
@@ -58,7 +60,13 @@ GL_HD u64 mul_eps(u32 a) {
 #endif
 }
 // c * (2^32 - 1) + r for c in {0, 1}: one IMAD.WIDE.U32.  Callers guarantee no overflow.
-GL_HD u64 fold(u32 c, u64 r) { return (u64)c * EPS + r; }
+GL_HD u64 fold(u32 c, u64 r) {
+#ifdef P2_FOLD_ALU          // tuning switch: add the mask 0 / 2^32 - 1 on the ALU pipe instead of an IMAD.WIDE
+    return r + (u64)(0u - c);
+#else
+    return (u64)c * EPS + r;
+#endif
+}
 
 GL_HD u64 canon(u64 x) { return x >= gl::P ? x - gl::P : x; }
 

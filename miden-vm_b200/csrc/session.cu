@@ -1737,15 +1737,10 @@ long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap)
             break;
         }
         case MDN_INFO_BUILD: {
-#ifdef MDN_ARITH_V2
-            v.push_back(2);
+#ifdef MDN_GEN1
+            v.push_back(1); v.push_back(1);
 #else
-            v.push_back(1);
-#endif
-#ifdef MDN_NTT_V2
-            v.push_back(2);
-#else
-            v.push_back(1);
+            v.push_back(2); v.push_back(2);
 #endif
             break;
         }

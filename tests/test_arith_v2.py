@@ -3,8 +3,7 @@ __host__ __device__ code whose only device-specific parts are five carry-flag pr
 compiles THAT header for the CPU (tests/cpp/test_arith_v2.cpp) and checks multiplication, the wide
 accumulators, exact division by 2^k, both linear layers and the whole permutation against 128-bit integer
 arithmetic, the canonical p2::permute and the reference KAT (poseidon2/test.rs:7-39), on canonical and
-non-canonical representatives.  The GPU side of the same header is covered by the -m gpu parity tests
-when the library is built with -DMDN_ARITH_V2."""
+non-canonical representatives.  The GPU side of the same header is what the -m gpu parity tests run."""
 import os
 import subprocess
 
@@ -19,7 +18,7 @@ def test_arith_v2_on_host():
 
 
 def test_ntt_v2_block_functions_on_host():
-    """ntt2.cuh (the -DMDN_NTT_V2 kernels' bodies) run on the CPU with the tables of ntt_tables.hpp: inverse
+    """ntt2.cuh (the bodies of the product's NTT kernels) run on the CPU with the tables of ntt_tables.hpp: inverse
     transform and all cosets of the LDE for 2^1 .. 2^16 (both the single-pass and the two-pass split) against a
     textbook transform; also pins the table layout the first-generation kernels read."""
     subprocess.check_call(["make", "-s", "-C", CPP, "test_ntt_v2"])

@@ -6,8 +6,8 @@ is host memory.  The same launch geometry, shared-memory tiles, barriers and hos
 these tests cover what the oracle tests cannot reach without a device: session.cu (phases, arena, tables, openings,
 staged API, error paths) and the index arithmetic of every kernel, against the oracle, bit for bit.  What they cannot
 show is listed in tests/emu/cuda_runtime.h (PTX carry primitives, hardware limits, races, speed); the real parity
-gate stays `-m gpu` on a B200.  The emulator builds the second-generation kernels (poseidon2_fast2.cuh, ntt2.cuh):
-the first-generation arithmetic is PTX-only.  binding.py refuses the emulator library unless MDN_ALLOW_EMULATOR=1."""
+gate stays `-m gpu` on a B200.  The emulator builds the product's default (second-generation) kernels; the first-generation
+arithmetic of libmiden_b200_gen1.so is PTX-only and cannot be emulated.  binding.py refuses the emulator library unless MDN_ALLOW_EMULATOR=1."""
 import os
 import subprocess
 import sys
@@ -26,7 +26,7 @@ def _build(gen):
 
 
 def test_binding_refuses_the_emulator_without_opt_in():
-    lib = _build("-DMDN_ARITH_V2 -DMDN_NTT_V2")
+    lib = _build("")
     env = dict(os.environ, MDN_LIB_PATH=lib)
     env.pop("MDN_ALLOW_EMULATOR", None)
     code = ("import sys; sys.path.insert(0, %r); import pkgload; B = pkgload.load_pkg().binding\n"
@@ -36,7 +36,7 @@ def test_binding_refuses_the_emulator_without_opt_in():
 
 
 def test_gpu_parity_suite_on_the_emulator():
-    lib = _build("-DMDN_ARITH_V2 -DMDN_NTT_V2")
+    lib = _build("")
     env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
                         "-k", SKIP, "-p", "no:cacheprovider", "--timeout", "300"],
@@ -51,7 +51,7 @@ def test_hash_sharded_proof_over_gloo_on_the_emulator(world):
     of the sibling digests the openings need) is byte-identical to the unsharded proof -- the product's N>1 host
     logic, here with one emulated device per process and gloo as the transport (NCCL on the GPU box:
     test_hash_sharded_proof_matches_single_gpu)."""
-    lib = _build("-DMDN_ARITH_V2 -DMDN_NTT_V2")
+    lib = _build("")
     env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1", SHARD_LOG_H="9", OMP_NUM_THREADS="1")
     env.pop("SHARD_BENCH", None)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",

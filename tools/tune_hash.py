@@ -3,7 +3,7 @@
 warps a scheduler can interleave).  Builds one library per HASH_MIN_BLOCKS value (the __launch_bounds__ minimum of
 k_leaf_hash / k_compress, 128 threads per block; none of 1..6 spills on sm_100a) and runs tools/ab_check.py on each.
 
-    python tools/tune_hash.py build [--gen "-DMDN_ARITH_V2 -DMDN_NTT_V2"]     # here (nvcc cross-compiles), libs go to tools/_tune/
+    python tools/tune_hash.py build [--gen "<extra nvcc flags>"]     # here (nvcc cross-compiles), libs go to tools/_tune/
     python tools/tune_hash.py run                                            # on the GPU box: prints leaf/compress ms per variant
 """
 import json
@@ -51,7 +51,7 @@ def run():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "build":
-        gen = sys.argv[3] if len(sys.argv) > 3 and sys.argv[2] == "--gen" else "-DMDN_ARITH_V2 -DMDN_NTT_V2"
+        gen = sys.argv[3] if len(sys.argv) > 3 and sys.argv[2] == "--gen" else ""
         build(gen)
     else:
         run()
