@@ -337,8 +337,11 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
 // Poseidon2 hashing
 // =============================================================================================
 static constexpr int HASH_THREADS = 128;
+// Minimum resident blocks the compiler must allow (tools/tune_hash.py sweep on the B200, leaf sponge / compress ms per
+// 2^20 proof: 1..3 -> 142 registers 95.6 / 17.8, 4 -> 126: 94.0 / 17.5, 5 -> 96: 92.5 / 17.4, 6 -> 80: 91.7 / 17.2; none spills).
+// The kernels are bound by the two integer pipes and more warps per scheduler interleave their FMA and ALU bursts.
 #ifndef HASH_MIN_BLOCKS
-#define HASH_MIN_BLOCKS 1
+#define HASH_MIN_BLOCKS 6
 #endif
 
 __global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_leaf_hash(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev,
