@@ -92,7 +92,9 @@ cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t pool, cudaMemPoolAttr a, void*
 cudaError_t cudaMemPoolGetAttribute(cudaMemPool_t pool, cudaMemPoolAttr a, void* v);
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p);
 }
-template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+namespace emu { extern size_t g_max_dyn_smem_opt_in; }
+// not per kernel: remembers the largest opt-in so that a launch above the 48 KB default without ANY opt-in is caught
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int v) { if ((size_t)v > emu::g_max_dyn_smem_opt_in) emu::g_max_dyn_smem_opt_in = (size_t)v; return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t bytes) { memcpy((void*)&sym, src, bytes); return cudaSuccess; }
 
 // ---- kernel launch: `k<<<grid, block, smem, stream>>>(args)` is rewritten by gen.py into

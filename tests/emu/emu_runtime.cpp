@@ -13,6 +13,7 @@ namespace emu {
 uint3 g_threadIdx, g_blockIdx;
 dim3 g_blockDim, g_gridDim;
 unsigned char* g_dyn_smem = nullptr;
+size_t g_max_dyn_smem_opt_in = 0;
 
 enum State { RUNNABLE, AT_WARP_BAR, AT_BLOCK_BAR, DONE };
 struct Fiber { ucontext_t ctx; State st; uint3 tid; char* stack; };
@@ -52,6 +53,7 @@ void launch(const LaunchCfg& c, const std::function<void()>& body) {
     unsigned nthreads = c.block.x * c.block.y * c.block.z;
     if (nthreads == 0 || nthreads > 1024) { fprintf(stderr, "emu: bad block size %u\n", nthreads); abort(); }
     if (c.smem > (227u << 10)) { fprintf(stderr, "emu: %zu bytes of dynamic shared memory exceed the 227 KB an sm_100a block can have\n", c.smem); abort(); }
+    if (c.smem > (48u << 10) && c.smem > g_max_dyn_smem_opt_in) { fprintf(stderr, "emu: %zu bytes of dynamic shared memory without cudaFuncAttributeMaxDynamicSharedMemorySize\n", c.smem); abort(); }
     while (g_stacks.size() < nthreads) g_stacks.push_back((char*)malloc(STACK_BYTES));
     g_fibers.resize(nthreads);
     g_smem_buf.assign(c.smem + 16, 0xCD);     // poison: reads of unwritten shared memory show up as garbage
