@@ -60,3 +60,15 @@ def test_hash_sharded_proof_over_gloo_on_the_emulator(world):
                         os.path.join(ROOT, "tests", "run_sharded.py")],
                        env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and f"SHARDED_OK world={world}" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_cpp_host_layer_prove_verify_tamper_on_the_emulator():
+    """miden-vm_b200/host/miden_prover.hpp (the reference's prover interface restated in C++ above the C ABI) through its
+    parity program tests/cpp/test_host_api.cpp, linked against the emulator: StarkConfig / ProverStatement /
+    Preprocessed / ProverInstance::prove, verified by the oracle, tampered proofs rejected."""
+    _build("")
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    subprocess.check_call(["make", "-s", "-C", cpp, "test_host_api_emu"])
+    r = subprocess.run([os.path.join(cpp, "test_host_api_emu")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "HOST_API_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
