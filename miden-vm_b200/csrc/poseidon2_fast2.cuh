@@ -68,6 +68,15 @@ GL_HD u64 fold(u32 c, u64 r) {
 #endif
 }
 
+// the fold used by the linear layers (wred, add_const): tuning switch P2_LINEAR_FOLD_ALU puts only those on the ALU pipe
+GL_HD u64 fold_lin(u32 c, u64 r) {
+#ifdef P2_LINEAR_FOLD_ALU
+    return r + (u64)(0u - c);
+#else
+    return fold(c, r);
+#endif
+}
+
 GL_HD u64 canon(u64 x) { return x >= gl::P ? x - gl::P : x; }
 
 // 128-bit (hi:lo) -> u64 representative.  2^64 = 2^32 - 1, 2^96 = -1 (mod p).
@@ -88,7 +97,7 @@ GL_HD u64 mul(u64 a, u64 b) {
 GL_HD u64 add_const(u64 x, u64 k) {
     u64 r; u32 c;
     addc64(x, k, r, c);
-    return fold(c, r);
+    return fold_lin(c, r);
 }
 
 // ---- 96-bit accumulators -------------------------------------------------------------------------
@@ -129,7 +138,7 @@ GL_HD W wtriple(u64 x) { W w = wshl(x, 1); wadd(w, x); return w; }
 GL_HD u64 wred(W w) {
     u64 r; u32 c;
     addc64(w.lo, mul_eps(w.hi), r, c);
-    return fold(c, r);
+    return fold_lin(c, r);
 }
 static constexpr u64 P8_LO = 0xFFFFFFF800000008ull;   // 8p = 2^67 - 2^35 + 8
 static constexpr u32 P8_HI = 7u;
