@@ -256,7 +256,8 @@ def main():
             tj = json.load(open(tf))
             traffic = tj.get("dram_bytes_per_launch")
             traffic_note = (f"ncu --set full capture of the main-tree launch: {traffic / 1e9:.2f} GB DRAM for "
-                            f"{tj.get('algorithmic_bytes_per_launch', 0) / 1e9:.2f} GB algorithmic; `achieved` averages the three leaf-sponge launches of a proof")
+                            f"{tj.get('algorithmic_bytes_per_launch', 0) / 1e9:.2f} GB algorithmic; `achieved` averages the three leaf-sponge launches of a proof; "
+                            "the capture is of the first-generation kernel (r1i), the second generation reads the same cells once in the same order")
         # The leaf sponge is bound by instruction issue on the two integer pipes, not by HBM: next to the HBM
         # fraction the contract asks for, report thread-instructions/s against what the SMs can issue
         # (148 SMs x 4 schedulers x 32 lanes x 1 instruction/clock at the sampled SM clock).
