@@ -72,3 +72,11 @@ def test_cpp_host_layer_prove_verify_tamper_on_the_emulator():
     subprocess.check_call(["make", "-s", "-C", cpp, "test_host_api_emu"])
     r = subprocess.run([os.path.join(cpp, "test_host_api_emu")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "HOST_API_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_graft_entry_smoke_on_the_emulator():
+    """__graft_entry__.smoke() (one small proof through the C ABI, checked against the oracle) runs unchanged."""
+    lib = _build("")
+    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
