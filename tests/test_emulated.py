@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 # too large for fibers (2^20 and up), need the CUDA driver (NVRTC kernels), or need several processes.  The 2^16 case of
 # BASELINE config 2 (two-pass NTT, 8.4 M permutations) takes two more minutes and runs with MDN_EMU_FULL=1.
-SKIP = "not 2_20 and not 2_21 and not 2_22 and not sharded and not jit" + ("" if os.environ.get("MDN_EMU_FULL") else " and not 2_16")
+SKIP = "not 2_20 and not 2_21 and not 2_22 and not full_size and not sharded and not jit" + ("" if os.environ.get("MDN_EMU_FULL") else " and not 2_16")
 
 
 def _build(gen):

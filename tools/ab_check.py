@@ -101,6 +101,9 @@ res["phases_ms"] = {k: round(float(getattr(t, k)), 3) for k in ("h2d_transpose",
 res["permutations"] = int(t.permutations)
 res["kernel_launches"] = int(t.kernel_launches)
 res["proof_digest"] = f"{int(np.bitwise_xor.reduce(proofs[-1][1])):016x}"
+import hashlib  # noqa: E402
+res["proof_sha256"] = hashlib.sha256(bytes(proofs[-1][0]) + np.ascontiguousarray(proofs[-1][1], dtype=np.uint64).tobytes()
+                                     + np.ascontiguousarray(proofs[-1][2], dtype=np.uint64).tobytes()).hexdigest()
 res["ok"] = all(res["checks"].values())
 line = json.dumps(res)
 print(line)
