@@ -338,7 +338,7 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
 // =============================================================================================
 static constexpr int HASH_THREADS = 128;
 // Minimum resident blocks the compiler must allow (tools/tune_hash.py sweep on the B200, leaf sponge / compress ms per
-// 2^20 proof: 1..3 -> 142 registers 95.6 / 17.8, 4 -> 126: 94.0 / 17.5, 5 -> 96: 92.5 / 17.4, 6 -> 80: 91.7 / 17.2; none spills).
+// 2^20 proof: 1..3 -> 142 registers 95.6 / 17.8, 4 -> 126: 94.0 / 17.5, 5 -> 96: 92.5 / 17.4, 6 -> 80: 91.7 / 17.2, 7 -> 72: 91.6 / 17.4, 8 -> 64: 91.5 / 17.3; 1..7 do not spill).
 // The kernels are bound by the two integer pipes and more warps per scheduler interleave their FMA and ALU bursts.
 #ifndef HASH_MIN_BLOCKS
 #define HASH_MIN_BLOCKS 6

@@ -68,12 +68,15 @@ GL_HD u64 fold(u32 c, u64 r) {
 #endif
 }
 
-// the fold used by the linear layers (wred, add_const): tuning switch P2_LINEAR_FOLD_ALU puts only those on the ALU pipe
+// The fold used by the linear layers (wred, add_const) adds the mask 0 / 2^32 - 1 on the ALU pipe: the kernels are bound
+// by the FMA-heavy pipe (an IMAD.WIDE costs ~1.6 plain IMADs there) and the ALU pipe has slack, so the 490 folds per
+// permutation outside the multiplications go there (B200: leaf sponge 91.7 -> 90.4 ms; profiles/tune_lf6.json).
+// -DP2_LINEAR_FOLD_IMAD restores the IMAD.WIDE form.
 GL_HD u64 fold_lin(u32 c, u64 r) {
-#ifdef P2_LINEAR_FOLD_ALU
-    return r + (u64)(0u - c);
-#else
+#ifdef P2_LINEAR_FOLD_IMAD
     return fold(c, r);
+#else
+    return r + (u64)(0u - c);
 #endif
 }
 
