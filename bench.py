@@ -270,7 +270,7 @@ def main():
             pass                                 # a library from before MDN_INFO_BUILD: first generation
         try:
             instr_per_perm = {1: (15960, "ncu inst_executed of the r1i capture (profiles/leaf_sponge_traffic.json)"),
-                              2: (13600, "static SASS count of p2f::permute, poseidon2_fast2.cuh (no ncu capture of this build yet)")}[build[0]]
+                              2: (14180, "static SASS count of p2f::permute, poseidon2_fast2.cuh: 3272 IMAD.WIDE + 3123 other IMAD + 7486 ALU-pipe + 301 other (no ncu capture of this build yet)")}[build[0]]
             clk = sampler.summary()
             sm_mhz = clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965
             perms_per_s = tim_v.permutations / ((km[2] + km[3]) * 1e-3) if km[2] + km[3] > 0 else None
@@ -301,7 +301,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon2 leaf sponge, main trace)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_kind} copy bandwidth",
-                         "note": "integer-ALU bound by construction (13.6-16k instructions per permutation per 64 input bytes); HBM fraction is low on purpose, see `issue`",
+                         "note": "integer-ALU bound by construction (14-16k instructions per permutation per 64 input bytes); HBM fraction is low on purpose, see `issue`",
                          "permutations_per_s": perms_per_s, "issue": issue},
             "build": {"field_arithmetic_generation": build[0], "ntt_generation": build[1]},
             "kernels_ms_per_step": dict(zip(names, km)),
