@@ -248,6 +248,13 @@ GL_HD void internal_layer(u64* s) {
 #define P2F_RC_INTERNAL p2::P2_RC_INTERNAL
 #endif
 
+// Tuning knob: unroll factor of the 22 internal rounds (1 keeps the kernel at ~26 KB of code; the first generation's
+// fully unrolled 93 KB stalled on instruction fetch).
+#ifndef P2_INT_UNROLL
+#define P2_INT_UNROLL 1
+#endif
+#define P2_PRAGMA_(x) _Pragma(#x)
+#define P2_UNROLL(n) P2_PRAGMA_(unroll n)
 // Output words are arbitrary representatives; canonicalise with glf::canon before storing.
 GL_HD void permute(u64* s) {
     external_layer(s);
@@ -261,7 +268,7 @@ GL_HD void permute(u64* s) {
             external_layer(s);
         }
         if (phase == 0) {
-#pragma unroll 1
+P2_UNROLL(P2_INT_UNROLL)
             for (int r = 0; r < 22; r++) {
                 s[0] = sbox(glf::add_const(s[0], P2F_RC_INTERNAL[r]));
                 internal_layer(s);
