@@ -19,6 +19,27 @@ typedef unsigned int u32;
 static constexpr u64 P = 0xFFFFFFFF00000001ULL;
 static constexpr u64 EPS = 0xFFFFFFFFULL;  // 2^64 mod p = 2^32 - 1
 
+#ifdef MDN_GL_FAST
+// Tuning knob (inert by default): add / sub / mul of the kernels that use gl:: directly (constraint interpreter, LogUp
+// rows, DEEP tail, OOD, FRI fold) on the carry flag and one 128-bit product, like poseidon2_fast2.cuh; same contracts
+// (canonical operands for add / sub, canonical results everywhere), same PTX templates, unsigned __int128 on the host.
+GL_HD void fast_subb64(u64 a, u64 b, u64& r, unsigned& m) {
+#ifdef __CUDA_ARCH__
+    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(r), "=r"(m) : "l"(a), "l"(b));
+#else
+    r = a - b; m = a < b ? 0xFFFFFFFFu : 0u;
+#endif
+}
+GL_HD void fast_addc64(u64 a, u64 b, u64& r, unsigned& c) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(a), "l"(b));
+#else
+    unsigned __int128 s = (unsigned __int128)a + b; r = (u64)s; c = (unsigned)(s >> 64);
+#endif
+}
+GL_HD u64 sub(u64 a, u64 b) { u64 d; unsigned m; fast_subb64(a, b, d, m); return d - (u64)m; }
+GL_HD u64 add(u64 a, u64 b) { return sub(a, P - b); }
+#else
 GL_HD u64 add(u64 a, u64 b) {
     u64 s = a + b;
     if (s < a) s += EPS;        // overflowed 2^64: fold the carry back (result < p)
@@ -30,9 +51,29 @@ GL_HD u64 sub(u64 a, u64 b) {
     if (a < b) d -= EPS;        // borrowed 2^64: add p
     return d;
 }
+#endif
 GL_HD u64 neg(u64 a) { return a ? P - a : 0; }
 GL_HD u64 dbl(u64 a) { return add(a, a); }
 
+#ifdef MDN_GL_FAST
+GL_HD u64 mul(u64 a, u64 b) {
+    unsigned __int128 q = (unsigned __int128)a * b;
+    u64 lo = (u64)q, hi = (u64)(q >> 64);
+    unsigned x2 = (unsigned)hi, x3 = (unsigned)(hi >> 32), m, c;
+    u64 t, r, e;
+    fast_subb64(lo, (u64)x3, t, m);
+    t -= (u64)m;
+#ifdef __CUDA_ARCH__
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(e) : "r"(x2), "r"(0xFFFFFFFFu));
+#else
+    e = (u64)x2 * EPS;
+#endif
+    fast_addc64(t, e, r, c);
+    r = (u64)c * EPS + r;
+    fast_subb64(r, P, t, m);
+    return t - (u64)m;
+}
+#else
 GL_HD u64 mulhi(u64 a, u64 b) {
 #ifdef __CUDA_ARCH__
     return __umul64hi(a, b);
@@ -53,6 +94,7 @@ GL_HD u64 reduce128(u64 lo, u64 hi) {
     return r;
 }
 GL_HD u64 mul(u64 a, u64 b) { return reduce128(a * b, mulhi(a, b)); }
+#endif
 GL_HD u64 sqr(u64 a) { return mul(a, a); }
 
 // Halve: a/2 mod p.
