@@ -40,6 +40,7 @@ typedef enum {
     MDN_ERR_UNSUPPORTED = -4,      /* e.g. log_blowup > 4, > 1024 live constraint values */
     MDN_ERR_AUX_BUILDER = -5,      /* aux-trace callback failed */
     MDN_ERR_NO_DEVICE = -6,
+    MDN_ERR_EXTERNAL_ASSERTION = -7,   /* ProverError::ExternalAssertionFailed / ::Reduction (prover/mod.rs:383-395) */
 } mdn_status;
 
 /* PcsParams::new(log_blowup, log_folding_arity, log_final_degree, folding_pow_bits,
@@ -166,16 +167,40 @@ int mdn_session_create(const mdn_pcs_params* params, int cuda_device, mdn_sessio
 void mdn_session_destroy(mdn_session* s);
 const char* mdn_last_error(const mdn_session* s);   /* s may be NULL: last create error */
 
-/* ---- one proof on several GPUs (hash sharding) -----------------------------------------------------
- * One process per GPU, every rank calls mdn_prove with the SAME statement/traces/challenger.  Each rank
- * computes the (cheap) LDEs itself and hashes only its contiguous range of Merkle leaves of every
- * commitment (rank g: leaves [g*L/G, (g+1)*L/G)), builds that sub-tree, and the ranks exchange the G
- * sub-roots with ONE all-gather per commitment; sibling digests needed by the query openings are
- * exchanged the same way.  All ranks return the identical proof.  `fn` must gather `n_u64` words from
- * every rank into `recv` (rank-major) -- e.g. torch.distributed.all_gather over NCCL/NVLink; the
- * payloads are 32 bytes per rank per commitment.  world must be a power of two; world = 1 disables. */
+/* ---- one proof on several GPUs ---------------------------------------------------------------------
+ * One process per GPU of one NVLink/NVSwitch box; every rank calls mdn_prove (or the staged calls) with the SAME
+ * statement / traces / challenger / flags and every rank returns the byte-identical proof.  The work of the ONE proof
+ * is partitioned (the reference has no counterpart: it is single-process rayon; the loops that are split are
+ * prover/commit.rs:142-180, lmcs/lifted_tree.rs:394-406, prover/constraints/mod.rs:246-259, prover/quotient.rs:163,
+ * pcs/deep/prover.rs:214-312, pcs/fri/prover.rs:137-211):
+ *   - rank g owns LDE cosets [g*B/G, (g+1)*B/G) of every committed column: forward coset NTTs, leaf sponge,
+ *     constraint evaluation, quotient-chunk interpolation, DEEP quotient and FRI folds of those cosets;
+ *   - rank g owns the Merkle sub-tree over leaves [g*L/G, (g+1)*L/G) of every commitment (input and FRI trees).
+ * Data crosses ranks as peer-memory stores inside the producing kernels (CUDA IPC mappings of each rank's proof
+ * arena over NVLink: leaf digests to the sub-tree owner, sub-roots / quotient chunk coefficients / the first small
+ * FRI layer / opened values to every rank), ordered by a device-side flag barrier; there is no host round trip and
+ * no library collective on the data path.  `fn` is only the bootstrap transport: it must gather `n_u64` words from
+ * every rank into `recv` (rank-major) -- e.g. torch.distributed.all_gather -- and carries the 64-byte CUDA IPC
+ * handles when an arena slab is created (first proof of a shape) and one word of rendezvous when slabs are
+ * released.  world must be a power of two <= min(8, 2^log_blowup); world = 1 turns the partition off.  Collective:
+ * every rank must call it at the same point.  The preprocessed bundle (mdn_session_set_preprocessed) and the
+ * utility entry points (mdn_coset_lde_batch, mdn_lmcs_commit) are not partitioned. */
 typedef int (*mdn_allgather_fn)(void* ctx, const uint64_t* send, uint64_t* recv, size_t n_u64);
 int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_allgather_fn fn, void* ctx);
+
+/* ---- Statement::eval_external (crates/lifted-air/src/air.rs:272-288, statement.rs:94-110) -------------------
+ * Cross-AIR assertions are host code of the statement.  When a callback is installed the prover calls it once per
+ * proof, after the aux traces are built -- on the host or on the device (mdn_air.lookup) -- and BEFORE the aux
+ * commitment, exactly where the reference evaluates them (prover/mod.rs:383-395):
+ *   challenges  : the shared randomness pool, 2 u64 per EF challenge          aux_values[i] : AIR i's aux values
+ *   (instance order, 2 u64 per EF value, n_aux_values[i] of them)            log_trace_heights : instance order
+ * Return 0 when every assertion evaluates to zero; > 0 with *failed_assertion = k for
+ * `ProverError::ExternalAssertionFailed { assertion: k }`; < 0 for a `ReductionError`.  mdn_prove* then returns
+ * MDN_ERR_EXTERNAL_ASSERTION and nothing of the aux phase is committed.  NULL (default) = no assertions. */
+typedef int (*mdn_external_check)(void* ctx, const uint64_t* challenges, uint32_t n_challenges,
+                                  const uint64_t* const* aux_values, const uint32_t* n_aux_values,
+                                  const uint8_t* log_trace_heights, uint32_t n_airs, uint32_t* failed_assertion);
+int mdn_session_set_external_check(mdn_session* s, mdn_external_check fn, void* ctx);
 
 /* ---- preprocessed columns: Preprocessed::build (crates/lifted-stark/src/preprocessed.rs:63-131) -----
  * `preprocessed[i]` = `BaseAir::preprocessed_trace()` of AIR i (HOST pointer; width 0 where the AIR declares

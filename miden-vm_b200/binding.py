@@ -61,6 +61,7 @@ class Timings(C.Structure):
 
 AUX_BUILDER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Matrix), u64p, u64p, u64p)
 ALLGATHER = C.CFUNCTYPE(C.c_int, C.c_void_p, u64p, u64p, C.c_size_t)
+EXTERNAL_CHECK = C.CFUNCTYPE(C.c_int, C.c_void_p, u64p, C.c_uint32, C.POINTER(u64p), u32p, C.POINTER(C.c_uint8), C.c_uint32, u32p)
 FLAG_DEVICE_TRACES = 1
 
 # Every symbol include/miden_b200.h declares (checked by tests/test_abi.py).
@@ -70,6 +71,7 @@ EXPORTS = [
     "mdn_lmcs_commit", "mdn_poseidon2_permute", "mdn_get_info", "mdn_get_timings",
     "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug", "mdn_session_set_shard",
     "mdn_session_set_preprocessed", "mdn_session_set_jit", "mdn_jit_compile_check", "mdn_jit_status", "mdn_abi_layout",
+    "mdn_session_set_external_check",
 ]
 
 _lib = None
@@ -120,6 +122,7 @@ def lib():
         L.mdn_get_info.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t]
         L.mdn_set_debug.argtypes = [C.c_void_p, C.c_int]
         L.mdn_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHER, C.c_void_p]
+        L.mdn_session_set_external_check.argtypes = [C.c_void_p, EXTERNAL_CHECK, C.c_void_p]
         L.mdn_session_set_preprocessed.argtypes = [C.c_void_p, C.POINTER(Statement), C.POINTER(Matrix), u64p]
         L.mdn_abi_layout.restype = C.c_size_t
         L.mdn_abi_layout.argtypes = [u32p, C.c_size_t]
@@ -174,9 +177,31 @@ class Session:
         return self._h
 
     def set_shard(self, rank: int, world: int, allgather_cb):
-        """Hash-shard every proof of this session over `world` ranks (mdn_session_set_shard)."""
+        """Split every proof of this session over `world` ranks (mdn_session_set_shard); collective."""
         self._allgather_cb = allgather_cb      # keep the ctypes trampoline alive
         self._check(lib().mdn_session_set_shard(self._h, rank, world, allgather_cb, None))
+
+    def set_external_check(self, fn):
+        """`Statement::eval_external`: fn(challenges u64[2n], aux_values [per AIR u64[]], log_heights bytes) ->
+        None / -1 when every assertion holds, else the index of the first failing assertion."""
+        if fn is None:
+            self._ext_cb = C.cast(None, EXTERNAL_CHECK)
+        else:
+            def tramp(ctx, ch, n_ch, vals, n_vals, lh, n_airs, failed):
+                try:
+                    chal = np.ctypeslib.as_array(ch, shape=(2 * n_ch,)).copy() if n_ch else np.zeros(0, np.uint64)
+                    av = [np.ctypeslib.as_array(vals[i], shape=(2 * n_vals[i],)).copy() if n_vals[i] else np.zeros(0, np.uint64) for i in range(n_airs)]
+                    k = fn(chal, av, bytes(lh[:n_airs]))
+                    if k is None or k < 0:
+                        return 0
+                    failed[0] = k
+                    return 1
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            self._ext_cb = EXTERNAL_CHECK(tramp)
+        self._check(lib().mdn_session_set_external_check(self._h, self._ext_cb, None))
 
     def set_jit(self, min_nodes: int):
         """Node threshold above which constraint programs are NVRTC-compiled (0 = interpreter only)."""

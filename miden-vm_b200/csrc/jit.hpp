@@ -327,7 +327,9 @@ inline std::string generate(const uint32_t* w, GenInfo* info, bool lookup = fals
          "  Ctx c;\n"
          "  c.L = (size_t)1 << (a.log_n + a.log_b);\n"
          "  c.pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;\n"
-         "  if (c.pos >= c.L) return;\n"
+         "  { const u32 ct0 = a.pad & 0xffu, cnt = (a.pad >> 8) & 0xffu;   /* cosets [ct0, ct0 + cnt); cnt == 0: all */\n"
+         "    if (c.pos >= (cnt ? (size_t)cnt << a.log_n : c.L)) return;\n"
+         "    c.pos += (size_t)ct0 << a.log_n; }\n"
          "  const u32 N = 1u << a.log_n;\n"
          "  const u32 t = (u32)(c.pos >> a.log_n), r = (u32)(c.pos & (N - 1));\n"
          "  c.pn = ((size_t)t << a.log_n) + ((r + 1) & (N - 1));\n"

@@ -18,6 +18,7 @@
 #ifdef MDN_NTT_V2
 #include "ntt2.cuh"               // host-checked by tests/cpp/test_ntt_v2.cpp
 #endif
+#include <algorithm>
 #include <cstdio>
 
 namespace mk {
@@ -32,6 +33,72 @@ void upload_constants() {
     cudaMemcpyToSymbol(p2::D_RC_EXT_INITIAL, p2::P2_RC_EXT_INITIAL, sizeof(u64) * 48);
     cudaMemcpyToSymbol(p2::D_RC_INTERNAL, p2::P2_RC_INTERNAL, sizeof(u64) * 22);
     cudaMemcpyToSymbol(p2::D_RC_EXT_TERMINAL, p2::P2_RC_EXT_TERMINAL, sizeof(u64) * 48);
+}
+
+// =============================================================================================
+// Peer memory: pushes and the cross-GPU barrier (kernels.cuh "One proof on G GPUs")
+// =============================================================================================
+#ifdef MDN_EMULATED
+static inline void st_release_sys(u64* p, u64 v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline u64 ld_acquire_sys(const u64* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static constexpr long long BARRIER_TIMEOUT = 600ll * 1000000000ll;   // emulated clock64() counts nanoseconds
+#else
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) { u64 v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+static constexpr long long BARRIER_TIMEOUT = 30000000000ll;          // ~15 s of SM clocks
+#endif
+// 16-byte store of element `idx` (in ulonglong2 units) to the destination(s) a PushDst selects
+__device__ __forceinline__ void push_u2(const PushDst& d, size_t idx, size_t owner_key, ulonglong2 v) {
+    if (d.mode == PUSH_ALL) {
+        for (u32 g = 0; g < d.world; g++) reinterpret_cast<ulonglong2*>(d.pp.p[g])[idx] = v;
+    } else {
+        u32 g = d.mode == PUSH_OWNER ? (u32)(owner_key >> d.owner_shift) : d.rank;
+        reinterpret_cast<ulonglong2*>(d.pp.p[g])[idx] = v;
+    }
+}
+struct BarrierArgs { PeerPtrs flags; u32 rank, world; u64 epoch; u32* err; };
+__global__ void k_barrier(BarrierArgs a) {
+    u32 p = threadIdx.x;
+    // every store of the kernels before this one on the stream (local and peer) is ordered before the signal
+    if (p < a.world) { __threadfence_system(); st_release_sys(a.flags.p[p] + a.rank, a.epoch); }
+    __syncthreads();
+    if (p < a.world) {
+        long long t0 = clock64();
+        while (ld_acquire_sys(a.flags.p[a.rank] + p) < a.epoch) {
+            if (clock64() - t0 > BARRIER_TIMEOUT) { atomicOr(a.err, 8u); break; }
+#ifdef MDN_EMULATED
+            emu::cpu_relax();
+#endif
+        }
+    }
+}
+void launch_barrier(const PeerPtrs& flags, u32 rank, u32 world, u64 epoch, u32* err, cudaStream_t st) {
+    BarrierArgs a; a.flags = flags; a.rank = rank; a.world = world; a.epoch = epoch; a.err = err;
+    k_barrier<<<1, 32, 0, st>>>(a);
+    COUNT_LAUNCH();
+}
+struct PushArgs { const u64* src; PeerPtrs dst; u32 rank, world; size_t n; };
+__global__ void __launch_bounds__(256) k_push(PushArgs a) {
+    size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((a.n & 1) == 0 && (((size_t)a.src) & 15) == 0) {      // symmetric offsets: the peers' views share the alignment
+        const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(a.src);
+        for (size_t i = i0; i < a.n / 2; i += stride) {
+            ulonglong2 v = s2[i];
+            for (u32 g = 0; g < a.world; g++) if (g != a.rank) reinterpret_cast<ulonglong2*>(a.dst.p[g])[i] = v;
+        }
+    } else {
+        for (size_t i = i0; i < a.n; i += stride) {
+            u64 v = a.src[i];
+            for (u32 g = 0; g < a.world; g++) if (g != a.rank) a.dst.p[g][i] = v;
+        }
+    }
+}
+void launch_push(const u64* src, const PeerPtrs& dst, u32 rank, u32 world, size_t n, cudaStream_t st) {
+    if (!n || world <= 1) return;
+    PushArgs a; a.src = src; a.dst = dst; a.rank = rank; a.world = world; a.n = n;
+    unsigned blocks = (unsigned)std::min<size_t>((n / 2 + 255) / 256 + 1, 148 * 8);
+    k_push<<<blocks, 256, 0, st>>>(a);
+    COUNT_LAUNCH();
 }
 
 // =============================================================================================
@@ -356,14 +423,14 @@ static constexpr int HASH_THREADS = HASH_THREADS_N;
 
 __global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_leaf_hash(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev,
                                                             u32 prev_log_n, u64* __restrict__ states_out,
-                                                            u64* __restrict__ dig, u32 r0, u32 log_rn) {
-    // rows r0 .. r0 + 2^log_rn of every coset (the whole tree when r0 = 0, log_rn = log_n; a
-    // contiguous range of Merkle leaves [r0*B, (r0 + 2^log_rn)*B) when the hashing is sharded)
+                                                            PushDst dig, u32 has_dig, u32 t0, u32 nt) {
+    // all rows of cosets t0 .. t0 + nt (the whole tree when t0 = 0, nt = B; this rank's cosets when one proof is
+    // split over several GPUs): a contiguous slab [t0 * N, (t0 + nt) * N) of every LDE column
     size_t L = (size_t)1 << (log_n + log_b);
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= ((size_t)1 << (log_rn + log_b))) return;
-    u32 t = (u32)(idx >> log_rn);
-    u32 r = r0 + (u32)(idx & (((size_t)1 << log_rn) - 1));
+    if (idx >= ((size_t)nt << log_n)) return;
+    u32 t = t0 + (u32)(idx >> log_n);
+    u32 r = (u32)(idx & (((size_t)1 << log_n) - 1));
     size_t pos = ((size_t)t << log_n) + r;
     u64 s[12];
     if (prev) {
@@ -388,18 +455,18 @@ __global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_leaf_hash(Lea
 #pragma unroll
         for (int k = 0; k < 12; k++) states_out[k * L + pos] = glf::canon(s[k]);
     }
-    if (dig) {
-        size_t i = ((size_t)r << log_b) | t;
-        ulonglong2* d = reinterpret_cast<ulonglong2*>(dig + i * 4);
-        d[0] = make_ulonglong2(glf::canon(s[0]), glf::canon(s[1]));
-        d[1] = make_ulonglong2(glf::canon(s[2]), glf::canon(s[3]));
+    if (has_dig) {
+        size_t i = ((size_t)r << log_b) | t;       // Merkle leaf = domain index
+        push_u2(dig, 2 * i, i, make_ulonglong2(glf::canon(s[0]), glf::canon(s[1])));
+        push_u2(dig, 2 * i + 1, i, make_ulonglong2(glf::canon(s[2]), glf::canon(s[3])));
     }
 }
 void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
-                      u64* states_out, u64* digests_out, u32 r0, u32 log_rn, cudaStream_t st) {
-    size_t cnt = (size_t)1 << (log_rn + log_blowup);
+                      u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st) {
+    size_t cnt = (size_t)nt << log_n;
     unsigned blocks = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
-    k_leaf_hash<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, digests_out, r0, log_rn);
+    PushDst d = dig ? *dig : local_dst(nullptr);
+    k_leaf_hash<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, d, dig ? 1u : 0u, t0, nt);
     COUNT_LAUNCH();
 }
 
@@ -422,9 +489,11 @@ void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, 
 
 // FRI round leaf: physical row of 2^la extension values [f[i + bitrev_la(j) * q]]_j (fri/prover.rs:137-165),
 // flattened to 2 * 2^la felts and absorbed with the rate-8 sponge (unaligned tree).
-__global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict__ ev, size_t q, u32 la, u64* __restrict__ dig) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q) return;
+__global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict__ ev, size_t q, u32 la, PushDst dig, u32 log_b, u32 t0, u32 log_nt) {
+    // thread -> leaf i with (i mod B) in [t0, t0 + nt): the leaves whose 2^la values (stride q, a multiple of B) this rank holds
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((q >> log_b) << log_nt)) return;
+    size_t i = ((idx >> log_nt) << log_b) | (t0 + (idx & ((1u << log_nt) - 1)));
     const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
     u64 s[12];
 #pragma unroll
@@ -440,13 +509,15 @@ __global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict
         }
         p2f::permute(s);
     }
-    ulonglong2* d = reinterpret_cast<ulonglong2*>(dig + i * 4);
-    d[0] = make_ulonglong2(glf::canon(s[0]), glf::canon(s[1]));
-    d[1] = make_ulonglong2(glf::canon(s[2]), glf::canon(s[3]));
+    push_u2(dig, 2 * i, i, make_ulonglong2(glf::canon(s[0]), glf::canon(s[1])));
+    push_u2(dig, 2 * i + 1, i, make_ulonglong2(glf::canon(s[2]), glf::canon(s[3])));
 }
-void launch_fri_leaf_hash(const u64* evals, size_t rows, u32 log_arity, u64* digests, cudaStream_t st) {
-    unsigned blocks = (unsigned)((rows + HASH_THREADS - 1) / HASH_THREADS);
-    k_fri_leaf<<<blocks, HASH_THREADS, 0, st>>>(evals, rows, log_arity, digests);
+static inline u32 log2_exact(u32 v) { u32 l = 0; while ((1u << l) < v) l++; return l; }
+void launch_fri_leaf_hash(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st) {
+    if (rows < ((size_t)1 << log_b)) { log_b = 0; t0 = 0; nt = 1; }      // tiny layers are never split
+    size_t cnt = (rows >> log_b) * nt;
+    unsigned blocks = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
+    k_fri_leaf<<<blocks, HASH_THREADS, 0, st>>>(evals, rows, log_arity, digests, log_b, t0, log2_exact(nt));
     COUNT_LAUNCH();
 }
 
@@ -479,13 +550,15 @@ struct ConstraintKArgs {
     const u64* w_hi; const u64* w_lo; u32 lo_bits;   // w_N powers
     u64 shift, w_l, w_h_inv;                          // LDE shift, w_L, w_H^-1
     u64 zh[16], inv_zh[16];                           // per coset t
+    u32 t0, nt;                                       // cosets [t0, t0 + nt)
 };
 
 template <int MAXS>
 __global__ void __launch_bounds__(128) k_constraints(ConstraintKArgs a) {
     size_t L = (size_t)1 << (a.log_n + a.log_b);
     size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= L) return;
+    if (pos >= ((size_t)a.nt << a.log_n)) return;
+    pos += (size_t)a.t0 << a.log_n;
     u32 N = 1u << a.log_n;
     u32 t = (u32)(pos >> a.log_n), r = (u32)(pos & (N - 1));
     size_t pos_next = ((size_t)t << a.log_n) + ((r + 1) & (N - 1));
@@ -554,8 +627,9 @@ int launch_constraints(const ConstraintArgs& a, cudaStream_t st) {
     // Z_H(x) on coset t: s^N * w_B^t - 1   (domain.rs:742-749)
     u64 s_pow_n = gl::exp_pow2(k.shift, a.log_n), w_b = gl::two_adic_generator(a.log_blowup), x = 1;
     for (u32 t = 0; t < B; t++) { k.zh[t] = gl::sub(gl::mul(s_pow_n, x), 1); k.inv_zh[t] = gl::inv(k.zh[t]); x = gl::mul(x, w_b); }
-    size_t L = (size_t)1 << log_lde;
-    unsigned blocks = (unsigned)((L + 127) / 128);
+    k.t0 = a.nt ? a.t0 : 0; k.nt = a.nt ? a.nt : B;
+    size_t cnt = (size_t)k.nt << a.log_n;
+    unsigned blocks = (unsigned)((cnt + 127) / 128);
     if (a.air.n_slots <= 16) k_constraints<16><<<blocks, 128, 0, st>>>(k);
     else if (a.air.n_slots <= 64) k_constraints<64><<<blocks, 128, 0, st>>>(k);
     else if (a.air.n_slots <= 256) k_constraints<256><<<blocks, 128, 0, st>>>(k);
@@ -793,25 +867,26 @@ void launch_ood_reduce(const u64* partial, u32 n_cols, u32 n_chunks, u64* out, c
 // DEEP quotient
 // =============================================================================================
 struct DeepKArgs {
-    DeepMat m[12]; int n_mats;
+    const DeepMat* m; int n_mats;
     u32 log_n, log_b;
     const u64* apow; u32 total_w;
     E2 z0, z1, fz0, fz1, beta;
-    u64* out;
+    PushDst out;
     const u64* w_hi; const u64* w_lo; u32 lo_bits;
     u64 shift, w_l;
+    u32 t0, nt;
 };
 __global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
     extern __shared__ u64 sm_apow[];
     for (u32 i = threadIdx.x; i < 2 * a.total_w; i += blockDim.x) sm_apow[i] = a.apow[i];
     __syncthreads();
-    size_t L = (size_t)1 << (a.log_n + a.log_b);
     size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= L) return;
+    if (pos >= ((size_t)a.nt << a.log_n)) return;
+    pos += (size_t)a.t0 << a.log_n;
     u32 t = (u32)(pos >> a.log_n), r = (u32)(pos & (((size_t)1 << a.log_n) - 1));
     E2 fr = gl::e2(0, 0);
     for (int m = 0; m < a.n_mats; m++) {
-        const DeepMat& M = a.m[m];
+        const DeepMat M = a.m[m];
         size_t Lm = (size_t)1 << (M.log_n + a.log_b);
         size_t pm = ((size_t)t << M.log_n) + (r & ((1u << M.log_n) - 1));
         const u64* base = M.base + pm;
@@ -840,18 +915,19 @@ __global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
     E2 q = gl::e2_add(gl::e2_mul(i0, gl::e2_sub(a.fz0, fr)),
                       gl::e2_mul(a.beta, gl::e2_mul(i1, gl::e2_sub(a.fz1, fr))));
     size_t i = ((size_t)r << a.log_b) | t;
-    reinterpret_cast<ulonglong2*>(a.out)[i] = make_ulonglong2(q.a, q.b);
+    push_u2(a.out, i, i, make_ulonglong2(q.a, q.b));
 }
 void launch_deep(const DeepArgs& a, cudaStream_t st) {
     DeepKArgs k;
-    for (int i = 0; i < a.n_mats; i++) k.m[i] = a.m[i];
-    k.n_mats = a.n_mats; k.log_n = a.log_n_max; k.log_b = a.log_blowup; k.apow = a.apow; k.total_w = a.total_w;
+    k.m = a.m; k.n_mats = a.n_mats; k.log_n = a.log_n_max; k.log_b = a.log_blowup; k.apow = a.apow; k.total_w = a.total_w;
     k.z0 = a.z0; k.z1 = a.z1; k.fz0 = a.fz0; k.fz1 = a.fz1; k.beta = a.beta; k.out = a.out;
     k.w_hi = a.T->w_hi; k.w_lo = a.T->w_lo; k.lo_bits = a.T->lo_bits;
     u32 log_lde = a.log_n_max + a.log_blowup;
     k.shift = gl::lde_shift(log_lde); k.w_l = gl::two_adic_generator(log_lde);
-    size_t L = (size_t)1 << log_lde;
-    k_deep<<<(unsigned)((L + 255) / 256), 256, 2 * a.total_w * sizeof(u64), st>>>(k);
+    u32 B = 1u << a.log_blowup;
+    k.t0 = a.nt ? a.t0 : 0; k.nt = a.nt ? a.nt : B;
+    size_t cnt = (size_t)k.nt << a.log_n_max;
+    k_deep<<<(unsigned)((cnt + 255) / 256), 256, 2 * a.total_w * sizeof(u64), st>>>(k);
     COUNT_LAUNCH();
 }
 
@@ -861,10 +937,11 @@ void launch_deep(const DeepArgs& a, cudaStream_t st) {
 // (pcs/fri/fold/arity2.rs, arity4.rs:46-121, arity8.rs:35-75 compute the same field element)
 // =============================================================================================
 struct FoldArgs { u64 winv[8]; u64 arity_inv; u64 w_dom_inv; u32 log_dom, la; E2 beta; };
-__global__ void __launch_bounds__(256) k_fri_fold(const u64* __restrict__ ev, FoldArgs fa, u64* __restrict__ next) {
+__global__ void __launch_bounds__(256) k_fri_fold(const u64* __restrict__ ev, FoldArgs fa, PushDst next, u32 log_b, u32 t0, u32 log_nt) {
     size_t q = (size_t)1 << (fa.log_dom - fa.la);
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q) return;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((q >> log_b) << log_nt)) return;
+    size_t i = ((idx >> log_nt) << log_b) | (t0 + (idx & ((1u << log_nt) - 1)));
     const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
     u32 a = 1u << fa.la;
     E2 y[8];
@@ -878,17 +955,19 @@ __global__ void __launch_bounds__(256) k_fri_fold(const u64* __restrict__ ev, Fo
         acc = gl::e2_add(gl::e2_mul(acc, x), c);
     }
     acc = gl::e2_mulf(acc, fa.arity_inv);
-    reinterpret_cast<ulonglong2*>(next)[i] = make_ulonglong2(acc.a, acc.b);
+    push_u2(next, i, i, make_ulonglong2(acc.a, acc.b));
 }
-void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, u64* next, cudaStream_t st) {
+void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, const PushDst& next, u32 log_b, u32 t0, u32 nt, cudaStream_t st) {
     size_t q = (size_t)1 << (log_dom - log_arity);
+    if (q < ((size_t)1 << log_b)) { log_b = 0; t0 = 0; nt = 1; }
     FoldArgs fa;
     u32 a = 1u << log_arity;
     u64 wi = gl::inv(gl::two_adic_generator(log_arity)), x = 1;
     for (u32 j = 0; j < 8; j++) { fa.winv[j] = j < a ? x : 0; x = gl::mul(x, wi); }
     fa.arity_inv = gl::inv((u64)a); fa.w_dom_inv = gl::inv(gl::two_adic_generator(log_dom));
     fa.log_dom = log_dom; fa.la = log_arity; fa.beta = beta;
-    k_fri_fold<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(evals, fa, next);
+    size_t cnt = (q >> log_b) * nt;
+    k_fri_fold<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(evals, fa, next, log_b, t0, log2_exact(nt));
     COUNT_LAUNCH();
 }
 
@@ -934,6 +1013,19 @@ __global__ void k_gather(const u64* const* __restrict__ ptrs, u64* __restrict__ 
 void launch_gather(const u64* const* d_ptrs, u64* d_out, size_t n, cudaStream_t st) {
     if (!n) return;
     k_gather<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ptrs, d_out, n);
+    COUNT_LAUNCH();
+}
+
+__global__ void k_gather_push(const u64* const* __restrict__ ptrs, const int* __restrict__ owner, PeerPtrs out, u32 rank, u32 world, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int o = owner[i];
+    if (o < 0) out.p[rank][i] = *ptrs[i];
+    else if ((u32)o == rank) { u64 v = *ptrs[i]; for (u32 g = 0; g < world; g++) out.p[g][i] = v; }
+}
+void launch_gather_push(const u64* const* d_ptrs, const int* d_owner, const PeerPtrs& out, u32 rank, u32 world, size_t n, cudaStream_t st) {
+    if (!n) return;
+    k_gather_push<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ptrs, d_owner, out, rank, world, n);
     COUNT_LAUNCH();
 }
 

@@ -19,6 +19,33 @@ using gl::u32;
 using gl::E2;
 
 // ---------------------------------------------------------------------------------------------
+// One proof on G GPUs (DESIGN.md "Multi-GPU"): peer memory instead of collectives.
+//   Every rank (one process per GPU) keeps its proof buffers in an arena whose slabs are mapped into every
+//   other rank with CUDA IPC; all ranks allocate in the same order, so a buffer has the same offset everywhere
+//   and `PeerPtrs` holds the G views of one such buffer (p[rank] = the local one).  Producers STORE their results
+//   straight into the consumer's memory over NVLink (leaf digests into the owner of the Merkle leaf range,
+//   sub-roots / quotient chunk coefficients / small FRI layers / opened values into every rank), and a
+//   device-side flag barrier orders the stores before the consumers' next kernel.  No host round trip and no
+//   library collective is on the data path.
+//   Partition: rank g owns LDE cosets t in [t0, t0 + nt), nt = B / G (a contiguous slab [t0*N, (t0+nt)*N) of
+//   every coset-major LDE column), and the Merkle sub-tree over leaves [g*L/G, (g+1)*L/G).
+// ---------------------------------------------------------------------------------------------
+static constexpr u32 MAX_RANKS = 8;
+struct PeerPtrs { u64* p[MAX_RANKS]; };
+// where a kernel's outputs go: 0 = local buffer only (p[rank]), 1 = the rank owning the element (index >> owner_shift),
+// 2 = every rank
+enum PushMode : u32 { PUSH_LOCAL = 0, PUSH_OWNER = 1, PUSH_ALL = 2 };
+struct PushDst { PeerPtrs pp; u32 rank, world, mode, owner_shift; };
+inline PushDst local_dst(u64* p) { PushDst d{}; d.pp.p[0] = p; d.rank = 0; d.world = 1; d.mode = PUSH_LOCAL; d.owner_shift = 0; return d; }
+
+// Cross-GPU barrier on the stream: signal every peer's flag slot with `epoch` (release, system scope) and wait until
+// every peer has signalled this rank (acquire).  flags.p[g] = rank g's array of MAX_RANKS slots (slot s written by
+// rank s).  A wait longer than ~10 s raises bit 8 of *err instead of hanging the device.
+void launch_barrier(const PeerPtrs& flags, u32 rank, u32 world, u64 epoch, u32* err, cudaStream_t st);
+// src (local) -> the same words of every other rank's view dst.p[g]
+void launch_push(const u64* src, const PeerPtrs& dst, u32 rank, u32 world, size_t n, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
 // NTT plan for one transform size N = 2^n = N1 * N2 (strided pass of size N1, contiguous pass N2)
 // ---------------------------------------------------------------------------------------------
 struct NttTables {
@@ -64,13 +91,16 @@ struct LeafArgs { LeafMat m[8]; int n_mats; };
 //   prev_states  : SoA [12][B << prev_log_n] states of the previous (shorter) group, or NULL
 //   states_out   : SoA [12][B << log_n] if more groups follow, else NULL
 //   digests_out  : tree leaf layer (4 u64 per leaf, indexed by DOMAIN index r*B + t), or NULL
-//   r0, log_rn   : only rows r0 .. r0 + 2^log_rn of each coset are hashed (leaf range [r0*B, ...))
+//   t0, nt       : only cosets t0 .. t0 + nt are hashed (all rows of each); leaf r*B + t goes to dig (PushDst:
+//                  local layer, the rank owning the leaf's sub-tree, or every rank); dig == NULL: no digests
 void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
-                      u64* states_out, u64* digests_out, u32 r0, u32 log_rn, cudaStream_t st);
+                      u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st);
 // parent[i] = perm(child[2i] | child[2i+1] | 0000)[0..4]
 void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
-// FRI round leaves: leaf i' (< quarter) = sponge([f[i'], f[i'+2q], f[i'+q], f[i'+3q]]) (8 felts, one block)
-void launch_fri_leaf_hash(const u64* evals /* EF interleaved */, size_t rows, u32 log_arity, u64* digests, cudaStream_t st);
+// FRI round leaves: leaf i' (< quarter) = sponge([f[i'], f[i'+2q], f[i'+q], f[i'+3q]]) (8 felts, one block).
+// Only leaves i' with (i' mod 2^log_b) in [t0, t0 + nt) are hashed (t0 = 0, nt = 2^log_b: all).
+void launch_fri_leaf_hash(const u64* evals /* EF interleaved */, size_t rows, u32 log_arity, const PushDst& digests,
+                          u32 log_b, u32 t0, u32 nt, cudaStream_t st);
 void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
@@ -102,6 +132,7 @@ struct ConstraintArgs {
     const u64* acc_in; u32 acc_in_log_n;   // previous accumulator planes [2][B << acc_in_log_n], or NULL
     u64* acc_out;                          // planes [2][B << log_n]
     const NttTables* T;                    // for w_H powers (selectors)
+    u32 t0, nt;                            // cosets evaluated: [t0, t0 + nt); nt == 0: all
 };
 int launch_constraints(const ConstraintArgs& a, cudaStream_t st);   // returns 0 or -1 (program too large)
 
@@ -139,18 +170,21 @@ void launch_ood_reduce(const u64* partial, u32 n_cols, u32 n_chunks, u64* out /*
 
 struct DeepMat { const u64* base; u32 width; u32 log_n; u32 alpha_off; u32 pad; };
 struct DeepArgs {
-    DeepMat m[12]; int n_mats;
+    const DeepMat* m; int n_mats;   // device array
     u32 log_n_max, log_blowup;
     const u64* apow;         // device: W EF pairs, alpha^(W-1-i)
     u32 total_w;
     E2 z0, z1, fz0, fz1, beta;
-    u64* out;                // EF interleaved, indexed by domain index
+    PushDst out;             // EF interleaved, indexed by domain index (local, or stored into every rank)
     const NttTables* T;      // tables of the max height (w_H powers)
+    u32 t0, nt;              // cosets evaluated: [t0, t0 + nt); nt == 0: all
 };
 void launch_deep(const DeepArgs& a, cudaStream_t st);
 
-// next[i'] = fold4([f[i'], f[i'+2q], f[i'+q], f[i'+3q]], s_inv = w_dom^(-i'), beta)
-void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, u64* next, cudaStream_t st);
+// next[i'] = fold4([f[i'], f[i'+2q], f[i'+q], f[i'+3q]], s_inv = w_dom^(-i'), beta) for the i' with
+// (i' mod 2^log_b) in [t0, t0 + nt)
+void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, const PushDst& next, u32 log_b, u32 t0, u32 nt,
+                     cudaStream_t st);
 
 // Proof-of-work: smallest w such that the duplexed state has (st[7] & mask) == 0.
 //   base_state: 12 u64 with the pending inputs already written at rate[0..in_len) and the rest of
@@ -162,6 +196,9 @@ void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 cou
 // sets *flag |= 4 when a[i] != b[i] for some i < n (self-check of the NVRTC constraint kernels)
 void launch_compare(const u64* a, const u64* b, size_t n, u32* flag, cudaStream_t st);
 void launch_gather(const u64* const* d_ptrs, u64* d_out, size_t n, cudaStream_t st);
+// sharded openings: owner[i] < 0: out.p[rank][i] = *ptrs[i]; owner[i] == rank: the value is stored into every rank's
+// out.p[g][i]; otherwise rank owner[i] provides it
+void launch_gather_push(const u64* const* d_ptrs, const int* d_owner, const PeerPtrs& out, u32 rank, u32 world, size_t n, cudaStream_t st);
 
 // test/export helper: LDE (coset-major columns) -> row-major with bit-reversed rows
 void launch_export_lde_bitrev_rm(const u64* lde, u32 log_n, u32 log_blowup, u32 width, u64* out_rm, cudaStream_t st);

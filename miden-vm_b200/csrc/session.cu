@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -56,6 +57,10 @@ struct Arena {
     std::vector<Slab> slabs;
     std::multimap<size_t, char*> free_blocks;
     size_t live = 0, grow_events = 0;
+    // One proof on several GPUs: every rank runs the same allocation sequence, so a block has the same slab index and
+    // offset on every rank; the hooks map a new slab into the peers (CUDA IPC) and unmap before slabs are freed.
+    std::function<void(char*, size_t)> on_new_slab;
+    std::function<void()> before_drop_slabs;
     static size_t round_up(size_t b) { return (b + 511) & ~(size_t)511; }
     void* alloc(size_t bytes) {
         bytes = round_up(bytes);
@@ -67,6 +72,7 @@ struct Arena {
         CUDA_OK(cudaMalloc((void**)&base, sz));
         slabs.push_back(Slab{base, sz, bytes});
         grow_events++; live++;
+        if (on_new_slab) on_new_slab(base, sz);
         return base;
     }
     void free(void* p, size_t bytes) { free_blocks.emplace(round_up(bytes), (char*)p); live--; }
@@ -78,14 +84,15 @@ struct Arena {
         if (slabs.size() > 1) {
             size_t total = 0;
             for (Slab& sl : slabs) total += sl.size;
+            if (before_drop_slabs) before_drop_slabs();
             for (Slab& sl : slabs) cudaFree(sl.base);
             slabs.clear();
             char* base = nullptr;
-            if (cudaMalloc((void**)&base, total) == cudaSuccess) slabs.push_back(Slab{base, total, 0});
+            if (cudaMalloc((void**)&base, total) == cudaSuccess) { slabs.push_back(Slab{base, total, 0}); if (on_new_slab) on_new_slab(base, total); }
             else cudaGetLastError();   // the next proof grows again
         }
     }
-    void destroy() { for (Slab& sl : slabs) cudaFree(sl.base); slabs.clear(); free_blocks.clear(); live = 0; }
+    void destroy() { if (before_drop_slabs && !slabs.empty()) before_drop_slabs(); for (Slab& sl : slabs) cudaFree(sl.base); slabs.clear(); free_blocks.clear(); live = 0; }
 };
 thread_local Arena* tl_arena = nullptr;   // set while an API call works on a proof
 struct ArenaScope { Arena* prev; explicit ArenaScope(Arena* a) : prev(tl_arena) { tl_arena = a; } ~ArenaScope() { tl_arena = prev; } };
@@ -175,11 +182,34 @@ struct mdn_session {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string error;
-    // hash sharding across ranks (mdn_session_set_shard): rank g hashes the contiguous leaf range g of every
-    // commitment tree; the only exchange is an all-gather of the G sub-roots
+    // ONE proof on G ranks (mdn_session_set_shard; kernels.cuh "One proof on G GPUs"): rank g computes LDE cosets
+    // [g*B/G, (g+1)*B/G) of every column -- forward NTTs, leaf sponge, constraints, DEEP, FRI folds -- and the Merkle
+    // sub-tree over leaves [g*L/G, (g+1)*L/G).  Results cross ranks as peer-memory stores ordered by a device-side
+    // barrier; the host callback is only the bootstrap transport for the CUDA IPC handles.
     u32 shard_rank = 0, shard_world = 1, shard_log_g = 0;
     mdn_allgather_fn allgather = nullptr; void* allgather_ctx = nullptr;
-    bool tree_sharded(u32 depth) const { return shard_world > 1 && depth >= shard_log_g + 6; }
+    bool shard_active = false;                     // inside a proof that is split over the ranks
+    u32 shard_min_log = 10;                        // FRI layers below 2^shard_min_log leaves are replicated (MDN_SHARD_MIN_LOG)
+    struct SlabView { char* base[mk::MAX_RANKS]; size_t size; };
+    std::vector<SlabView> slab_views;              // every rank's mapping of arena slab i
+    u64* sync_local = nullptr; mk::PeerPtrs sync_flags{}; u64 sync_epoch = 0;
+    bool sharded() const { return shard_active && shard_world > 1; }
+    bool tree_sharded(u32 depth) const { return sharded() && depth >= shard_log_g + 6; }
+    bool fri_layer_sharded(u32 log_dom) const {    // domain 2^log_dom split by coset: folds and leaves stay rank-local
+        const u32 la = params.log_folding_arity, lb = params.log_blowup;
+        return sharded() && log_dom >= la + lb && log_dom >= la + shard_min_log;
+    }
+    u32 nt() const { return sharded() ? (1u << params.log_blowup) >> shard_log_g : (1u << params.log_blowup); }   // cosets of this rank
+    u32 t0() const { return sharded() ? shard_rank * nt() : 0; }
+    int coset_owner(u32 t) const { return sharded() ? (int)(t / nt()) : -1; }
+    mdn_external_check external_check = nullptr; void* external_ctx = nullptr;   // Statement::eval_external (mdn_session_set_external_check)
+    void shard_map_slab(char* base, size_t size);
+    void shard_unmap_slabs();
+    void shard_teardown();
+    void shard_barrier();
+    void shard_check(const char* where);
+    mk::PeerPtrs peers_of(const u64* p) const;
+    mk::PushDst push_dst(u64* p, u32 mode, u32 owner_shift = 0) const;
     std::map<u32, std::unique_ptr<NttPlan>> ntt_plans;
     std::map<std::pair<u32, u32>, std::unique_ptr<PremulPlan>> premul_plans;   // (n, kind)
 
@@ -317,7 +347,7 @@ PremulPlan& mdn_session::premul_quotient(u32 n, u32 log_d) {
 }
 
 void mdn_session::reset_proof() {
-    in_proof = false;
+    in_proof = false; shard_active = false;
     log_heights.clear(); order.clear(); publics.clear(); randomness.clear();
     aux_values_p.clear(); aux_values_off.clear();
     tr = Transcript();
@@ -332,11 +362,94 @@ void mdn_session::release_proof_memory() {
     arena.reset();
 }
 
+// ---------------------------------------------------------------------------------------------
+// One proof on G ranks: peer mappings of the arena, device barrier
+// ---------------------------------------------------------------------------------------------
+// Collective (every rank reaches it at the same point of the same allocation sequence): export the new slab, gather
+// the G handles through the host callback, map the peers' slabs.
+void mdn_session::shard_map_slab(char* base, size_t size) {
+    if (shard_world <= 1) return;
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, base));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    const size_t W = 10;
+    std::vector<u64> mine(W), all(W * shard_world);
+    memcpy(mine.data(), &h, 64); mine[8] = size; mine[9] = slab_views.size();
+    if (allgather(allgather_ctx, mine.data(), all.data(), W) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed");
+    SlabView v{}; v.size = size;
+    for (u32 g = 0; g < shard_world; g++) {
+        if (all[g * W + 8] != size || all[g * W + 9] != mine[9])
+            fail(MDN_ERR_INVALID_ARG, "rank %u allocated a different proof arena (slab %llu of %llu bytes here, slab %llu of %llu bytes there): every rank must prove the same statement with the same flags",
+                 g, (unsigned long long)mine[9], (unsigned long long)size, (unsigned long long)all[g * W + 9], (unsigned long long)all[g * W + 8]);
+        if (g == shard_rank) { v.base[g] = base; continue; }
+        cudaIpcMemHandle_t hg; memcpy(&hg, &all[g * W], 64);
+        void* m = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&m, hg, cudaIpcMemLazyEnablePeerAccess));
+        v.base[g] = (char*)m;
+    }
+    slab_views.push_back(v);
+}
+// Collective: nobody frees a slab a peer still has mapped.
+void mdn_session::shard_unmap_slabs() {
+    if (slab_views.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& v : slab_views) for (u32 g = 0; g < shard_world; g++) if (g != shard_rank && v.base[g]) cudaIpcCloseMemHandle(v.base[g]);
+    slab_views.clear();
+    if (shard_world > 1 && allgather) { std::vector<u64> one(1, 0), all(shard_world); allgather(allgather_ctx, one.data(), all.data(), 1); }
+}
+void mdn_session::shard_teardown() {
+    if (shard_world > 1) {
+        release_proof_memory();
+        arena.destroy();                    // unmaps the peers first (before_drop_slabs)
+        if (sync_local) {
+            for (u32 g = 0; g < shard_world; g++) if (g != shard_rank && sync_flags.p[g]) cudaIpcCloseMemHandle(sync_flags.p[g]);
+            cudaFree(sync_local); sync_local = nullptr;
+        }
+    }
+    arena.on_new_slab = nullptr; arena.before_drop_slabs = nullptr;
+    sync_flags = mk::PeerPtrs{}; sync_epoch = 0;
+    shard_rank = 0; shard_world = 1; shard_log_g = 0; allgather = nullptr; allgather_ctx = nullptr; shard_active = false;
+}
+mk::PeerPtrs mdn_session::peers_of(const u64* p) const {
+    mk::PeerPtrs r{};
+    if (shard_world <= 1) { r.p[0] = const_cast<u64*>(p); return r; }
+    for (size_t i = 0; i < slab_views.size() && i < arena.slabs.size(); i++) {
+        const char* b = arena.slabs[i].base;
+        if ((const char*)p >= b && (const char*)p < b + arena.slabs[i].size) {
+            size_t off = (const char*)p - b;
+            for (u32 g = 0; g < shard_world; g++) r.p[g] = (u64*)(slab_views[i].base[g] + off);
+            return r;
+        }
+    }
+    fail(MDN_ERR_CUDA, "internal: buffer outside the shared proof arena");
+}
+mk::PushDst mdn_session::push_dst(u64* p, u32 mode, u32 owner_shift) const {
+    if (!sharded() || mode == mk::PUSH_LOCAL) return mk::local_dst(p);
+    mk::PushDst d{};
+    d.pp = peers_of(p); d.rank = shard_rank; d.world = shard_world; d.mode = mode; d.owner_shift = owner_shift;
+    return d;
+}
+void mdn_session::shard_barrier() {
+    if (!sharded()) return;
+    mk::launch_barrier(sync_flags, shard_rank, shard_world, ++sync_epoch, (u32*)d_flag.p, stream);
+}
+void mdn_session::shard_check(const char* where) {
+    if (!sharded()) return;
+    u32 flag = 0;
+    CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    if (flag & 8) { CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); fail(MDN_ERR_CUDA, "cross-GPU barrier timed out (%s): a peer rank stopped or proves a different statement", where); }
+}
+
 void mdn_session::check_input_flag(const char* what) {
     u32 flag = 0;
     CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
-    if (flag) { CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); fail(MDN_ERR_INVALID_ARG, "%s contains a non-canonical field element (>= p)", what); }
+    if (flag) {
+        CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));
+        if (flag & 8) fail(MDN_ERR_CUDA, "cross-GPU barrier timed out: a peer rank stopped or proves a different statement");
+        fail(MDN_ERR_INVALID_ARG, "%s contains a non-canonical field element (>= p)", what);
+    }
 }
 
 // Host -> device copy on the copy stream.  Pinned (or registered) memory goes straight to the DMA engine;
@@ -397,21 +510,24 @@ void mdn_session::lde_matrix(CommittedMat& m) {
     NttPlan& plan = ntt(m.log_n);
     PremulPlan& pm = premul_trace(m.log_n);
     ProfScope ps(prof, PC_NTT);
-    ntt_bytes += (double)(N + L) * m.width * 8.0;   // read the trace column once, write the LDE once
+    ntt_bytes += (double)(N + (size_t)nt() * N) * m.width * 8.0;   // read the trace column once, write this rank's cosets of the LDE once
     mk::launch_intt(m.coef, N, m.width, plan.T, stream);
-    // column groups sized so a group's LDE (the fwd passes' working set) stays L2-resident
-    size_t col_bytes = L * sizeof(u64);
+    // this rank's cosets only (all B of them on one GPU); column groups sized so a group's LDE (the fwd passes'
+    // working set) stays L2-resident
+    const u32 tb = t0(), tn = nt();
+    (void)B;
+    size_t col_bytes = (size_t)tn * N * sizeof(u64);
     u32 group = (u32)std::max<size_t>(1, (48u << 20) / col_bytes);
     std::vector<mk::FwdItem> items;
     for (u32 cc = 0; cc < m.width; cc++)
-        for (u32 t = 0; t < B; t++)
+        for (u32 t = tb; t < tb + tn; t++)
             items.push_back(mk::FwdItem{m.coef + (size_t)cc * N, m.lde + (size_t)cc * L + (size_t)t * N, t, 0});
     DevBuf d_items;
     d_items.alloc(items.size() * sizeof(mk::FwdItem) / sizeof(u64), stream);
     CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(mk::FwdItem), cudaMemcpyHostToDevice, stream));
     for (u32 c0 = 0; c0 < m.width; c0 += group) {
         u32 cn = std::min(group, m.width - c0);
-        mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)c0 * B, cn * B, plan.T, pm.P, stream);
+        mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)c0 * tn, cn * tn, plan.T, pm.P, stream);
     }
 }
 
@@ -429,7 +545,11 @@ void mdn_session::lde_and_commit(Committed& c, float* t_lde, float* t_hash, bool
     if (t_hash) *t_hash += b;
 }
 
-// leaf sponge states per height group (ascending), then the compression layers
+// leaf sponge states per height group (ascending), then the compression layers.
+// Split over ranks: every rank hashes the leaves of its cosets and stores each digest into the rank that owns the
+// leaf's sub-tree (leaf index = domain index r*B + t, owner = index >> (depth - log G)); after the barrier every rank
+// compresses its own sub-tree, stores its sub-root into all ranks, and the top log G layers are recomputed everywhere.
+// Trees too small to split are replicated: the digests go to every rank.
 void mdn_session::build_tree(Committed& c) {
     u32 lb = params.log_blowup;
     u32 log_n_max = 0;
@@ -438,6 +558,10 @@ void mdn_session::build_tree(Committed& c) {
     size_t L = (size_t)1 << depth;
     c.tree.depth = depth;
     c.tree.nodes.alloc((2 * L - 1) * 4, stream);
+    const bool sh = sharded(), split = tree_sharded(depth);
+    const u32 lg = shard_log_g, tb = t0(), tn = nt();
+    mk::PushDst dig = push_dst(c.tree.layer(depth), sh ? (split ? mk::PUSH_OWNER : mk::PUSH_ALL) : mk::PUSH_LOCAL, depth - (split ? lg : 0));
+    shard_barrier();   // the tree buffer is a fresh allocation: no rank may still be using the memory under its old identity
     DevBuf states_a, states_b;
     const u64* prev = nullptr; u32 prev_log = 0;
     size_t i = 0;
@@ -457,27 +581,20 @@ void mdn_session::build_tree(Committed& c) {
         if (!last) out.alloc((size_t)12 << (ln + lb), stream);
         {
             ProfScope ps(prof, PC_LEAF);
-            // only the last (tallest) group is sharded; shorter groups are cheap and their states are
-            // needed by every rank
-            bool sh = last && tree_sharded(depth);
-            u32 log_rn = sh ? ln - shard_log_g : ln;
-            u32 r0 = sh ? shard_rank << log_rn : 0;
-            size_t Lg = (size_t)1 << (log_rn + lb);
+            size_t Lg = (size_t)tn << ln;
             for (int q = 0; q < args.n_mats; q++) { leaf_bytes += (double)Lg * args.m[q].width * 8.0; perms += Lg * ((args.m[q].width + 7) / 8); }
             leaf_bytes += last ? (double)Lg * 32.0 : (double)Lg * 96.0;
-            mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? c.tree.layer(depth) : nullptr, r0, log_rn, stream);
+            mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? &dig : nullptr, tb, tn, stream);
         }
         prev = out.p; prev_log = ln;
         i = j;
     }
-    if (!tree_sharded(depth)) {
+    shard_barrier();   // every digest of this rank's leaf range (or of the whole replicated tree) has arrived
+    if (!split) {
         ProfScope ps(prof, PC_COMPRESS);
         perms += L - 1;
         for (u32 d = depth; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
     } else {
-        // this rank's contiguous sub-tree, then ONE all-gather of the G sub-roots (32 bytes each), then the
-        // top log2(G) layers on every rank
-        u32 lg = shard_log_g;
         {
             ProfScope ps(prof, PC_COMPRESS);
             for (u32 d = depth; d-- > lg;) {
@@ -486,16 +603,15 @@ void mdn_session::build_tree(Committed& c) {
                 mk::launch_compress_layer(c.tree.layer(d + 1) + 2 * start * 4, c.tree.layer(d) + start * 4, cnt, stream);
             }
         }
-        std::vector<u64> mine(4), all(4 * (size_t)shard_world);
-        CUDA_OK(cudaMemcpyAsync(mine.data(), c.tree.layer(lg) + (size_t)shard_rank * 4, 32, cudaMemcpyDeviceToHost, stream));
-        CUDA_OK(cudaStreamSynchronize(stream));
-        if (allgather(allgather_ctx, mine.data(), all.data(), 4) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed");
-        CUDA_OK(cudaMemcpyAsync(c.tree.layer(lg), all.data(), all.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
+        u64* mine = c.tree.layer(lg) + (size_t)shard_rank * 4;
+        mk::launch_push(mine, peers_of(mine), shard_rank, shard_world, 4, stream);
+        shard_barrier();
         ProfScope ps(prof, PC_COMPRESS);
         for (u32 d = lg; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
     }
     CUDA_OK(cudaMemcpyAsync(c.root, c.tree.layer(0), 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+    shard_check("commitment");
 }
 
 // GrindingChallenger::grind on the device: smallest witness (sequential p3 order), then the
@@ -668,7 +784,28 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     if (params.log_folding_arity < 1 || params.log_folding_arity > 3) fail(MDN_ERR_INVALID_ARG, "invalid folding arity: log_arity %u (must be 1, 2, or 3)", params.log_folding_arity);
     u32 lb = params.log_blowup;
     if (lb == 0 || lb > 4) fail(MDN_ERR_UNSUPPORTED, "log_blowup must be in 1..=4");
+    if (st->n_public_values && !st->public_values) fail(MDN_ERR_INVALID_ARG, "public_values is NULL");
+    if (st->n_observe_felts && !st->observe_felts) fail(MDN_ERR_INVALID_ARG, "observe_felts is NULL");
+    for (u32 i = 0; i < st->n_public_values; i++) if (st->public_values[i] >= gl::P) fail(MDN_ERR_INVALID_ARG, "public value %u is not a canonical field element (>= p)", i);
+    for (u32 i = 0; i < st->n_observe_felts; i++) if (st->observe_felts[i] >= gl::P) fail(MDN_ERR_INVALID_ARG, "observed statement felt %u is not a canonical field element (>= p)", i);
+    // limits of this backend, checked before any device work: 8 matrices of one height per tree (leaf-sponge launch
+    // arguments); the DEEP kernel takes its matrices in batches, so their number is not limited
+    {
+        std::map<u32, u32> per_height_main, per_height_aux;
+        for (u32 i = 0; i < st->n_airs; i++) {
+            if (st->airs[i].width) per_height_main[traces[i].log_height]++;
+            if (st->airs[i].aux_width) per_height_aux[traces[i].log_height]++;
+        }
+        for (auto* mp : {&per_height_main, &per_height_aux})
+            for (auto& kv : *mp) if (kv.second > 8) fail(MDN_ERR_UNSUPPORTED, "%u traces of height 2^%u in one commitment (at most 8 matrices of one height per tree)", kv.second, kv.first);
+    }
     bool on_device = (flags & MDN_FLAG_DEVICE_TRACES) != 0;
+    if (shard_world > 1) {
+        if (!use_arena) fail(MDN_ERR_UNSUPPORTED, "a proof split over several ranks needs the proof arena (unset MDN_NO_ARENA)");
+        if (lb < shard_log_g) fail(MDN_ERR_UNSUPPORTED, "a proof can be split over at most 2^log_blowup = %u ranks (one LDE coset each)", 1u << lb);
+        shard_active = true;
+        shard_barrier();   // no rank stores into a peer's arena for this proof before every rank has left the previous one
+    }
     CUDA_OK(cudaEventRecord(ev[0], stream));
 
     u32 k = st->n_airs;
@@ -967,7 +1104,10 @@ void mdn_session::build_logup_aux(u32 j, u64* aux_cm, u64 final_out[2]) {
                 CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
                 CUDA_OK(cudaStreamSynchronize(stream));
                 if (flag & 4) {
-                    CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));   // NB: drops a concurrent zero-denominator report; the re-run below raises it again
+                    // clear the comparison bit only: a zero-denominator (2) or input (1) report raised by the same kernels stays
+                    u32 keep = flag & ~4u;
+                    CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));
+                    if (keep) { CUDA_OK(cudaMemcpyAsync(d_flag.p, &keep, sizeof keep, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream)); }
                     if (C > 1) CUDA_OK(cudaMemcpyAsync(aux_cm + 2 * N, aux2.p + 2 * N, 2 * (size_t)(C - 1) * N * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
                     CUDA_OK(cudaMemcpyAsync(totals.p, tot2.p, 2 * N * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
                     CUDA_OK(cudaStreamSynchronize(stream));
@@ -1030,6 +1170,7 @@ void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values
         }
         u32 nav = airs[inst].desc.num_aux_values;
         aux_values_off[j] = flat_values.size();
+        if (nav && !dev_aux && !zero_aux && (!aux_values || !aux_values[inst])) fail(MDN_ERR_INVALID_ARG, "aux values of instance %u are NULL", inst);
         for (u32 v = 0; v < 2 * nav; v++) {
             u64 x = dev_aux ? logup_final[v] : (zero_aux ? 0 : aux_values[inst][v]);
             if (x >= gl::P) fail(MDN_ERR_INVALID_ARG, "non-canonical aux value");
@@ -1038,6 +1179,18 @@ void mdn_session::commit_aux(const mdn_matrix* aux, const u64* const* aux_values
         co += N * w; lo += (N << lb) * w;
     }
     if (!zero_aux) check_input_flag("an aux trace");
+    // Statement::eval_external on the aux values in instance order -- including the finals of aux traces built on the
+    // device -- before anything is committed (prover/mod.rs:383-395, ProverError::ExternalAssertionFailed)
+    if (external_check) {
+        std::vector<std::vector<u64>> by_inst(k);
+        for (u32 j = 0; j < k; j++) by_inst[order[j]] = aux_values_p[j];
+        std::vector<const u64*> vp(k); std::vector<u32> vn(k); std::vector<uint8_t> lh(k);
+        for (u32 i = 0; i < k; i++) { vp[i] = by_inst[i].data(); vn[i] = (u32)by_inst[i].size() / 2; lh[i] = (uint8_t)log_heights[i]; }
+        u32 failed = 0;
+        int rc = external_check(external_ctx, (const u64*)randomness.data(), (u32)randomness.size(), vp.data(), vn.data(), lh.data(), k, &failed);
+        if (rc > 0) fail(MDN_ERR_EXTERNAL_ASSERTION, "external assertion %u failed", failed);
+        if (rc < 0) fail(MDN_ERR_EXTERNAL_ASSERTION, "eval_external reported a reduction error");
+    }
     lde_and_commit(aux_c, nullptr, nullptr);
     tr.send_commitment(aux_c.root);
     memcpy(dbg_roots[1], aux_c.root, 32);
@@ -1080,6 +1233,7 @@ void mdn_session::finish() {
         ca.alpha = alpha; ca.beta = beta;
         ca.acc_in = acc_cur < 0 ? nullptr : acc_pp[acc_cur].p; ca.acc_in_log_n = acc_prev_log; ca.acc_out = acc_pp[nxt].p;
         ca.T = &ntt(ln).T;
+        ca.t0 = t0(); ca.nt = nt();            // this rank's cosets (all of them on one GPU)
         ProfScope ps(prof, PC_CONSTRAINTS);
         if (air.jit && air.jit->checked < 0) air.jit.reset();   // failed its self-check earlier in this session
         jit_used.push_back(air.jit ? 1 : 0);
@@ -1101,8 +1255,9 @@ void mdn_session::finish() {
               for (u32 t = 0; t < B; t++) { ja.zh[t] = gl::sub(gl::mul(s_pow_n, x), 1); ja.inv_zh[t] = gl::inv(ja.zh[t]); x = gl::mul(x, w_b); } }
             ja.beta_a = beta.a; ja.beta_b = beta.b;
             ja.log_n = ln; ja.log_b = lb; ja.acc_in_log_n = ca.acc_in_log_n; ja.lo_bits = ca.T->lo_bits; ja.log_max_period = air.dev.log_max_period;
-            size_t Lj = (size_t)1 << (ln + lb);
-            try { air.jit->launch(ja, (unsigned)((Lj + 127) / 128), 128, stream); }
+            size_t Lj = (size_t)1 << (ln + lb), own = (size_t)ca.nt << ln;
+            ja.pad = ca.t0 | (ca.nt << 8);
+            try { air.jit->launch(ja, (unsigned)((own + 127) / 128), 128, stream); }
             catch (const std::exception& e) { fail(MDN_ERR_CUDA, "%s", e.what()); }
             mk::count_launch();
             if (air.jit->checked == 0) {
@@ -1112,12 +1267,22 @@ void mdn_session::finish() {
                 DevBuf chk; chk.alloc(2 * Lj, stream);
                 mk::ConstraintArgs cb = ca; cb.acc_out = chk.p;
                 if (mk::launch_constraints(cb, stream) != 0) fail(MDN_ERR_UNSUPPORTED, "constraint program too large for the interpreter");
-                mk::launch_compare(chk.p, ca.acc_out, 2 * Lj, (u32*)d_flag.p, stream);
+                for (u32 coord = 0; coord < 2; coord++) {     // the points this rank evaluated
+                    size_t o = (size_t)coord * Lj + ((size_t)ca.t0 << ln);
+                    mk::launch_compare(chk.p + o, ca.acc_out + o, own, (u32*)d_flag.p, stream);
+                }
                 u32 flag = 0;
                 CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
                 CUDA_OK(cudaStreamSynchronize(stream));
-                if (flag) {
+                if (sharded()) {
+                    // every rank must take the same branch (the ranks' allocation sequences have to stay identical)
+                    std::vector<u64> mine(1, flag & 4), all(shard_world);
+                    if (allgather(allgather_ctx, mine.data(), all.data(), 1) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed");
+                    for (u64 f : all) flag |= (u32)f;
+                }
+                if (flag & 4) {
                     CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));
+                    if (flag & ~4u) { u32 keep = flag & ~4u; CUDA_OK(cudaMemcpyAsync(d_flag.p, &keep, sizeof keep, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream)); }
                     CUDA_OK(cudaMemcpyAsync(ca.acc_out, chk.p, 2 * Lj * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
                     CUDA_OK(cudaStreamSynchronize(stream));
                     air.jit->checked = -1; jit_used.back() = 0;
@@ -1130,7 +1295,13 @@ void mdn_session::finish() {
     DevBuf acc = std::move(acc_pp[acc_cur]);
     acc_pp[1 - acc_cur].release();
     CUDA_OK(cudaEventRecord(ev[5], stream));
+    const u32 tb = t0(), tn = nt();
     if (keep_debug) {
+        if (sharded()) {   // debug export only: collect every rank's cosets of the accumulator
+            shard_barrier();
+            for (u32 coord = 0; coord < 2; coord++) { u64* own = acc.p + (size_t)coord * L + (size_t)tb * Nmax; mk::launch_push(own, peers_of(own), shard_rank, shard_world, (size_t)tn * Nmax, stream); }
+            shard_barrier();
+        }
         // natural order on gJ: index r*B + t  <- planes [coord][t*N + r]
         std::vector<u64> planes(2 * L);
         CUDA_OK(cudaMemcpyAsync(planes.data(), acc.p, 2 * L * sizeof(u64), cudaMemcpyDeviceToHost, stream));
@@ -1148,28 +1319,48 @@ void mdn_session::finish() {
     //    (for a satisfied AIR that equals the reference's evaluate-on-gJ-then-upsample, quotient.rs:45-56,
     //    because C/Z_H is then a polynomial of degree < N*D); chunk t < D is the LDE coset t*(B/D).
     //    The committed matrix has column 2t + coord.
+    //    Split over ranks: chunk t lives on the rank that owns coset t*(B/D); that rank interpolates it and stores
+    //    the coefficients into every rank (the all-gather of chunk coefficients of SURVEY 8(e), as peer stores),
+    //    then every rank evaluates all chunks on its own cosets.
     const u32 D = 1u << log_qd, cstep = B >> log_qd;
     {
         NttPlan& plan = ntt(log_max_n);
         PremulPlan& pm = premul_quotient(log_max_n, log_qd);
         size_t rq = prof.begin(PC_NTT);
-        ntt_bytes += (double)(Nmax + L) * 2 * D * 8.0;
-        for (u32 coord = 0; coord < 2; coord++) mk::launch_intt(acc.p + (size_t)coord * L, (size_t)cstep * Nmax, D, plan.T, stream);
+        ntt_bytes += (double)(Nmax + L) * 2 * D * 8.0 / (sharded() ? shard_world : 1);
+        // own chunks: c with c*cstep in [tb, tb + tn)
+        u32 c_lo = (tb + cstep - 1) / cstep, c_hi = std::min(D, (tb + tn + cstep - 1) / cstep);
+        if (c_hi > c_lo)
+            for (u32 coord = 0; coord < 2; coord++)
+                mk::launch_intt(acc.p + (size_t)coord * L + (size_t)c_lo * cstep * Nmax, (size_t)cstep * Nmax, c_hi - c_lo, plan.T, stream);
+        if (sharded()) {
+            shard_barrier();   // every rank is done writing / reading its accumulator planes
+            for (u32 c = c_lo; c < c_hi; c++)
+                for (u32 coord = 0; coord < 2; coord++) {
+                    u64* chunk = acc.p + (size_t)coord * L + (size_t)c * cstep * Nmax;
+                    mk::launch_push(chunk, peers_of(chunk), shard_rank, shard_world, Nmax, stream);
+                }
+            shard_barrier();
+        }
         quot_c.lde_buf.alloc(L * 2 * D, stream);
         quot_c.coef_buf = std::move(acc);
         quot_c.mats.push_back(CommittedMat{quot_c.lde_buf.p, quot_c.coef_buf.p, log_max_n, 2 * D});
         std::vector<mk::FwdItem> items;
         for (u32 t = 0; t < D; t++)
             for (u32 coord = 0; coord < 2; coord++)
-                for (u32 t2 = 0; t2 < B; t2++)
+                for (u32 t2 = tb; t2 < tb + tn; t2++)
                     items.push_back(mk::FwdItem{quot_c.coef_buf.p + (size_t)coord * L + (size_t)t * cstep * Nmax,
                                                 quot_c.lde_buf.p + (size_t)(2 * t + coord) * L + (size_t)t2 * Nmax, t * B + t2, 0});
         DevBuf d_items; d_items.alloc(items.size() * sizeof(mk::FwdItem) / sizeof(u64), stream);
         CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(mk::FwdItem), cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
-        // column-pair groups keep the working set near L2 size
-        u32 per = 2 * B;   // items per chunk t
-        for (u32 t = 0; t < D; t++) mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)t * per, per, plan.T, pm.P, stream);
+        // groups of whole chunks keep the working set near L2 size
+        u32 per = 2 * tn;   // items per chunk t
+        u32 chunks_per_launch = std::max(1u, B / tn);
+        for (u32 t = 0; t < D; t += chunks_per_launch) {
+            u32 cn = std::min(chunks_per_launch, D - t);
+            mk::launch_fwd_ntt((const mk::FwdItem*)d_items.p + (size_t)t * per, cn * per, plan.T, pm.P, stream);
+        }
         prof.end(rq);
         build_tree(quot_c);
         tr.send_commitment(quot_c.root);
@@ -1289,24 +1480,49 @@ void mdn_session::finish() {
     // 7c. DEEP quotient over the LDE domain (deep/prover.rs:214-312)
     DevBuf d_apow; d_apow.alloc(2 * (size_t)W, stream);
     CUDA_OK(cudaMemcpyAsync(d_apow.p, apow.data(), W * sizeof(E2), cudaMemcpyHostToDevice, stream));
+    // FRI shape (fri/mod.rs:80-94) and which layers stay split by coset: layer r (domain 2^(log_lde - la*r)) is
+    // produced rank-locally while fri_layer_sharded() holds; the first small layer is stored into every rank and
+    // everything after it is replicated.  The debug export of the DEEP evaluations needs layer 0 everywhere.
+    const u32 la = params.log_folding_arity;
+    u32 rounds; size_t final_deg;
+    {
+        u32 target = params.log_final_degree + lb;
+        u32 steps = log_lde > target ? log_lde - target : 0;
+        rounds = (steps + la - 1) / la;
+        u32 lf = log_lde > la * rounds ? log_lde - la * rounds : 0;
+        final_deg = (size_t)1 << (lf > lb ? lf - lb : 0);
+    }
+    std::vector<char> layer_sh(rounds + 1, 0);
+    for (u32 r = 0; r <= rounds && log_lde >= la * r; r++) {
+        bool shd = fri_layer_sharded(log_lde - la * r) && r < rounds && !(r == 0 && keep_debug);
+        layer_sh[r] = shd && (r == 0 || layer_sh[r - 1]);
+        if (!layer_sh[r]) break;
+    }
     std::vector<DevBuf> fri_layers;   // EF interleaved, natural domain order
     fri_layers.emplace_back(); fri_layers[0].alloc(2 * L, stream);
     {
         mk::DeepArgs da; da.n_mats = 0;
+        std::vector<mk::DeepMat> all_mats;
         size_t mi = 0;
         for (int g = 0; g < ng; g++)
             for (size_t m = 0; m < groups[g]->mats.size(); m++, mi++) {
                 CommittedMat& cm = groups[g]->mats[m];
                 if (!cm.width) continue;
-                if (da.n_mats == 12) fail(MDN_ERR_UNSUPPORTED, "more than 12 committed matrices");
-                da.m[da.n_mats++] = mk::DeepMat{cm.lde, cm.width, cm.log_n, aligned_off[mi], 0};
+                all_mats.push_back(mk::DeepMat{cm.lde, cm.width, cm.log_n, aligned_off[mi], 0});
             }
+        // descriptors travel through device memory, so the number of committed matrices is not limited
+        DevBuf d_mats; d_mats.alloc(std::max<size_t>(1, all_mats.size() * sizeof(mk::DeepMat) / sizeof(u64)), stream);
+        CUDA_OK(cudaMemcpyAsync(d_mats.p, all_mats.data(), all_mats.size() * sizeof(mk::DeepMat), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));   // all_mats is a stack vector
+        da.m = (const mk::DeepMat*)d_mats.p; da.n_mats = (int)all_mats.size();
         // NB: the quotient matrix's device columns are already in committed order (2t + coord).
         da.log_n_max = log_max_n; da.log_blowup = lb; da.apow = d_apow.p; da.total_w = W;
         da.z0 = z; da.z1 = z_next; da.fz0 = fz[0]; da.fz1 = fz[1]; da.beta = dbeta;
-        da.out = fri_layers[0].p; da.T = &ntt(log_max_n).T;
-        ProfScope ps(prof, PC_DEEP);
-        mk::launch_deep(da, stream);
+        da.out = push_dst(fri_layers[0].p, sharded() && !layer_sh[0] ? mk::PUSH_ALL : mk::PUSH_LOCAL);
+        da.T = &ntt(log_max_n).T; da.t0 = tb; da.nt = tn;
+        if (sharded() && !layer_sh[0]) shard_barrier();   // fresh target buffer on every rank
+        { ProfScope ps(prof, PC_DEEP); mk::launch_deep(da, stream); }
+        if (sharded() && !layer_sh[0]) shard_barrier();
     }
     CUDA_OK(cudaStreamSynchronize(stream));
     if (keep_debug) {
@@ -1320,16 +1536,8 @@ void mdn_session::finish() {
         }
     }
     // 7d. FRI commit phase (fri/prover.rs:93-242)
-    const u32 la = params.log_folding_arity;
-    u32 rounds; size_t final_deg;
-    {
-        u32 target = params.log_final_degree + lb;
-        u32 steps = log_lde > target ? log_lde - target : 0;
-        rounds = (steps + la - 1) / la;                       // fri/mod.rs:80-94
-        u32 lf = log_lde > la * rounds ? log_lde - la * rounds : 0;
-        final_deg = (size_t)1 << (lf > lb ? lf - lb : 0);
-    }
     std::vector<Tree> fri_trees(rounds);
+    std::vector<char> fri_split(rounds, 0);
     dbg_fri_roots.clear();
     u32 log_dom = log_lde;
     for (u32 r = 0; r < rounds; r++) {
@@ -1338,11 +1546,35 @@ void mdn_session::finish() {
         Tree& t = fri_trees[r];
         t.depth = log_dom - la;
         t.nodes.alloc((2 * q - 1) * 4, stream);
+        const bool in_sh = layer_sh[r] != 0;                       // this rank holds its cosets' entries of layer r only
+        const bool split = in_sh && tree_sharded(t.depth);         // sub-tree per rank, else a replicated tree
+        fri_split[r] = split;
+        const u32 ft0 = in_sh ? tb : 0, fnt = in_sh ? tn : B;
+        mk::PushDst dig = push_dst(t.layer(t.depth), in_sh ? (split ? mk::PUSH_OWNER : mk::PUSH_ALL) : mk::PUSH_LOCAL, t.depth - (split ? shard_log_g : 0));
+        if (in_sh) shard_barrier();
         {
             ProfScope ps(prof, PC_FRI);
-            perms += q * (la == 3 ? 2 : 1) + q - 1;
-            mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, t.layer(t.depth), stream);
+            perms += (q * (la == 3 ? 2 : 1) + q - 1) / (in_sh ? shard_world : 1);
+            mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
+        }
+        if (in_sh) shard_barrier();
+        if (!split) {
+            ProfScope ps(prof, PC_FRI);
             for (u32 d = t.depth; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
+        } else {
+            const u32 lg = shard_log_g;
+            {
+                ProfScope ps(prof, PC_FRI);
+                for (u32 d = t.depth; d-- > lg;) {
+                    size_t cnt = (size_t)1 << (d - lg), start = (size_t)shard_rank << (d - lg);
+                    mk::launch_compress_layer(t.layer(d + 1) + 2 * start * 4, t.layer(d) + start * 4, cnt, stream);
+                }
+            }
+            u64* mine = t.layer(lg) + (size_t)shard_rank * 4;
+            mk::launch_push(mine, peers_of(mine), shard_rank, shard_world, 4, stream);
+            shard_barrier();
+            ProfScope ps(prof, PC_FRI);
+            for (u32 d = lg; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
         }
         u64 root[4];
         CUDA_OK(cudaMemcpyAsync(root, t.layer(0), sizeof root, cudaMemcpyDeviceToHost, stream));
@@ -1352,9 +1584,16 @@ void mdn_session::finish() {
         grind(params.folding_pow_bits);
         E2 fb = tr.ch.sample_ext();
         fri_layers.emplace_back(); fri_layers[r + 1].alloc(2 * q, stream);
-        { ProfScope ps(prof, PC_FRI); mk::launch_fri_fold(fri_layers[r].p, log_dom, la, fb, fri_layers[r + 1].p, stream); }
+        {
+            const bool bcast = in_sh && !layer_sh[r + 1];          // the first replicated layer: stored into every rank
+            mk::PushDst nxt = push_dst(fri_layers[r + 1].p, bcast ? mk::PUSH_ALL : mk::PUSH_LOCAL);
+            if (bcast) shard_barrier();
+            { ProfScope ps(prof, PC_FRI); mk::launch_fri_fold(fri_layers[r].p, log_dom, la, fb, nxt, lb, ft0, fnt, stream); }
+            if (bcast) shard_barrier();
+        }
         log_dom -= la;
     }
+    shard_check("FRI commit phase");
     // final polynomial (fri/prover.rs:228-239): values on the size-final_deg subgroup are the
     // final-layer entries at natural indices i*B; iDFT on the host, sent in descending order.
     {
@@ -1384,13 +1623,16 @@ void mdn_session::finish() {
     for (u32 i = 0; i < params.num_queries; i++) qs.push_back((size_t)tr.ch.sample_bits(log_lde));
     dbg_queries.assign(qs.begin(), qs.end());
     Indices ti = Indices::make(qs, log_lde);
-    // 7f. openings: one pointer list, one gather (pcs/prover.rs:89-101; lifted_tree.rs:155-180)
+    // 7f. openings: one pointer list, one gather (pcs/prover.rs:89-101; lifted_tree.rs:155-180).  Split over ranks,
+    //     every opened word has an owner -- the rank holding that LDE coset / FRI coset / Merkle sub-tree -- which
+    //     stores it into every rank's value buffer (-1: replicated data, read locally).
     std::vector<const u64*> ptrs;
-    std::vector<int> sib_owner;   // per input-tree sibling (emission order): owning rank or -1 (replicated)
+    std::vector<int> owner;
     struct Emit { int kind; size_t count; size_t pad; };   // kind 0: `count` fields then `pad` zero fields; 1: commitment (4)
     std::vector<Emit> plan;
     for (int g = 0; g < ng; g++) {
         Committed& c = *groups[g];
+        const bool replicated = (&c == &prep_c);   // the preprocessed bundle is committed once, whole, on every rank
         Indices leafs = ti.folded(c.tree.depth);
         for (size_t idx : leafs.idx)
             for (auto& cm : c.mats) {
@@ -1398,16 +1640,15 @@ void mdn_session::finish() {
                 size_t im = idx & (((size_t)1 << ldm) - 1);
                 size_t t = im & (B - 1), rr = im >> lb;
                 size_t pos = (t << cm.log_n) + rr, Lm = (size_t)1 << ldm;
-                for (u32 col = 0; col < cm.width; col++) ptrs.push_back(cm.lde + (size_t)col * Lm + pos);
+                for (u32 col = 0; col < cm.width; col++) { ptrs.push_back(cm.lde + (size_t)col * Lm + pos); owner.push_back(replicated ? -1 : coset_owner((u32)t)); }
                 plan.push_back(Emit{0, cm.width, (size_t)((cm.width + 7) / 8 * 8 - cm.width)});
             }
         for (auto& ds : hostfs::missing_siblings(leafs)) {
-            for (int q = 0; q < 4; q++) ptrs.push_back(c.tree.layer(ds.first) + ds.second * 4 + q);
-            // sharded tree: a node below the sub-root level exists only on the rank owning its leaf range
-            int owner = -1;
-            if (tree_sharded(c.tree.depth) && ds.first > shard_log_g) owner = (int)(ds.second >> (ds.first - shard_log_g));
+            // split tree: a node below the sub-root level exists only on the rank owning its leaf range
+            int own = -1;
+            if (!replicated && tree_sharded(c.tree.depth) && ds.first > shard_log_g) own = (int)(ds.second >> (ds.first - shard_log_g));
+            for (int q = 0; q < 4; q++) { ptrs.push_back(c.tree.layer(ds.first) + ds.second * 4 + q); owner.push_back(own); }
             plan.push_back(Emit{1, 4, 0});
-            sib_owner.push_back(owner);
         }
     }
     {
@@ -1419,43 +1660,39 @@ void mdn_session::finish() {
             const u64* lay = fri_layers[r].p;
             u32 a = 1u << la;
             for (size_t idx : fi.idx) {
+                int own = layer_sh[r] ? coset_owner((u32)(idx & (B - 1))) : -1;    // the row's 2^la entries share idx's coset
                 for (u32 e = 0; e < a; e++) {
                     size_t src = idx + (size_t)gl::bitrev32(e, la) * q;
                     ptrs.push_back(lay + 2 * src); ptrs.push_back(lay + 2 * src + 1);
+                    owner.push_back(own); owner.push_back(own);
                 }
                 plan.push_back(Emit{0, 2 * (size_t)a, 0});
             }
             for (auto& ds : hostfs::missing_siblings(fi)) {
-                for (int qq = 0; qq < 4; qq++) ptrs.push_back(fri_trees[r].layer(ds.first) + ds.second * 4 + qq);
+                int own = -1;
+                if (fri_split[r] && ds.first > shard_log_g) own = (int)(ds.second >> (ds.first - shard_log_g));
+                for (int qq = 0; qq < 4; qq++) { ptrs.push_back(fri_trees[r].layer(ds.first) + ds.second * 4 + qq); owner.push_back(own); }
                 plan.push_back(Emit{1, 4, 0});
             }
             ld -= la;
         }
     }
     {
-        DevBuf d_ptrs, d_vals; d_ptrs.alloc(ptrs.size(), stream); d_vals.alloc(ptrs.size(), stream);
+        DevBuf d_ptrs, d_vals, d_owner; d_ptrs.alloc(ptrs.size(), stream); d_vals.alloc(ptrs.size(), stream);
         CUDA_OK(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(u64), cudaMemcpyHostToDevice, stream));
-        { ProfScope ps(prof, PC_GATHER); mk::launch_gather((const u64* const*)d_ptrs.p, d_vals.p, ptrs.size(), stream); }
+        if (!sharded()) {
+            ProfScope ps(prof, PC_GATHER); mk::launch_gather((const u64* const*)d_ptrs.p, d_vals.p, ptrs.size(), stream);
+        } else {
+            d_owner.alloc((owner.size() + 1) / 2, stream);
+            CUDA_OK(cudaMemcpyAsync(d_owner.p, owner.data(), owner.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            shard_barrier();
+            { ProfScope ps(prof, PC_GATHER); mk::launch_gather_push((const u64* const*)d_ptrs.p, (const int*)d_owner.p, peers_of(d_vals.p), shard_rank, shard_world, ptrs.size(), stream); }
+            shard_barrier();
+        }
         std::vector<u64> vals(ptrs.size());
         CUDA_OK(cudaMemcpyAsync(vals.data(), d_vals.p, vals.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
-        if (shard_world > 1) {
-            // exchange the sibling digests that live in another rank's sub-tree: every rank contributes the
-            // ones it owns (zeros elsewhere), one all-gather, take each from its owner
-            std::vector<size_t> pos; std::vector<int> own;
-            size_t o2 = 0, si = 0;
-            for (auto& e : plan) {
-                if (e.kind == 0) { o2 += e.count; continue; }
-                if (si < sib_owner.size()) { if (sib_owner[si] >= 0) { pos.push_back(o2); own.push_back(sib_owner[si]); } si++; }
-                o2 += 4;
-            }
-            if (!pos.empty()) {
-                std::vector<u64> mine(4 * pos.size(), 0), all(4 * pos.size() * shard_world);
-                for (size_t q = 0; q < pos.size(); q++) if (own[q] == (int)shard_rank) for (int w4 = 0; w4 < 4; w4++) mine[4 * q + w4] = vals[pos[q] + w4];
-                if (allgather(allgather_ctx, mine.data(), all.data(), mine.size()) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed");
-                for (size_t q = 0; q < pos.size(); q++) for (int w4 = 0; w4 < 4; w4++) vals[pos[q] + w4] = all[(size_t)own[q] * mine.size() + 4 * q + w4];
-            }
-        }
+        shard_check("query openings");
         size_t o = 0;
         for (auto& e : plan) {
             if (e.kind == 0) { for (size_t i = 0; i < e.count; i++) tr.hint_field(vals[o++]); for (size_t i = 0; i < e.pad; i++) tr.hint_field(0); }
@@ -1479,7 +1716,7 @@ void mdn_session::finish() {
     timings.kernel_launches = mk::launch_count();
     prof.resolve(timings.kernel_ms, timings.kernel_regions);
     timings.leaf_hash_bytes = leaf_bytes; timings.ntt_bytes = ntt_bytes; timings.permutations = perms;
-    in_proof = false;   // the API wrapper returns the proof's device memory to the arena once this frame is gone
+    in_proof = false; shard_active = false;   // the API wrapper returns the proof's device memory to the arena once this frame is gone
 }
 
 // =============================================================================================
@@ -1525,6 +1762,8 @@ void mdn_session_destroy(mdn_session* s) {
     cudaSetDevice(s->device);
     // every stream-ordered allocation must be returned before the stream goes away
     s->reset_proof();
+    s->allgather = nullptr;     // the peers may be gone already: unmap without a rendezvous
+    s->shard_teardown();
     s->prep_c = Committed();
     s->d_publics.release(); s->d_randomness.release(); s->d_aux_values.release(); s->d_flag.release();
     s->ntt_plans.clear(); s->premul_plans.clear();
@@ -1633,6 +1872,9 @@ int mdn_coset_lde_batch(mdn_session* s, const mdn_matrix* mat, uint32_t added_bi
     API_TRY(s)
     CUDA_OK(cudaSetDevice(s->device));
     if (added_bits != s->params.log_blowup) fail(MDN_ERR_UNSUPPORTED, "added_bits must equal the session's log_blowup");
+    if (mat->log_height > 22) fail(MDN_ERR_UNSUPPORTED, "trace height 2^%u exceeds the supported 2^22", mat->log_height);
+    if (mat->log_height + added_bits > 32) fail(MDN_ERR_DOMAIN, "LDE log order %u exceeds two-adicity 32", mat->log_height + added_bits);
+    if (s->in_proof) fail(MDN_ERR_INVALID_ARG, "mdn_coset_lde_batch called inside a proof");
     if (shift != gl::lde_shift(mat->log_height + added_bits)) fail(MDN_ERR_UNSUPPORTED, "only the canonical LDE shift 7^(2^(32-log_lde)) is supported");
     if (!s->d_flag.p) { s->d_flag.alloc(1, s->stream); CUDA_OK(cudaMemsetAsync(s->d_flag.p, 0, 8, s->stream)); }
     Committed c;
@@ -1641,7 +1883,7 @@ int mdn_coset_lde_batch(mdn_session* s, const mdn_matrix* mat, uint32_t added_bi
     c.mats.push_back(CommittedMat{c.lde_buf.p, c.coef_buf.p, mat->log_height, mat->width});
     s->upload_matrix(*mat, false, c.coef_buf.p);
     s->check_input_flag("the matrix");
-    s->lde_and_commit(c, nullptr, nullptr);
+    s->lde_matrix(c.mats[0]);          // the LDE only: no tree
     DevBuf rm; rm.alloc(L * mat->width, s->stream);
     mk::launch_export_lde_bitrev_rm(c.lde_buf.p, mat->log_height, added_bits, mat->width, rm.p, s->stream);
     CUDA_OK(cudaMemcpyAsync(out, rm.p, L * mat->width * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
@@ -1752,9 +1994,46 @@ long long mdn_get_info(mdn_session* s, mdn_info what, uint64_t* out, size_t cap)
 
 int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_allgather_fn fn, void* ctx) {
     if (!s) return MDN_ERR_INVALID_ARG;
-    if (world == 0 || (world & (world - 1)) || rank >= world || (world > 1 && !fn)) { s->error = "invalid shard configuration (world must be a power of two, callback required)"; return MDN_ERR_INVALID_ARG; }
-    s->shard_rank = rank; s->shard_world = world; s->allgather = fn; s->allgather_ctx = ctx;
-    s->shard_log_g = 0; while ((1u << s->shard_log_g) < world) s->shard_log_g++;
+    if (world == 0 || (world & (world - 1)) || world > mk::MAX_RANKS || rank >= world || (world > 1 && !fn)) {
+        s->error = "invalid shard configuration (world must be a power of two <= 8, callback required)"; return MDN_ERR_INVALID_ARG;
+    }
+    if (s->in_proof) { s->error = "mdn_session_set_shard called inside a proof"; return MDN_ERR_INVALID_ARG; }
+    try {
+        CUDA_OK(cudaSetDevice(s->device));
+        s->shard_teardown();
+        if (world == 1) return MDN_OK;
+        s->shard_rank = rank; s->shard_world = world; s->allgather = fn; s->allgather_ctx = ctx;
+        s->shard_log_g = 0; while ((1u << s->shard_log_g) < world) s->shard_log_g++;
+        if (const char* e = getenv("MDN_SHARD_MIN_LOG")) s->shard_min_log = (u32)atoi(e);
+        // the proof arena starts over as a shared arena: every slab is mapped into every rank when it is created
+        s->arena.destroy();
+        s->arena.on_new_slab = [s](char* base, size_t size) { s->shard_map_slab(base, size); };
+        s->arena.before_drop_slabs = [s]() { s->shard_unmap_slabs(); };
+        // barrier flags: one slot per source rank, zeroed before any peer can see the buffer
+        CUDA_OK(cudaMalloc((void**)&s->sync_local, 4096));
+        CUDA_OK(cudaMemsetAsync(s->sync_local, 0, 4096, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaIpcGetMemHandle(&h, s->sync_local));
+        std::vector<u64> mine(8), all(8 * (size_t)world);
+        memcpy(mine.data(), &h, 64);
+        if (fn(ctx, mine.data(), all.data(), 8) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed");
+        for (u32 g = 0; g < world; g++) {
+            if (g == rank) { s->sync_flags.p[g] = s->sync_local; continue; }
+            cudaIpcMemHandle_t hg; memcpy(&hg, &all[8 * (size_t)g], 64);
+            void* m = nullptr;
+            CUDA_OK(cudaIpcOpenMemHandle(&m, hg, cudaIpcMemLazyEnablePeerAccess));
+            s->sync_flags.p[g] = (u64*)m;
+        }
+        s->sync_epoch = 0;
+    } catch (const MdnError& e) { s->error = e.what(); return e.code; }
+    catch (const std::exception& e) { s->error = e.what(); return MDN_ERR_INVALID_ARG; }
+    return MDN_OK;
+}
+
+int mdn_session_set_external_check(mdn_session* s, mdn_external_check fn, void* ctx) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    s->external_check = fn; s->external_ctx = ctx;
     return MDN_OK;
 }
 

@@ -35,6 +35,16 @@ struct orc_proof { const uint8_t* log_trace_heights; size_t n_heights; const uin
 static thread_local std::string g_err;
 const char* orc_last_error() { return g_err.c_str(); }
 
+// OpenMP team size of every later call.  `torch.distributed.run` exports OMP_NUM_THREADS=1 to its workers, which
+// would run the CPU baseline single-threaded; bench.py sets the team size explicitly (n <= 0: all online CPUs).
+int orc_set_threads(int n) {
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_dynamic(0);
+    omp_set_num_threads(n);
+    return n;
+}
+int orc_get_threads() { return omp_get_max_threads(); }
+
 void orc_poseidon2_permute(uint64_t* st, size_t n) {
     for (size_t i = 0; i < n; i++) {
         State s; for (int k = 0; k < 12; k++) s[k] = Fp(st[12 * i + k]);

@@ -48,6 +48,11 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
 template <class T> static inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+// cross-process "peer memory" (one proof on several ranks): the arena slabs are POSIX shared memory here, the
+// system-scope fence is a host fence, and clock64() counts nanoseconds
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+long long clock64();
+namespace emu { void cpu_relax(); }
 
 // ---- runtime API subset used by session.cu / kernels.cu ------------------------------------------------
 typedef int cudaError_t;
@@ -91,6 +96,13 @@ cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int device);
 cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t pool, cudaMemPoolAttr a, void* v);
 cudaError_t cudaMemPoolGetAttribute(cudaMemPool_t pool, cudaMemPoolAttr a, void* v);
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p);
+// CUDA IPC stand-in: with MDN_EMU_SHM=1 every cudaMalloc is a named POSIX shared-memory object, the handle carries
+// its name, and cudaIpcOpenMemHandle maps it into the opening process
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void* p);
 }
 namespace emu { extern size_t g_max_dyn_smem_opt_in; }
 // not per kernel: remembers the largest opt-in so that a launch above the 48 KB default without ANY opt-in is caught

@@ -4,9 +4,15 @@
 // one after another, "device memory" is host memory, streams are synchronous, events carry wall-clock time.
 #include "cuda_runtime.h"
 #include <ucontext.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <string>
 #include <vector>
 
 namespace emu {
@@ -110,11 +116,64 @@ cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvali
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
-cudaError_t cudaMalloc(void** p, size_t bytes) { *p = aligned_alloc(256, (bytes + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorInvalidValue; }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
+// ---- device memory: plain heap, or (MDN_EMU_SHM=1, the multi-rank tests) named shared memory so that another
+//      rank's process can map it through the cudaIpc* stand-ins ---------------------------------------------
+namespace {
+struct ShmBlock { std::string name; size_t bytes; bool owner; };
+std::map<void*, ShmBlock> g_shm;
+unsigned g_shm_seq = 0;
+bool shm_mode() { static int m = getenv("MDN_EMU_SHM") ? 1 : 0; return m != 0; }
+struct ShmCleanup { ~ShmCleanup() { for (auto& kv : g_shm) if (kv.second.owner) shm_unlink(kv.second.name.c_str()); } } g_shm_cleanup;
+}
+long long clock64() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+namespace emu { void cpu_relax() { sched_yield(); } }
+static void* plain_alloc(size_t bytes) { return aligned_alloc(256, (bytes + 255) / 256 * 256 + 256); }
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+    if (!shm_mode()) { *p = plain_alloc(bytes); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+    char name[64];
+    snprintf(name, sizeof name, "/mdn_emu_%d_%u", (int)getpid(), g_shm_seq++);
+    size_t sz = (bytes + 4095) / 4096 * 4096 + 4096;
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return cudaErrorInvalidValue;
+    if (ftruncate(fd, (off_t)sz) != 0) { close(fd); shm_unlink(name); return cudaErrorInvalidValue; }
+    void* m = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { shm_unlink(name); return cudaErrorInvalidValue; }
+    g_shm[m] = ShmBlock{name, sz, true};
+    *p = m;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+    auto it = g_shm.find(p);
+    if (it == g_shm.end()) { free(p); return cudaSuccess; }
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    g_shm.erase(it);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    auto it = g_shm.find(p);
+    if (it == g_shm.end() || !it->second.owner) return cudaErrorInvalidValue;
+    memset(h, 0, sizeof *h);
+    snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+    memcpy(h->reserved + 48, &it->second.bytes, sizeof(size_t));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    size_t sz; memcpy(&sz, h.reserved + 48, sizeof sz);
+    int fd = shm_open(h.reserved, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void* m = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return cudaErrorInvalidValue;
+    g_shm[m] = ShmBlock{h.reserved, sz, false};
+    *p = m;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) { return cudaFree(p); }
+cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { *p = plain_alloc(bytes); return *p ? cudaSuccess : cudaErrorInvalidValue; }
 cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
+cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = plain_alloc(bytes); return *p ? cudaSuccess : cudaErrorInvalidValue; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }

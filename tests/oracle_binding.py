@@ -65,6 +65,8 @@ def lib():
             build()
         L = C.CDLL(path)
         L.orc_last_error.restype = C.c_char_p
+        L.orc_set_threads.restype = C.c_int; L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_get_threads.restype = C.c_int
         L.orc_fp_mul.restype = C.c_uint64; L.orc_fp_mul.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_fp_inv.restype = C.c_uint64; L.orc_fp_inv.argtypes = [C.c_uint64]
         L.orc_two_adic_generator.restype = C.c_uint64; L.orc_two_adic_generator.argtypes = [C.c_uint32]

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 # too large for fibers (2^20 and up), need the CUDA driver (NVRTC kernels), or need several processes.  The 2^16 case of
 # BASELINE config 2 (two-pass NTT, 8.4 M permutations) takes two more minutes and runs with MDN_EMU_FULL=1.
-SKIP = "not 2_20 and not 2_21 and not 2_22 and not full_size and not sharded and not jit" + ("" if os.environ.get("MDN_EMU_FULL") else " and not 2_16")
+SKIP = "not 2_20 and not 2_21 and not 2_22 and not full_size and not sharded and not split_proof and not jit" + ("" if os.environ.get("MDN_EMU_FULL") else " and not 2_16")
 
 
 def _build(gen):
@@ -46,19 +46,24 @@ def test_gpu_parity_suite_on_the_emulator():
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, tail
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_hash_sharded_proof_over_gloo_on_the_emulator(world):
-    """One proof hash-sharded over `world` ranks (mdn_session_set_shard: leaf ranges + all-gather of sub-roots and
-    of the sibling digests the openings need) is byte-identical to the unsharded proof -- the product's N>1 host
-    logic, here with one emulated device per process and gloo as the transport (NCCL on the GPU box:
-    test_hash_sharded_proof_matches_single_gpu)."""
+@pytest.mark.parametrize("world,min_log", [(2, None), (4, 2), (8, None)])
+def test_one_proof_split_over_ranks_on_the_emulator(world, min_log):
+    """ONE proof split over `world` ranks (mdn_session_set_shard: LDE cosets, leaf sponge, constraints, quotient chunks,
+    DEEP and FRI folds per coset; Merkle sub-trees per leaf range; peer-memory stores ordered by the device barrier) is
+    byte-identical to the unsplit proof -- the product's N>1 path, here with one emulated device per process, gloo as
+    the bootstrap transport and POSIX shared memory standing in for the CUDA IPC mappings (on the GPU box:
+    test_split_proof_matches_single_gpu).  min_log = 2 keeps even tiny FRI layers split, so the rank-local folds, the
+    split FRI trees and the first-replicated-layer store are exercised at every round of a small proof; the stage
+    outputs (roots, quotient accumulator, DEEP evaluations, FRI roots, query indices) are compared as well."""
     lib = _build("")
-    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1", SHARD_LOG_H="9", OMP_NUM_THREADS="1")
+    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1", MDN_EMU_SHM="1", SHARD_LOG_H="9", OMP_NUM_THREADS="1")
     env.pop("SHARD_BENCH", None)
+    if min_log is not None:
+        env.update(MDN_SHARD_MIN_LOG=str(min_log), SHARD_DEBUG_STAGES="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(29711 + world),
                         os.path.join(ROOT, "tests", "run_sharded.py")],
-                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+                       env=env, capture_output=True, text=True, timeout=1200, cwd=ROOT)
     assert r.returncode == 0 and f"SHARDED_OK world={world}" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 

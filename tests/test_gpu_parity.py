@@ -613,9 +613,9 @@ def test_two_sessions_are_independent():
         a.close(); b.close()
 
 
-def test_hash_sharded_proof_matches_single_gpu():
-    """mdn_session_set_shard: the same proof split over 2 GPUs (leaf ranges + all-gather of sub-roots over
-    NCCL) must be byte-identical.  Needs two visible GPUs (run with `gpurun --gpus 2`)."""
+def test_split_proof_matches_single_gpu():
+    """mdn_session_set_shard: the same proof split over 2 GPUs (LDE cosets + Merkle sub-trees per rank, peer-memory
+    stores over NVLink, device barrier) must be byte-identical.  Needs two visible GPUs (run with `gpurun --gpus 2`)."""
     import os, subprocess, sys, torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
