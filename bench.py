@@ -9,8 +9,12 @@ Metric: main-trace cells proved per second = sum_j 2^{n_j} * w_j / t_prove (BASE
 `value`  : traces already resident in HBM when the timed region starts.
 `e2e`    : the same call through the C ABI with pinned HOST trace buffers; the H2D copy of the
            traces and the host-side proof assembly are inside the timed region.
-Multi-GPU (N > 1): one process per GPU, each proving an independent trace (proof-level sharding,
-no data-path collective, weak scaling); the time is the max over ranks.
+Multi-GPU (N > 1): one process per GPU.  Default: ONE proof split over the N GPUs (`mdn_session_set_shard`: LDE cosets,
+leaf sponge, constraints, DEEP and FRI folds per coset, Merkle sub-trees per leaf range, peer-memory stores over NVLink);
+strong scaling, `value` = cells of the one proof / max-over-ranks time, and -- outside the timed region -- the proof is
+checked to be the same bytes on every rank and the same bytes as an unsplit single-GPU proof
+(`proof_identical_across_ranks`, `proof_identical_to_single_gpu`).  `--sharding proof`: one independent proof per GPU
+(weak scaling, no data exchange).
 """
 import argparse
 import ctypes as C
@@ -174,9 +178,10 @@ def main():
     ap.add_argument("--ref-log-height", type=int, default=0, help="CPU arm: 0 = the same height as --log-height")
     ap.add_argument("--cpu-log-height", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharding", choices=["proof", "hash"], default="proof",
-                    help="N>1: 'proof' = one independent proof per GPU (throughput, default); 'hash' = ONE proof whose "
-                         "Merkle hashing is split over the GPUs with an all-gather of sub-roots (latency)")
+    ap.add_argument("--sharding", choices=["coset", "proof"], default="coset",
+                    help="N>1: 'coset' (default) = ONE proof split over the GPUs -- LDE cosets, leaf sponge, constraints, DEEP and FRI "
+                         "folds per coset, Merkle sub-trees per leaf range, peer-memory stores over NVLink (strong scaling); "
+                         "'proof' = one independent proof per GPU (weak scaling, no data exchange)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -212,11 +217,11 @@ def main():
     lib = B.lib()   # raises BackendMissing if the CUDA library is absent: no fallback
     params = W.miden_pcs_params()
     lh = args.log_height
-    hash_sharded = world > 1 and args.sharding == "hash"
+    hash_sharded = world > 1 and args.sharding == "coset"     # ONE proof split over the ranks
     wl = W.Workload([lh] * 3, seed=W.SEED if hash_sharded else pkg.parallel.rank_seed(W.SEED, rank))
     sess = B.Session(params, local_rank)
     if hash_sharded:
-        sess.set_shard(rank, world, pkg.parallel.make_allgather_callback(f"cuda:{local_rank}"))
+        sess.set_shard(rank, world, pkg.parallel.make_allgather_callback(f"cuda:{local_rank}"))   # bootstrap transport of the IPC handles
 
     def observe(c, felts):
         lib.mdn_challenger_observe(C.byref(c), B.ptr(np.ascontiguousarray(felts, dtype=np.uint64)), len(felts))
@@ -270,6 +275,26 @@ def main():
 
     total_v = pkg.parallel.max_over_ranks(total_v, "cuda")
     total_e = pkg.parallel.max_over_ranks(total_e, "cuda")
+
+    # Outside every timed region: the split proof must be the same bytes on every rank and the same bytes as the proof
+    # of an unsplit single-GPU session (every rank proves it once as its local reference).
+    identical_ranks = identical_single = None
+    if hash_sharded:
+        import hashlib
+
+        def digest(pf):
+            return hashlib.sha256(bytes(pf[0]) + np.ascontiguousarray(pf[1], dtype=np.uint64).tobytes()
+                                  + np.ascontiguousarray(pf[2], dtype=np.uint64).tobytes()).digest()
+        single = B.Session(params, local_rank)
+        ref = single.prove(wl.statement, dev_m, ch, None, B.FLAG_DEVICE_TRACES)
+        single.close()
+        mine = [digest(proof), digest(proof_e), digest(ref)]
+        t = torch.tensor(list(b"".join(mine)), dtype=torch.uint8, device="cuda")
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        rows = [bytes(o.cpu().tolist()) for o in outs]
+        identical_ranks = all(r[:64] == rows[0][:64] for r in rows) and rows[0][:32] == rows[0][32:64]
+        identical_single = all(r[:32] == r[64:96] for r in rows)
     cells = wl.cells
     proofs_per_step = 1 if hash_sharded else world
     value = proofs_per_step * cells * args.steps / total_v
@@ -319,10 +344,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_v / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if hash_sharded else "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"synthetic 2^{lh} x (51,22,16) Miden-shaped prove (DummyMidenAir degree-9 constraint, zero aux 4/3/1 EF cols), "
-                                   "96-bit params: blowup 8, FRI arity 4, final degree 2^7, 27 queries, PoW 4/12/16, Poseidon2 LMCS + duplex challenger",
+            "config": {"workload": workload_name(lh),
                        "cells_per_proof": cells, "proofs_per_step": proofs_per_step,
-                       "sharding": ("one proof, Merkle hashing sharded by leaf range, all-gather of sub-roots" if hash_sharded else "one independent proof per GPU") if world > 1 else "single GPU",
+                       "sharding": ("ONE proof split over the GPUs: LDE cosets / leaf sponge / constraints / DEEP / FRI folds per coset, Merkle sub-trees per leaf range, "
+                                    "peer-memory stores + device barrier over NVLink (no library collective on the data path)" if hash_sharded else "one independent proof per GPU") if world > 1 else "single GPU",
                        "l2": "inputs (0.75 GB traces, 8 GB LDE) larger than L2", "timing": "wall clock around the synchronous C-ABI call, device synchronised on both sides, max over ranks",
                        "host_sched": sched, "step_log_ms_poolMiB_phases": pool_log if os.environ.get("MDN_BENCH_STEP_LOG") else None, "device_event_ms_per_step": tim_v.total, "per_step_ms": [round(x * 1e3, 2) for x in steps_v],
                        "per_step_device_event_ms": tim_v.dev_ms,
@@ -345,6 +370,9 @@ def main():
                           "evaluate_constraints": tim_v.evaluate_constraints, "commit_quotient": tim_v.commit_quotient, "open": tim_v.open},
             "proof_bytes": proof_bytes,
         }
+        if hash_sharded:
+            line["proof_identical_across_ranks"] = bool(identical_ranks)
+            line["proof_identical_to_single_gpu"] = bool(identical_single)
         if world == 1:
             # checker leg (oracle as verifier, outside every timed region): the last e2e proof must verify
             import helpers as H

@@ -1730,6 +1730,15 @@ extern "C" {
 
 int mdn_session_create(const mdn_pcs_params* params, int cuda_device, mdn_session** out) {
     if (!params || !out) { g_create_error = "null argument"; return MDN_ERR_INVALID_ARG; }
+    // PcsParams::new (pcs/params.rs:53-99), before any device is touched
+    if (params->log_folding_arity < 1 || params->log_folding_arity > 3) { g_create_error = "invalid folding arity: log_arity " + std::to_string(params->log_folding_arity) + " (must be 1, 2, or 3)"; return MDN_ERR_INVALID_ARG; }
+    if (params->log_blowup == 0) { g_create_error = "log_blowup must be at least 1"; return MDN_ERR_INVALID_ARG; }
+    if (params->num_queries == 0) { g_create_error = "num_queries must be at least 1"; return MDN_ERR_INVALID_ARG; }
+    if (params->log_final_degree + params->log_blowup < params->log_folding_arity - 1) {
+        g_create_error = "log_final_degree " + std::to_string(params->log_final_degree) + " + log_blowup " + std::to_string(params->log_blowup) + " is below the minimum target " +
+                         std::to_string(params->log_folding_arity - 1) + " reachable by fixed-arity folding";
+        return MDN_ERR_INVALID_ARG;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {

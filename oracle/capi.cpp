@@ -19,6 +19,18 @@ __attribute__((constructor)) static void orc_tune_malloc() {
     mallopt(M_TOP_PAD, 256 << 20);
 }
 
+// StatefulSponge over the reference's MockBinaryPermutation (see orc_mock_sponge below)
+template <size_t WIDTH, size_t RATE>
+static void mock_sponge(const uint64_t* in, size_t n, uint64_t* state_out) {
+    std::array<uint64_t, WIDTH> st{};
+    sponge_absorb_generic<uint64_t, WIDTH, RATE>(st, in, n, [](std::array<uint64_t, WIDTH>& s) {
+        uint64_t w = 0;
+        for (size_t i = 0; i < WIDTH; i++) w += s[i] * (uint64_t)(i + 1);
+        s.fill(w);
+    });
+    for (size_t i = 0; i < WIDTH; i++) state_out[i] = st[i];
+}
+
 extern "C" {
 
 struct orc_pcs_params { uint32_t log_blowup, log_folding_arity, log_final_degree, folding_pow_bits, deep_pow_bits, num_queries, query_pow_bits; };
@@ -84,6 +96,48 @@ int orc_fri_fold_row(uint32_t log_arity, const uint64_t* row, uint64_t s_inv, co
         out[0] = r.a.v; out[1] = r.b.v;
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// ---- hooks for the reference's own unit vectors (tests/test_reference_vectors.py, tests/golden/reference_unit_vectors.json)
+// StatefulSponge over the reference's MockBinaryPermutation (crates/stateful-hasher/src/testing.rs:38-49: every element
+// becomes sum(state[i] * (i + 1)), wrapping u64), for the (WIDTH, RATE) pairs its tests use (field_sponge.rs:85-160).
+int orc_mock_sponge(uint32_t width, uint32_t rate, const uint64_t* in, size_t n, uint64_t* state_out) {
+    if (width == 4 && rate == 2) mock_sponge<4, 2>(in, n, state_out);
+    else if (width == 6 && rate == 3) mock_sponge<6, 3>(in, n, state_out);
+    else if (width == 8 && rate == 4) mock_sponge<8, 4>(in, n, state_out);
+    else if (width == 12 && rate == 8) mock_sponge<12, 8>(in, n, state_out);
+    else return -1;
+    return 0;
+}
+// TreeIndices (lmcs/tree_indices.rs): op 0 = new (sorted, de-duplicated; -1 if an index is out of range),
+// 1 = fold_to_depth(arg) (-1 if arg > depth), 2 = shrink_depth(arg), 3 = missing_siblings as (depth, position) pairs.
+// Returns the number of u64 written to out (op 3: 2 per node) and the resulting depth in *depth_out.
+long long orc_tree_indices(int op, const uint64_t* idx, size_t n, uint32_t depth, uint32_t arg, uint64_t* out, size_t cap, uint32_t* depth_out) {
+    std::vector<size_t> v(idx, idx + n);
+    for (size_t x : v) if (depth < 64 && x >= (size_t(1) << depth)) return -1;     // TreeIndices::new validation (:34-45)
+    TreeIndices t = TreeIndices::make(v, depth);
+    std::vector<uint64_t> res;
+    if (op == 1) { if (arg > depth) return -1; t = t.fold_to_depth(arg); }
+    else if (op == 2) t.shrink_depth(arg);
+    if (op == 3) { for (auto& ds : missing_siblings(t)) { res.push_back(ds.first); res.push_back(ds.second); } }
+    else for (size_t x : t.idx) res.push_back(x);
+    if (depth_out) *depth_out = t.depth;
+    for (size_t i = 0; i < res.size() && i < cap; i++) out[i] = res[i];
+    return (long long)res.size();
+}
+// PcsParams::new validation (pcs/params.rs:53-99): 0 ok, 1 InvalidFoldingArity, 2 ZeroBlowup, 3 ZeroQueries,
+// 4 FinalDegreeUnreachable; FriParams::num_rounds / final_poly_degree (pcs/fri/mod.rs:80-115) for an LDE of 2^log_lde.
+int orc_pcs_params_check(const orc_pcs_params* p) {
+    if (p->log_folding_arity < 1 || p->log_folding_arity > 3) return 1;
+    if (p->log_blowup == 0) return 2;
+    if (p->num_queries == 0) return 3;
+    if (p->log_final_degree + p->log_blowup < p->log_folding_arity - 1) return 4;
+    return 0;
+}
+void orc_fri_shape(const orc_pcs_params* p, uint32_t log_lde, uint32_t* rounds, uint64_t* final_degree) {
+    PcsParams q; q.log_blowup = p->log_blowup; q.log_folding_arity = p->log_folding_arity; q.log_final_degree = p->log_final_degree;
+    *rounds = fri_num_rounds(q, log_lde);
+    *final_degree = fri_final_poly_degree(q, log_lde);
 }
 
 static Matrix to_matrix(const orc_matrix& m) {

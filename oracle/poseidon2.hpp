@@ -57,22 +57,29 @@ inline void poseidon2_permute(State& s) {
 
 using Digest = std::array<Fp, 4>;
 
-// Overwrite-mode sponge absorb, WIDTH 12 / RATE 8 (crates/stateful-hasher/src/field_sponge.rs:41-59):
-// each full chunk of 8 overwrites state[0..8] then permutes; a trailing partial chunk is
-// zero-filled to the rate boundary and permuted; an empty input leaves the state untouched.
-inline void sponge_absorb(State& st, const Fp* in, size_t n) {
+// Overwrite-mode sponge absorb (crates/stateful-hasher/src/field_sponge.rs:41-59), generic in the element type, the
+// width/rate and the permutation like the reference's `StatefulSponge<P, WIDTH, RATE, OUT>`: each full chunk of RATE
+// overwrites state[0..RATE] then permutes; a trailing partial chunk is zero-filled to the rate boundary and permuted;
+// an empty input leaves the state untouched.  The production instance is (Fp, 12, 8, Poseidon2); the reference's own
+// unit vectors use a mock permutation over u64 (tests/test_reference_vectors.py pins this function on them).
+template <class T, size_t WIDTH, size_t RATE, class Perm>
+inline void sponge_absorb_generic(std::array<T, WIDTH>& st, const T* in, size_t n, Perm&& permute) {
+    static_assert(RATE < WIDTH, "rate must leave a capacity");
     size_t i = 0;
-    while (i + 8 <= n) {
-        for (int k = 0; k < 8; k++) st[k] = in[i + k];
-        poseidon2_permute(st);
-        i += 8;
+    while (i + RATE <= n) {
+        for (size_t k = 0; k < RATE; k++) st[k] = in[i + k];
+        permute(st);
+        i += RATE;
     }
     if (i < n) {
         size_t rem = n - i;
         for (size_t k = 0; k < rem; k++) st[k] = in[i + k];
-        for (size_t k = rem; k < 8; k++) st[k] = Fp();
-        poseidon2_permute(st);
+        for (size_t k = rem; k < RATE; k++) st[k] = T();
+        permute(st);
     }
+}
+inline void sponge_absorb(State& st, const Fp* in, size_t n) {
+    sponge_absorb_generic<Fp, 12, 8>(st, in, n, [](State& s) { poseidon2_permute(s); });
 }
 inline Digest sponge_squeeze(const State& st) { return Digest{st[0], st[1], st[2], st[3]}; }
 
