@@ -104,7 +104,11 @@ void launch_push(const u64* src, const PeerPtrs& dst, u32 rank, u32 world, size_
 // =============================================================================================
 // transpose: row-major (n_rows x width) -> column-major
 // =============================================================================================
-__global__ void k_transpose(const u64* __restrict__ src, u64* __restrict__ dst, u32 n_rows, u32 width, u32* bad) {
+// Rows [row0, row0 + n_rows) of a row-major matrix (src points at row row0) -> columns of height col_stride; the
+// destination is one buffer (world == 1) or the same buffer on every rank (a proof split over ranks uploads a
+// different row range on every rank and stores the transposed slice into all of them).
+struct TransposeDst { PeerPtrs dst; PeerPtrs bad; u32 world; };
+__global__ void k_transpose(const u64* __restrict__ src, TransposeDst d, u32 n_rows, u32 width, size_t col_stride, u32 row0) {
     __shared__ u64 tile[32][33];
     u32 r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     bool any_bad = false;
@@ -116,16 +120,29 @@ __global__ void k_transpose(const u64* __restrict__ src, u64* __restrict__ dst, 
             tile[i][threadIdx.x] = v;
         }
     }
-    if (any_bad && bad) atomicOr(bad, 1u);
+    if (any_bad) for (u32 g = 0; g < d.world; g++) if (d.bad.p[g]) atomicOr(reinterpret_cast<u32*>(d.bad.p[g]), 1u);
     __syncthreads();
     for (u32 i = threadIdx.y; i < 32; i += 8) {
         u32 c = c0 + i, r = r0 + threadIdx.x;
-        if (r < n_rows && c < width) dst[(size_t)c * n_rows + r] = tile[threadIdx.x][i];
+        if (r < n_rows && c < width) {
+            u64 v = tile[threadIdx.x][i];
+            size_t o = (size_t)c * col_stride + row0 + r;
+            for (u32 g = 0; g < d.world; g++) d.dst.p[g][o] = v;
+        }
     }
 }
 void launch_transpose_rm_to_cm(const u64* src, u64* dst, u32 n_rows, u32 width, u32* d_bad_flag, cudaStream_t st) {
+    TransposeDst d{}; d.dst.p[0] = dst; d.bad.p[0] = reinterpret_cast<u64*>(d_bad_flag); d.world = 1;
     dim3 grid((n_rows + 31) / 32, (width + 31) / 32), block(32, 8);
-    k_transpose<<<grid, block, 0, st>>>(src, dst, n_rows, width, d_bad_flag);
+    k_transpose<<<grid, block, 0, st>>>(src, d, n_rows, width, (size_t)n_rows, 0u);
+    COUNT_LAUNCH();
+}
+void launch_transpose_slice_push(const u64* src_slice, const PeerPtrs& dst_cm, const PeerPtrs& bad, u32 world, u32 row0, u32 n_rows_slice,
+                                 u32 n_rows_total, u32 width, cudaStream_t st) {
+    if (!n_rows_slice || !width) return;
+    TransposeDst d{}; d.dst = dst_cm; d.bad = bad; d.world = world;
+    dim3 grid((n_rows_slice + 31) / 32, (width + 31) / 32), block(32, 8);
+    k_transpose<<<grid, block, 0, st>>>(src_slice, d, n_rows_slice, width, (size_t)n_rows_total, row0);
     COUNT_LAUNCH();
 }
 
@@ -784,22 +801,23 @@ __global__ void k_pow_tables(PowTable tab, u32 n, u32 h, u64* __restrict__ A, u6
     u64* dst = is_a ? A : B;
     reinterpret_cast<ulonglong2*>(dst)[idx] = make_ulonglong2(w.a, w.b);
 }
-__global__ void k_pow_bitrev(const u64* __restrict__ A, const u64* __restrict__ B, u32 n, u32 h, u64* __restrict__ wvec) {
-    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= ((size_t)1 << n)) return;
+__global__ void k_pow_bitrev(const u64* __restrict__ A, const u64* __restrict__ B, u32 n, u32 h, u64* __restrict__ wvec_slice, size_t p0, size_t cnt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    size_t p = p0 + i;
+    u64* wvec = wvec_slice - 2 * p0;
     ulonglong2 a = reinterpret_cast<const ulonglong2*>(A)[p >> h], b = reinterpret_cast<const ulonglong2*>(B)[p & ((1u << h) - 1)];
     E2 w = gl::e2_mul(gl::e2(a.x, a.y), gl::e2(b.x, b.y));
     reinterpret_cast<ulonglong2*>(wvec)[p] = make_ulonglong2(w.a, w.b);
 }
-void launch_pow_bitrev(E2 y, u32 n, u64* wvec, u64* scratch, cudaStream_t st) {
-    size_t N = (size_t)1 << n;
+void launch_pow_bitrev(E2 y, u32 n, u64* wvec, u64* scratch, size_t p0, size_t cnt, cudaStream_t st) {
     PowTable tab;
     E2 x = y;
     for (u32 i = 0; i < 24; i++) { tab.sq[i] = x; x = gl::e2_sqr(x); }
     u32 h = n / 2, na = 1u << (n - h), nb = 1u << h;
     u64* A = scratch; u64* B = scratch + 2 * (size_t)na;
     k_pow_tables<<<(na + nb + 127) / 128, 128, 0, st>>>(tab, n, h, A, B);
-    k_pow_bitrev<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(A, B, n, h, wvec);
+    k_pow_bitrev<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(A, B, n, h, wvec, p0, cnt);
     COUNT_LAUNCH(); COUNT_LAUNCH();
 }
 

@@ -71,6 +71,10 @@ struct PremulTables {
 
 // d_bad_flag (optional): set to 1 if any value is not a canonical field element (>= p)
 void launch_transpose_rm_to_cm(const u64* src_rm, u64* dst_cm, u32 n_rows, u32 width, u32* d_bad_flag, cudaStream_t st);
+// Rows [row0, row0 + n_rows_slice) (src_slice points at row row0) -> the same rows of the column-major matrix on EVERY
+// rank (dst_cm.p[g], columns of height n_rows_total); a non-canonical value raises bit 0 of every rank's bad.p[g].
+void launch_transpose_slice_push(const u64* src_slice, const PeerPtrs& dst_cm, const PeerPtrs& bad, u32 world, u32 row0, u32 n_rows_slice,
+                                 u32 n_rows_total, u32 width, cudaStream_t st);
 
 // In-place inverse NTT of `n_cols` columns (stride col_stride): natural evaluations over H ->
 // coefficients (unscaled by 1/N; the forward premul tables carry it), stored bit-reversed.
@@ -161,8 +165,9 @@ static constexpr u32 LOGUP_MAX_COLS = 16;
 // ---------------------------------------------------------------------------------------------
 // DEEP / FRI / misc
 // ---------------------------------------------------------------------------------------------
-// wvec[p] = y^(bitrev_n(p)) for p < 2^n  (EF interleaved); scratch: 2 * (2^(n - n/2) + 2^(n/2)) u64
-void launch_pow_bitrev(E2 y, u32 n, u64* wvec, u64* scratch, cudaStream_t st);
+// wvec[i] = y^(bitrev_n(p0 + i)) for i < cnt  (EF interleaved; p0 = 0, cnt = 2^n: the whole vector);
+// scratch: 2 * (2^(n - n/2) + 2^(n/2)) u64
+void launch_pow_bitrev(E2 y, u32 n, u64* wvec, u64* scratch, size_t p0, size_t cnt, cudaStream_t st);
 // partial dot products: out[(col * n_chunks + chunk) * 4 + {0,1}] (point 0), {2,3} (point 1)
 void launch_ood_dot(const u64* coef, size_t col_stride, u32 n_cols, u32 n, const u64* w0, const u64* w1,
                     u64* partial, u32 n_chunks, cudaStream_t st);

@@ -445,6 +445,12 @@ void mdn_session::check_input_flag(const char* what) {
     u32 flag = 0;
     CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+    if (sharded()) {   // slices checked by the other ranks report into every rank's word (launch_transpose_slice_push)
+        u32 peer_flag = 0;
+        CUDA_OK(cudaMemcpyAsync(&peer_flag, sync_local + 16, sizeof peer_flag, cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        if (peer_flag) { CUDA_OK(cudaMemsetAsync(sync_local + 16, 0, 8, stream)); flag |= peer_flag & 1u; }
+    }
     if (flag) {
         CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream));
         if (flag & 8) fail(MDN_ERR_CUDA, "cross-GPU barrier timed out: a peer rank stopped or proves a different statement");
@@ -980,7 +986,34 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     // H2D copies run on a second stream, so the LDE of matrix j overlaps the copy of matrix j+1
     // (copies of pinned buffers are asynchronous; pageable buffers degrade to a staged copy).
     std::vector<DevBuf> staging(k);
-    if (!on_device) {
+    if (!on_device && sharded()) {
+        // A proof split over G ranks: every rank copies 1/G of the rows of every trace to its GPU, transposes that slice
+        // and stores it into the column-major trace of EVERY rank over NVLink, so each PCIe link carries 1/G of the
+        // trace instead of all of it.  Traces too short to split are copied whole by every rank.
+        const u32 lg = shard_log_g;
+        auto slice_rows = [&](u32 ln) -> size_t { return ln >= lg + 5 ? ((size_t)1 << (ln - lg)) : ((size_t)1 << ln); };
+        for (u32 j = 0; j < k; j++) staging[j].alloc(slice_rows(main_c.mats[j].log_n) * main_c.mats[j].width, stream);
+        shard_barrier();                       // the coefficient buffer is a fresh allocation on every rank
+        CUDA_OK(cudaEventRecord(copy_ev[7], stream));
+        CUDA_OK(cudaStreamWaitEvent(copy_stream, copy_ev[7], 0));
+        mk::PeerPtrs bad{};
+        for (u32 g = 0; g < shard_world; g++) bad.p[g] = sync_flags.p[g] + 16;
+        for (u32 j = 0; j < k; j++) {
+            const mdn_matrix& m = traces[order[j]];
+            CommittedMat& cm = main_c.mats[j];
+            const bool whole = cm.log_n < lg + 5;
+            size_t rows = slice_rows(cm.log_n), row0 = whole ? 0 : rows * shard_rank;
+            host_to_device(staging[j].p, m.values + row0 * cm.width, rows * cm.width);
+            CUDA_OK(cudaEventRecord(copy_ev[j % 7], copy_stream));
+            CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[j % 7], 0));
+            ProfScope ps(prof, PC_TRANSPOSE);
+            if (whole) mk::launch_transpose_rm_to_cm(staging[j].p, cm.coef, 1u << cm.log_n, cm.width, (u32*)d_flag.p, stream);
+            else mk::launch_transpose_slice_push(staging[j].p, peers_of(cm.coef), bad, shard_world, (u32)row0, (u32)rows, 1u << cm.log_n, cm.width, stream);
+        }
+        shard_barrier();                       // every rank's slices have arrived everywhere
+        CUDA_OK(cudaEventRecord(ev[1], stream));
+        for (u32 j = 0; j < k; j++) { keep_raw_main(j); lde_matrix(main_c.mats[j]); }
+    } else if (!on_device) {
         for (u32 j = 0; j < k; j++) staging[j].alloc(((size_t)1 << main_c.mats[j].log_n) * main_c.mats[j].width, stream);
         CUDA_OK(cudaEventRecord(copy_ev[7], stream));
         CUDA_OK(cudaStreamWaitEvent(copy_stream, copy_ev[7], 0));
@@ -1392,24 +1425,33 @@ void mdn_session::finish() {
     struct MatEval { std::vector<u64> v; };   // width x 4
     std::vector<std::vector<MatEval>> evals(ng);
     {
-        ProfScope ps_ood(prof, PC_OOD);
+        // Split over ranks: a column's dot product with the weight vector is a sum over coefficient slots, so rank g
+        // takes slots [g*N/G, (g+1)*N/G) of every (tall enough) column -- it builds only that slice of each weight
+        // vector -- and the G partial sums per column meet in every rank's buffer (peer stores) and are added on the host.
+        size_t ood_region = prof.begin(PC_OOD);
         // all dot products are queued first and fetched with ONE device->host copy
         size_t total_cols = 0;
         for (int g = 0; g < ng; g++) for (auto& cm : groups[g]->mats) total_cols += cm.width;
-        DevBuf d_out; d_out.alloc(std::max<size_t>(1, total_cols * 4), stream);
+        const size_t T = std::max<size_t>(1, total_cols * 4);
+        const u32 G = sharded() ? shard_world : 1, me = sharded() ? shard_rank : 0, lg = sharded() ? shard_log_g : 0;
+        DevBuf d_all; d_all.alloc(T * G, stream);
+        u64* d_out = d_all.p + (size_t)me * T;
+        auto sliced = [&](u32 ln) { return G > 1 && ln >= lg + shard_min_log; };
         std::vector<DevBuf> keep;                              // weight vectors / partial sums stay alive until the copy
-        std::map<u32, std::pair<u64*, u64*>> weights;          // per log height: (w0, w1)
+        std::map<u32, std::pair<u64*, u64*>> weights;          // per log height: (w0, w1), this rank's slice
         auto make_w = [&](u32 ln, E2 y0, E2 y1) {
-            keep.emplace_back(); keep.back().alloc((size_t)2 << ln, stream); u64* a = keep.back().p;
-            keep.emplace_back(); keep.back().alloc((size_t)2 << ln, stream); u64* b = keep.back().p;
+            size_t S = sliced(ln) ? ((size_t)1 << (ln - lg)) : ((size_t)1 << ln), p0 = sliced(ln) ? S * me : 0;
+            keep.emplace_back(); keep.back().alloc(2 * S, stream); u64* a = keep.back().p;
+            keep.emplace_back(); keep.back().alloc(2 * S, stream); u64* b = keep.back().p;
             size_t tw = 2 * (((size_t)1 << (ln - ln / 2)) + ((size_t)1 << (ln / 2)));
             keep.emplace_back(); keep.back().alloc(2 * tw, stream); u64* sc = keep.back().p;
-            mk::launch_pow_bitrev(y0, ln, a, sc, stream);
-            mk::launch_pow_bitrev(y1, ln, b, sc + tw, stream);
+            mk::launch_pow_bitrev(y0, ln, a, sc, p0, S, stream);
+            mk::launch_pow_bitrev(y1, ln, b, sc + tw, p0, S, stream);
             return std::make_pair(a, b);
         };
         size_t col_off = 0;
-        std::vector<std::pair<size_t, u64>> scale;             // (first u64 index, 1/N) per matrix
+        struct Scale { size_t off; u64 n_inv; bool sliced; };
+        std::vector<Scale> scale;                              // (first u64 index, 1/N, summed over ranks?) per matrix
         for (int g = 0; g < ng; g++) {
             evals[g].resize(groups[g]->mats.size());
             for (size_t m = 0; m < groups[g]->mats.size(); m++) {
@@ -1418,13 +1460,16 @@ void mdn_session::finish() {
                 if (!cm.width) continue;
                 u32 ln = cm.log_n, lr = log_max_n - ln;
                 size_t Nm = (size_t)1 << ln;
-                u32 n_chunks = (u32)std::max<size_t>(1, std::min<size_t>(Nm / 4096, 256));   // k_ood_reduce walks the chunks serially
+                const bool sl = sliced(ln);
+                const u32 ls = sl ? ln - lg : ln;                      // log of the slice this rank sums over
+                const size_t S = (size_t)1 << ls, s0 = sl ? S * me : 0;
+                u32 n_chunks = (u32)std::max<size_t>(1, std::min<size_t>(S / 4096, 256));   // k_ood_reduce walks the chunks serially
                 if (g != gq) {
                     auto it = weights.find(ln);
                     if (it == weights.end()) it = weights.emplace(ln, make_w(ln, gl::e2_exp_pow2(z, lr), gl::e2_exp_pow2(z_next, lr))).first;
                     keep.emplace_back(); keep.back().alloc((size_t)cm.width * n_chunks * 4, stream);
-                    mk::launch_ood_dot(cm.coef, Nm, cm.width, ln, it->second.first, it->second.second, keep.back().p, n_chunks, stream);
-                    mk::launch_ood_reduce(keep.back().p, cm.width, n_chunks, d_out.p + col_off * 4, stream);
+                    mk::launch_ood_dot(cm.coef + s0, Nm, cm.width, ls, it->second.first, it->second.second, keep.back().p, n_chunks, stream);
+                    mk::launch_ood_reduce(keep.back().p, cm.width, n_chunks, d_out + col_off * 4, stream);
                 } else {
                     // quotient chunk t: stored coefficients are a_k * (g*w_J^t)^k (planes coord, column t*(B/D)),
                     // so q_t(y) is their evaluation at y / (g * w_J^t); outputs land at columns 2t, 2t+1.
@@ -1433,24 +1478,34 @@ void mdn_session::finish() {
                         u64 f = gl::mul(shift_inv, gl::pow(wj_inv, t));
                         auto wv = make_w(ln, gl::e2_mulf(z, f), gl::e2_mulf(z_next, f));
                         keep.emplace_back(); keep.back().alloc((size_t)2 * n_chunks * 4, stream);
-                        mk::launch_ood_dot(cm.coef + (size_t)t * cstep * Nm, (size_t)B * Nm, 2, ln, wv.first, wv.second, keep.back().p, n_chunks, stream);
-                        mk::launch_ood_reduce(keep.back().p, 2, n_chunks, d_out.p + (col_off + 2 * t) * 4, stream);
+                        mk::launch_ood_dot(cm.coef + (size_t)t * cstep * Nm + s0, (size_t)B * Nm, 2, ls, wv.first, wv.second, keep.back().p, n_chunks, stream);
+                        mk::launch_ood_reduce(keep.back().p, 2, n_chunks, d_out + (col_off + 2 * t) * 4, stream);
                     }
                 }
-                scale.emplace_back(col_off * 4, gl::inv((u64)Nm));   // launch_intt leaves coefficients scaled by N
+                scale.push_back(Scale{col_off * 4, gl::inv((u64)Nm), sl});   // launch_intt leaves coefficients scaled by N
                 col_off += cm.width;
             }
         }
-        std::vector<u64> host(total_cols * 4);
-        CUDA_OK(cudaMemcpyAsync(host.data(), d_out.p, host.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        prof.end(ood_region);
+        if (G > 1) {
+            shard_barrier();                                   // d_all is a fresh allocation on every rank
+            mk::launch_push(d_out, peers_of(d_out), shard_rank, shard_world, T, stream);
+            shard_barrier();
+        }
+        std::vector<u64> host(T * G);
+        CUDA_OK(cudaMemcpyAsync(host.data(), d_all.p, host.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
         size_t si = 0;
         for (int g = 0; g < ng; g++)
             for (size_t m = 0; m < groups[g]->mats.size(); m++) {
                 CommittedMat& cm = groups[g]->mats[m];
                 if (!cm.width) continue;
-                size_t off = scale[si].first; u64 n_inv = scale[si].second; si++;
-                for (size_t q = 0; q < (size_t)cm.width * 4; q++) evals[g][m].v[q] = gl::mul(host[off + q], n_inv);
+                const Scale& sc = scale[si++];
+                for (size_t q = 0; q < (size_t)cm.width * 4; q++) {
+                    u64 v = host[(size_t)me * T + sc.off + q];
+                    if (sc.sliced) { v = 0; for (u32 r = 0; r < G; r++) v = gl::add(v, host[(size_t)r * T + sc.off + q]); }
+                    evals[g][m].v[q] = gl::mul(v, sc.n_inv);
+                }
             }
     }
     // aligned flat evaluation lists per point (deep/prover.rs:150-154)
