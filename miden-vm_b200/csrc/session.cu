@@ -388,6 +388,7 @@ void mdn_session::shard_map_slab(char* base, size_t size) {
         v.base[g] = (char*)m;
     }
     slab_views.push_back(v);
+    { std::vector<u64> one(1, 0), got(shard_world); if (allgather(allgather_ctx, one.data(), got.data(), 1) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed"); }   // every rank has mapped it
 }
 // Collective: nobody frees a slab a peer still has mapped.
 void mdn_session::shard_unmap_slabs() {
@@ -517,7 +518,15 @@ void mdn_session::lde_matrix(CommittedMat& m) {
     PremulPlan& pm = premul_trace(m.log_n);
     ProfScope ps(prof, PC_NTT);
     ntt_bytes += (double)(N + (size_t)nt() * N) * m.width * 8.0;   // read the trace column once, write this rank's cosets of the LDE once
-    mk::launch_intt(m.coef, N, m.width, plan.T, stream);
+    if (sharded() && m.log_n >= shard_log_g + shard_min_log) {
+        // interpolation split by column: rank g transforms columns [g*w/G, (g+1)*w/G) and stores the coefficients into
+        // every rank (the all-gather of coefficient columns of SURVEY 8(e), as peer stores)
+        u32 c0 = (u32)((u64)m.width * shard_rank / shard_world), c1 = (u32)((u64)m.width * (shard_rank + 1) / shard_world);
+        if (c1 > c0) mk::launch_intt(m.coef + (size_t)c0 * N, N, c1 - c0, plan.T, stream);
+        shard_barrier();     // every rank is done with the raw columns (transposes, the copy kept for the LogUp build)
+        if (c1 > c0) mk::launch_push(m.coef + (size_t)c0 * N, peers_of(m.coef + (size_t)c0 * N), shard_rank, shard_world, (size_t)(c1 - c0) * N, stream);
+        shard_barrier();
+    } else mk::launch_intt(m.coef, N, m.width, plan.T, stream);
     // this rank's cosets only (all B of them on one GPU); column groups sized so a group's LDE (the fwd passes'
     // working set) stays L2-resident
     const u32 tb = t0(), tn = nt();
@@ -2090,6 +2099,8 @@ int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_all
             s->sync_flags.p[g] = (u64*)m;
         }
         s->sync_epoch = 0;
+        // rendezvous: no rank may go on (and possibly fail and free its buffer) before every rank has mapped it
+        { std::vector<u64> one(1, 0), got(world); if (fn(ctx, one.data(), got.data(), 1) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed"); }
     } catch (const MdnError& e) { s->error = e.what(); return e.code; }
     catch (const std::exception& e) { s->error = e.what(); return MDN_ERR_INVALID_ARG; }
     return MDN_OK;

@@ -408,6 +408,62 @@ def test_full_size_2_20_verifies():
     s.close()
 
 
+def _bit_exact_vs_oracle_prover(s, params, wl, prep_commitment=None):
+    """Full streams + the stage values that are recorded without the debug copies (roots, OOD point, FRI roots, query
+    indices) against the ORACLE PROVER on the same inputs."""
+    ch = W.initial_challenger(params, prod_observe)
+    heights, fields, comms = s.prove(wl.statement, wl.matrices, ch)
+    h, oh, of, oc = H.oracle_prove(params, wl, ch)
+    try:
+        for what, name in ((0, "main_root"), (1, "aux_root"), (2, "quotient_root"), (3, "ood_point"), (6, "fri_roots"), (7, "query_indices")):
+            assert np.array_equal(s.info(what), H.oracle_info(h, what)), f"stage {name} differs"
+        assert heights == oh
+        assert np.array_equal(comms, oc), "commitment stream differs"
+        assert np.array_equal(fields, of), "field stream differs"
+    finally:
+        ob.lib().orc_prove_free(h)
+    return heights, fields, comms
+
+
+def test_full_size_2_20_bit_exact_vs_oracle_prover():
+    """The metric's own configuration -- synthetic 2^20 x (51,22,16), 96-bit parameters -- bit for bit against the oracle
+    PROVER (not only its verifier): every root, the OOD point, the FRI roots, the query indices and the complete
+    `fields` / `commitments` streams.  The oracle needs tens of seconds on the GPU box's host cores."""
+    ob.lib().orc_set_threads(0)
+    params = W.miden_pcs_params()
+    s = B.Session(params, 0)
+    try:
+        _bit_exact_vs_oracle_prover(s, params, W.Workload([20, 20, 20]))
+    finally:
+        s.close()
+
+
+def test_config5_width_mixed_heights_preprocessed_2_20_bit_exact():
+    """BASELINE config 5's features at Miden widths: 51 + 3 + 22 main columns (aux 4 / 0 / 3 EF columns) on mixed heights
+    2^20 / 2^18 / 2^19, the 2^18 AIR with preprocessed columns (a tree shorter than the max LDE, virtually lifted),
+    production parameters with full FRI -- bit-exact against the oracle prover."""
+    import test_airs
+    ob.lib().orc_set_threads(0)
+    params = W.miden_pcs_params()
+    lhs = (20, 18, 19)
+    prep_prog = test_airs.preprocessed_workload((6,), (True,)).programs[0]
+    t1 = W.synthetic_trace(71, lhs[1], 3)
+    pm = W.synthetic_trace(72, lhs[1], 2)
+    t1[:, 0] = _mulmod(pm[:, 0], t1[:, 1])
+    t1[:, 2] = _addmod(np.roll(pm[:, 1], -1), t1[:, 1])
+    traces = [W.synthetic_trace(70, lhs[0], 51), t1, W.synthetic_trace(73, lhs[2], 22)]
+    wl = W.Workload(list(lhs), widths=[51, 3, 22], aux_widths=[4, 0, 3], traces=traces,
+                    programs=[pkg.air_program.dummy_miden_air(), prep_prog, pkg.air_program.dummy_miden_air()],
+                    log_quotient_degrees=[3, 1, 3], num_aux_values=[4, 0, 3], preprocessed=[None, pm, None])
+    s = B.Session(params, 0)
+    try:
+        commitment = s.set_preprocessed(wl.statement, wl.preprocessed_matrices)
+        _bit_exact_vs_oracle_prover(s, params, wl)
+        assert np.array_equal(commitment, wl.oracle_prep_commitment)
+    finally:
+        s.close()
+
+
 def test_config5_shape_2_22_with_preprocessed_verifies():
     """BASELINE config 5 shape (tallest trace 2^22, mixed heights, a preprocessed tree, full FRI with the
     production parameters): the proof must be accepted by the oracle verifier.  Narrower than the Miden widths so
