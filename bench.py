@@ -114,6 +114,7 @@ def cpu_baseline(log_height, steps=1, warmup=0, budget_s=None):
     the number actually timed is returned and reported."""
     n_thr = host_threads()
     os.environ["OMP_NUM_THREADS"] = str(n_thr)      # before libgomp initialises
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # the GPU hosts are shared: spinning at barriers collapses when a neighbour takes cores
     os.environ.pop("OMP_THREAD_LIMIT", None)
     import helpers as H
     import oracle_binding as ob
