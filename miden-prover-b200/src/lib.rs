@@ -245,11 +245,9 @@ impl<'s> GpuStarkProver<'s> {
         // (d) host callbacks: build_aux_trace for AIRs without a lowered lookup; eval_external for the statement
         let mut ctx = CallbackCtx { statement };
         let ctx_ptr = &mut ctx as *mut CallbackCtx<'_, MA> as *mut c_void;
-        let all_on_device = self.lookups.iter().all(Option::is_some);
-        let aux_cb: MdnAuxBuilder = if all_on_device { None } else { Some(aux_trampoline::<MA>) };
-        // NB: a NULL builder means all-zero aux traces (testing/airs/miden.rs:84-94); with every aux trace built on the
-        // device the callback is never invoked, but it must be non-NULL unless every AIR ships a lookup program.
-        let aux_cb = if all_on_device && self.lookups.is_empty() { None } else { aux_cb.or(Some(aux_trampoline::<MA>)) };
+        // (a NULL builder would mean all-zero aux traces, testing/airs/miden.rs:84-94; the callback is simply never
+        //  invoked for an AIR that ships a lookup program)
+        let aux_cb: MdnAuxBuilder = Some(aux_trampoline::<MA>);
         unsafe { mdn_session_set_external_check(self.session.raw, Some(external_trampoline::<MA>), ctx_ptr) };
 
         let mut proof = core::mem::MaybeUninit::<MdnProof>::uninit();
