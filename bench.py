@@ -315,9 +315,9 @@ def main():
         if os.path.exists(tf):
             tj = json.load(open(tf))
             traffic = tj.get("dram_bytes_per_launch")
-            traffic_note = (f"ncu --set full capture of the main-tree launch: {traffic / 1e9:.2f} GB DRAM for "
-                            f"{tj.get('algorithmic_bytes_per_launch', 0) / 1e9:.2f} GB algorithmic; `achieved` averages the three leaf-sponge launches of a proof; "
-                            "the capture is of the first-generation kernel (r1i), the second generation reads the same cells once in the same order")
+            traffic_note = (f"ncu --set full capture of the main-tree launch of the shipped kernel ({tj.get('capture', 'profiles/')}): {traffic / 1e9:.2f} GB DRAM for "
+                            f"{tj.get('algorithmic_bytes_per_launch', 0) / 1e9:.2f} GB algorithmic; `achieved` averages the three leaf-sponge launches of a proof (main, aux, quotient tree); "
+                            f"binding unit = FMA-heavy pipe at {tj.get('pipe_fmaheavy_pct', 0):.1f} % busy (ALU pipe {tj.get('pipe_alu_pct', 0):.1f} %, issue slots {tj.get('issue_active_pct', 0):.1f} %)")
         # The leaf sponge is bound by instruction issue on the two integer pipes, not by HBM: next to the HBM
         # fraction the contract asks for, report thread-instructions/s against what the SMs can issue
         # (148 SMs x 4 schedulers x 32 lanes x 1 instruction/clock at the sampled SM clock).
@@ -329,8 +329,9 @@ def main():
         except Exception:
             pass                                 # a library from before MDN_INFO_BUILD: first generation
         try:
-            instr_per_perm = {1: (15960, "ncu inst_executed of the r1i capture (profiles/leaf_sponge_traffic.json)"),
-                              2: (14180, "static SASS count of p2f::permute, poseidon2_fast2.cuh: 3272 IMAD.WIDE + 3123 other IMAD + 7486 ALU-pipe + 301 other (no ncu capture of this build yet)")}[build[0]]
+            ipp2 = (tj.get("thread_instructions_per_permutation") if os.path.exists(tf) else None) or 13673
+            instr_per_perm = {1: (15960, "ncu inst_executed of the first-generation kernel (round-1 capture r1i)"),
+                              2: (round(ipp2), "ncu smsp__inst_executed x 32 / permutations of the k_leaf_hash capture of the shipped second-generation kernel (profiles/leaf_sponge_traffic.json, profiles/r2b_kernels.json)")}[build[0]]
             clk = sampler.summary()
             sm_mhz = clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965
             perms_per_s = tim_v.permutations / ((km[2] + km[3]) * 1e-3) if km[2] + km[3] > 0 else None
