@@ -19,10 +19,15 @@ typedef unsigned int u32;
 static constexpr u64 P = 0xFFFFFFFF00000001ULL;
 static constexpr u64 EPS = 0xFFFFFFFFULL;  // 2^64 mod p = 2^32 - 1
 
+#if !defined(MDN_GL_SLOW) && !defined(MDN_GL_FAST)
+#define MDN_GL_FAST 1
+#endif
 #ifdef MDN_GL_FAST
-// Tuning knob (inert by default): add / sub / mul of the kernels that use gl:: directly (constraint interpreter, LogUp
-// rows, DEEP tail, OOD, FRI fold) on the carry flag and one 128-bit product, like poseidon2_fast2.cuh; same contracts
-// (canonical operands for add / sub, canonical results everywhere), same PTX templates, unsigned __int128 on the host.
+// add / sub / mul of the kernels that use gl:: directly (constraint interpreter, LogUp rows, DEEP tail, OOD, FRI fold) on
+// the carry flag and one 128-bit product, like poseidon2_fast2.cuh; same contracts (canonical operands for add / sub,
+// canonical results everywhere), same PTX templates, unsigned __int128 on the host.  The default since r2 (B200, 2^20
+// proof: constraints 1.56 -> 1.27 ms, OOD 2.40 -> 1.93, DEEP 4.30 -> 3.51, FRI 6.40 -> 6.27, identical proof bytes:
+// profiles/r2_tuning.md); -DMDN_GL_SLOW restores the branchy forms (the first-generation A/B library uses them).
 GL_HD void fast_subb64(u64 a, u64 b, u64& r, unsigned& m) {
 #ifdef __CUDA_ARCH__
     asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(r), "=r"(m) : "l"(a), "l"(b));

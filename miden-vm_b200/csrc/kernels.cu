@@ -371,13 +371,8 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
 }
 
 #else   // MDN_NTT_V2: block functions of ntt2.cuh (host-checked by tests/cpp/test_ntt_v2.cpp) ------------------------
-// Tuning knob for tools/tune_hash.py: -DNTT_MIN_BLOCKS=k asks for k resident blocks of the NTT kernels (unset: ptxas
-// chooses, 48-74 registers -- the configuration of every measurement so far).
-#ifdef NTT_MIN_BLOCKS
-#define NTT_BOUNDS __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
-#else
+// ptxas chooses the register count (48-64); forcing 2 or 3 resident blocks was measured and loses 5 % (profiles/r2_tuning.md)
 #define NTT_BOUNDS __launch_bounds__(NTT_THREADS)
-#endif
 __global__ void NTT_BOUNDS k_intt_strided(u64* cols, size_t col_stride, NttTables T, u32 log_c) {
     extern __shared__ u64 sm[];
     ntt2::intt_strided_block(blockIdx.x, blockIdx.y, sm, cols, col_stride, T, log_c);
@@ -427,10 +422,7 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
 // =============================================================================================
 // Poseidon2 hashing
 // =============================================================================================
-#ifndef HASH_THREADS_N
-#define HASH_THREADS_N 128      // tuning knob (tools/tune_hash.py)
-#endif
-static constexpr int HASH_THREADS = HASH_THREADS_N;
+static constexpr int HASH_THREADS = 128;     // 64 and 256 threads per block measure the same or worse (profiles/r2_tuning.md)
 // Minimum resident blocks the compiler must allow (tools/tune_hash.py sweep on the B200, leaf sponge / compress ms per
 // 2^20 proof: 1..3 -> 142 registers 95.6 / 17.8, 4 -> 126: 94.0 / 17.5, 5 -> 96: 92.5 / 17.4, 6 -> 80: 91.7 / 17.2, 7 -> 72: 91.6 / 17.4, 8 -> 64: 91.5 / 17.3; 1..7 do not spill).
 // The kernels are bound by the two integer pipes and more warps per scheduler interleave their FMA and ALU bursts.

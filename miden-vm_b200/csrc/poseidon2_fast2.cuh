@@ -49,9 +49,7 @@ GL_HD void subb64(u64 a, u64 b, u64& r, u32& m) {
 // a * (2^32 - 1) as a 64-bit product.  The explicit mul.wide keeps ptxas fusing it with the following add.cc
 // into one IMAD.WIDE.U32 with carry-out (a plain C product of a limb of the 128-bit multiply does not fuse).
 GL_HD u64 mul_eps(u32 a) {
-#ifdef P2_EPS_ALU           // tuning switch: (a << 32) - a on the ALU pipe instead of an IMAD.WIDE on the FMA pipe
-    return ((u64)a << 32) - (u64)a;
-#elif defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__)   // ((a << 32) - a on the ALU pipe was measured twice and loses: leaf sponge 90.3 -> 98.7 ms, profiles/r2_tuning.md)
     u64 m;
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(m) : "r"(a), "r"(0xFFFFFFFFu));
     return m;
@@ -59,12 +57,15 @@ GL_HD u64 mul_eps(u32 a) {
     return (u64)a * 0xFFFFFFFFull;
 #endif
 }
-// c * (2^32 - 1) + r for c in {0, 1}: one IMAD.WIDE.U32.  Callers guarantee no overflow.
+// c * (2^32 - 1) + r for c in {0, 1}.  Callers guarantee no overflow.  Added as the mask 0 / 2^32 - 1 on the ALU pipe:
+// the hash kernels are bound by the FMA-heavy pipe (ncu r2b: 77.7 % busy against 63.3 % for the ALU pipe), where the
+// IMAD.WIDE form of this fold costs four cycles per warp (B200, 2^20 proof: leaf sponge 90.3 -> 89.0 ms, identical proof
+// bytes; profiles/r2_tuning.md).  -DP2_FOLD_IMAD restores the one-instruction IMAD.WIDE.U32 form.
 GL_HD u64 fold(u32 c, u64 r) {
-#ifdef P2_FOLD_ALU          // tuning switch: add the mask 0 / 2^32 - 1 on the ALU pipe instead of an IMAD.WIDE
-    return r + (u64)(0u - c);
-#else
+#ifdef P2_FOLD_IMAD
     return (u64)c * EPS + r;
+#else
+    return r + (u64)(0u - c);
 #endif
 }
 
@@ -248,13 +249,8 @@ GL_HD void internal_layer(u64* s) {
 #define P2F_RC_INTERNAL p2::P2_RC_INTERNAL
 #endif
 
-// Tuning knob: unroll factor of the 22 internal rounds (1 keeps the kernel at ~26 KB of code; the first generation's
-// fully unrolled 93 KB stalled on instruction fetch).
-#ifndef P2_INT_UNROLL
-#define P2_INT_UNROLL 1
-#endif
-#define P2_PRAGMA_(x) _Pragma(#x)
-#define P2_UNROLL(n) P2_PRAGMA_(unroll n)
+// The 22 internal rounds stay a rolled loop (~26 KB of code; the first generation's fully unrolled 93 KB stalled on
+// instruction fetch, and unrolling by two moved the leaf sponge by 0.15 % on the B200, profiles/r2_tuning.md).
 // Output words are arbitrary representatives; canonicalise with glf::canon before storing.
 GL_HD void permute(u64* s) {
     external_layer(s);
@@ -268,7 +264,7 @@ GL_HD void permute(u64* s) {
             external_layer(s);
         }
         if (phase == 0) {
-P2_UNROLL(P2_INT_UNROLL)
+#pragma unroll 1
             for (int r = 0; r < 22; r++) {
                 s[0] = sbox(glf::add_const(s[0], P2F_RC_INTERNAL[r]));
                 internal_layer(s);

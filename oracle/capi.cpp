@@ -174,7 +174,7 @@ void orc_coset_lde_batch(const orc_matrix* mat, uint32_t added_bits, uint64_t sh
 void orc_lmcs_commit(const orc_matrix* mats, uint32_t n, uint64_t root[4], uint64_t* layers_out) {
     std::vector<Matrix> ms;
     for (uint32_t i = 0; i < n; i++) { Matrix m = to_matrix(mats[i]); bit_reverse_rows(m); ms.push_back(std::move(m)); }
-    LmcsTree t = LmcsTree::build(std::move(ms), 8);
+    LmcsTree t = LmcsTree::build(std::move(ms), lmcs_alignment());
     for (int i = 0; i < 4; i++) root[i] = t.root()[i].v;
     if (layers_out) {
         size_t o = 0;
@@ -234,7 +234,20 @@ static Statement to_statement(const orc_statement* st) {
     for (uint32_t i = 0; i < st->n_observe_felts; i++) s.observe_felts.push_back(Fp(st->observe_felts[i]));
     return s;
 }
+// STARK hash configuration of every later call (0 = Poseidon2, the default; 1 = Blake3_256) and, for Blake3, the
+// pre-bound challenger = the bytes its HashChallenger input buffer holds after `config.challenger()` +
+// `observe_protocol_params` (air/src/config.rs:299-307,188-198); the `orc_challenger*` argument is then ignored.
+static std::vector<uint8_t> g_hash_challenger_input;
+int orc_set_hash(int kind, const uint8_t* challenger_input, size_t n) {
+    if (kind != 0 && kind != 1) return -1;
+    hash_kind() = kind ? H_BLAKE3 : H_POSEIDON2;
+    g_hash_challenger_input.assign(challenger_input, challenger_input + (challenger_input ? n : 0));
+    return 0;
+}
+void orc_blake3(const uint8_t* p, size_t n, uint8_t out[32]) { auto h = blake3::hash(p, n); memcpy(out, h.data(), 32); }
+
 static Challenger to_challenger(const orc_challenger* c) {
+    if (hash_kind() == H_BLAKE3) return Challenger::from_bytes(g_hash_challenger_input.data(), g_hash_challenger_input.size());
     Challenger ch;
     for (int i = 0; i < 12; i++) ch.st[i] = Fp(c->sponge_state[i]);
     for (uint32_t i = 0; i < c->input_len; i++) ch.in_buf[i] = Fp(c->input_buffer[i]);

@@ -45,7 +45,7 @@ struct LmcsTree {
                     for (size_t k = 0; k < f; k++) states[i * f + k] = states[i];
             }
 #if ORC_HAVE_X8
-            if (h >= 8 && x8_available()) {   // 8 leaves per AVX-512 permutation
+            if (h >= 8 && x8_available() && hash_kind() == H_POSEIDON2) {   // 8 leaves per AVX-512 permutation
 #pragma omp parallel for schedule(static) if (h > 256)
                 for (size_t r8 = 0; r8 < h / 8; r8++) sponge_absorb_x8(&states[8 * r8], m.row(8 * r8), m.width, m.width);
             } else
@@ -65,7 +65,7 @@ struct LmcsTree {
             const std::vector<Digest>& prev = t.layers[d + 1];
             std::vector<Digest> next(prev.size() / 2);
 #if ORC_HAVE_X8
-            if (next.size() >= 8 && x8_available()) {
+            if (next.size() >= 8 && x8_available() && hash_kind() == H_POSEIDON2) {
 #pragma omp parallel for schedule(static) if (next.size() > 256)
                 for (size_t i8 = 0; i8 < next.size() / 8; i8++) compress2_x8(&prev[16 * i8], &next[8 * i8]);
             } else

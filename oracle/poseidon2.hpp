@@ -6,7 +6,9 @@
 // Pinned by the known-answer test poseidon2/test.rs:7-39 (tests/test_oracle_kat.py).
 #pragma once
 #include "field.hpp"
+#include "blake3.hpp"
 #include <array>
+#include <vector>
 
 namespace orc {
 
@@ -57,6 +59,31 @@ inline void poseidon2_permute(State& s) {
 
 using Digest = std::array<Fp, 4>;
 
+// Which of the reference's STARK hash configurations the LMCS and the challenger follow (air/src/config.rs):
+//   H_POSEIDON2: StatefulSponge<Poseidon2, 12, 8, 4> leaves (alignment 8), TruncatedPermutation nodes, DuplexChallenger
+//                (:204-223, 255-273) -- the default;
+//   H_BLAKE3   : ChainingHasher<Blake3> leaves (alignment 1: state <- blake3(state || little-endian u64 of every felt of
+//                the row), crates/stateful-hasher/src/chaining.rs:31-52,161-169), blake3(left || right) nodes
+//                (CompressionFunctionFromHasher<Blake3, 2, 32>), SerializingChallenger64<HashChallenger<u8, Blake3, 32>>
+//                (:276-307).  A 32-byte digest travels as four raw little-endian u64 in a `Digest`.
+// One process-wide switch: the oracle is test infrastructure with a single client at a time.
+enum HashKind { H_POSEIDON2 = 0, H_BLAKE3 = 1 };
+inline HashKind& hash_kind() { static HashKind k = H_POSEIDON2; return k; }
+inline size_t lmcs_alignment() { return hash_kind() == H_BLAKE3 ? 1 : 8; }
+
+inline void digest_to_bytes(const Fp* d, uint8_t* out) { for (int i = 0; i < 4; i++) for (int k = 0; k < 8; k++) out[8 * i + k] = (uint8_t)(d[i].v >> (8 * k)); }
+inline void bytes_to_digest(const uint8_t* b, Fp* d) {
+    for (int i = 0; i < 4; i++) { u64 v = 0; for (int k = 0; k < 8; k++) v |= (u64)b[8 * i + k] << (8 * k); d[i] = Fp::raw(v); }
+}
+// ChainingHasher::absorb_into: state <- H(state || into_byte_stream(row)); an empty row still re-hashes the state
+inline void chaining_absorb_blake3(Fp* st4, const Fp* in, size_t n) {
+    std::vector<uint8_t> buf(32 + 8 * n);
+    digest_to_bytes(st4, buf.data());
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < 8; k++) buf[32 + 8 * i + k] = (uint8_t)(in[i].v >> (8 * k));   // canonical u64, little-endian
+    auto h = blake3::hash(buf);
+    bytes_to_digest(h.data(), st4);
+}
+
 // Overwrite-mode sponge absorb (crates/stateful-hasher/src/field_sponge.rs:41-59), generic in the element type, the
 // width/rate and the permutation like the reference's `StatefulSponge<P, WIDTH, RATE, OUT>`: each full chunk of RATE
 // overwrites state[0..RATE] then permutes; a trailing partial chunk is zero-filled to the rate boundary and permuted;
@@ -79,6 +106,7 @@ inline void sponge_absorb_generic(std::array<T, WIDTH>& st, const T* in, size_t 
     }
 }
 inline void sponge_absorb(State& st, const Fp* in, size_t n) {
+    if (hash_kind() == H_BLAKE3) { chaining_absorb_blake3(st.data(), in, n); return; }
     sponge_absorb_generic<Fp, 12, 8>(st, in, n, [](State& s) { poseidon2_permute(s); });
 }
 inline Digest sponge_squeeze(const State& st) { return Digest{st[0], st[1], st[2], st[3]}; }
@@ -86,6 +114,13 @@ inline Digest sponge_squeeze(const State& st) { return Digest{st[0], st[1], st[2
 // 2-to-1 compression = p3 TruncatedPermutation<_, 2, 4, 12>: perm([l | r | 0000])[0..4]
 // (air/src/config.rs:217; equality with Poseidon2::merge shown by poseidon2/test.rs:208-230).
 inline Digest compress2(const Digest& l, const Digest& r) {
+    if (hash_kind() == H_BLAKE3) {
+        uint8_t buf[64];
+        digest_to_bytes(l.data(), buf); digest_to_bytes(r.data(), buf + 32);
+        auto h = blake3::hash(buf, 64);
+        Digest d; bytes_to_digest(h.data(), d.data());
+        return d;
+    }
     State s;
     for (int i = 0; i < 4; i++) { s[i] = l[i]; s[4 + i] = r[i]; s[8 + i] = Fp(); }
     poseidon2_permute(s);

@@ -126,7 +126,7 @@ inline LmcsTree commit_traces(const std::vector<Matrix>& traces_proof_order, uns
         ldes.push_back(coset_lde_bitrev(t, log_blowup, lde_shift(lh + log_blowup)));
     }
     ORC_TIMER("  lmcs build");
-    return LmcsTree::build(std::move(ldes), 8);   // build_aligned_tree: alignment = RATE
+    return LmcsTree::build(std::move(ldes), lmcs_alignment());   // build_aligned_tree: alignment = RATE (8) for the sponge, 1 for the chaining hasher
 }
 
 // Preprocessed::build (preprocessed.rs:41-110): AIRs with preprocessed columns sorted by (height, air index),
@@ -318,7 +318,7 @@ inline void pcs_open(const PcsParams& params, unsigned log_max_n, Ef z, Ef z_nex
         for (size_t m = 0; m < trees[g]->leaves.size(); m++) {
             const Matrix& cm = coeffs[g][m];
             unsigned lr = log_max_n - log2_strict(cm.height);
-            size_t w = cm.width, aw = aligned_len(w, 8);
+            size_t w = cm.width, aw = aligned_len(w, lmcs_alignment());
             widths.push_back(w); aligned_widths.push_back(aw);
             for (int p = 0; p < 2; p++) {
                 Ef x = ef_exp_pow2(pts[p], lr);
@@ -572,7 +572,7 @@ inline Proof stark_prove(const PcsParams& params, const Statement& st, const std
     // 5. quotient commit
     Matrix qlde = [&] { ORC_TIMER("quotient lde"); return quotient_chunk_lde(acc, log_max_n, log_qd, lb); }();
     std::vector<Matrix> ql; ql.push_back(qlde);
-    LmcsTree q_tree = [&] { ORC_TIMER("quotient tree"); return LmcsTree::build(std::move(ql), 8); }();
+    LmcsTree q_tree = [&] { ORC_TIMER("quotient tree"); return LmcsTree::build(std::move(ql), lmcs_alignment()); }();
     ch.send_commitment(q_tree.root());
     // 6. OOD point (domain.rs:539-552)
     unsigned log_lde = log_max_n + lb;
@@ -689,7 +689,7 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
         groups.insert(groups.begin(), pg);
     }
     const size_t gm = has_prep ? 1 : 0;   // index of the main group
-    for (auto& g : groups) for (size_t w : g.widths) g.aligned.push_back(aligned_len(w, 8));
+    for (auto& g : groups) for (size_t w : g.widths) g.aligned.push_back(aligned_len(w, lmcs_alignment()));
 
     // --- DEEP oracle (pcs/deep/verifier.rs): read evals, grind, alpha/beta, reduced openings
     size_t W = 0;
@@ -779,7 +779,7 @@ inline void stark_verify(const PcsParams& params, const Statement& st, const Pro
             al.push_back(evals[0][aoff + 2 * c] + u * evals[0][aoff + 2 * c + 1]);
             an.push_back(evals[1][aoff + 2 * c] + u * evals[1][aoff + 2 * c + 1]);
         }
-        moff += aligned_len(air.width, 8); aoff += aligned_len(2 * air.aux_width, 8);
+        moff += aligned_len(air.width, lmcs_alignment()); aoff += aligned_len(2 * air.aux_width, lmcs_alignment());
         // selectors_at (domain.rs:518-530) at the lifted point
         Ef zl = ef_exp_pow2(z, log_max_n - ln);
         Ef van = ef_exp_pow2(zl, ln) - Fp::raw(1);

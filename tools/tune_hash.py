@@ -6,11 +6,11 @@ tools/ab_check.py on each (KAT, bit-exact small proofs, 2^20 proof verified by t
     python tools/tune_hash.py build [name=flags ...]     # here (nvcc cross-compiles); libraries go to tools/_tune/
     python tools/tune_hash.py run                        # on the GPU box: one line per variant + gpurun_out/tune_*.json
 
-Knobs (all inert by default): -DHASH_MIN_BLOCKS=k (default 6: 80 registers), -DHASH_THREADS_N=n (128), -DP2_INT_UNROLL=u (1),
--DP2_LINEAR_FOLD_IMAD, -DP2_FOLD_ALU, -DP2_EPS_ALU, -DNTT_MIN_BLOCKS=k (unset), -DMDN_GEN1 (first generation),
--DMDN_GL_FAST (carry-flag add/sub/mul for the kernels that use gl:: directly: interpreter, LogUp rows, DEEP, OOD; 35 % fewer
-static instructions; logic checked with `make -C tests/emu GEN=-DMDN_GL_FAST` + the emulated parity suite).
-Round-1 results: profiles/r1_summary.md "r1l" (HASH_MIN_BLOCKS 1..8, P2_EPS_ALU, linear-layer folds)."""
+Remaining switches: -DHASH_MIN_BLOCKS=k (default 6: 80 registers), -DP2_LINEAR_FOLD_IMAD, -DP2_FOLD_IMAD (both folds back on the FMA
+pipe), -DMDN_GL_SLOW (branchy gl:: arithmetic), -DMDN_GEN1 (first generation).  Every other knob of round 1 was timed in
+round 2 and removed (profiles/r2_tuning.md): hash block sizes 64/256, NTT resident-block bounds, internal rounds unrolled by
+two and x2*(2^32-1) on the ALU pipe all lost or made no difference; MDN_GL_FAST and the ALU-pipe fold won and are defaults.
+Round-1 results: profiles/r1_summary.md "r1l" (HASH_MIN_BLOCKS 1..8, linear-layer folds)."""
 import json
 import os
 import subprocess
@@ -19,8 +19,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "miden-vm_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_tune")
-DEFAULT = ["base=", "iu2=-DP2_INT_UNROLL=2", "ht256=-DHASH_THREADS_N=256 -DHASH_MIN_BLOCKS=3", "ht64=-DHASH_THREADS_N=64 -DHASH_MIN_BLOCKS=12",
-           "ntt2=-DNTT_MIN_BLOCKS=2", "ntt3=-DNTT_MIN_BLOCKS=3", "ntt4=-DNTT_MIN_BLOCKS=4", "linimad=-DP2_LINEAR_FOLD_IMAD", "glfast=-DMDN_GL_FAST"]
+DEFAULT = ["base=", "foldimad=-DP2_FOLD_IMAD", "linimad=-DP2_LINEAR_FOLD_IMAD", "glslow=-DMDN_GL_SLOW", "mb5=-DHASH_MIN_BLOCKS=5", "mb7=-DHASH_MIN_BLOCKS=7"]
 
 
 def build(specs):
