@@ -93,10 +93,11 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows), "source": "nvml", "poll_ms_max": round(getattr(self, "poll_ms", 0.0), 2)}
 
 
-def workload_name(lh):
+def workload_name(lh, hash_name="poseidon2"):
     """`config.workload` of BOTH arms (the driver compares the two lines' configs)."""
+    h = "Poseidon2 LMCS + duplex challenger" if hash_name == "poseidon2" else "Blake3_256 LMCS (chaining hasher) + hash challenger"
     return (f"synthetic 2^{lh} x (51,22,16) Miden-shaped prove (DummyMidenAir degree-9 constraint, zero aux 4/3/1 EF cols), "
-            "96-bit params: blowup 8, FRI arity 4, final degree 2^7, 27 queries, PoW 4/12/16, Poseidon2 LMCS + duplex challenger")
+            f"96-bit params: blowup 8, FRI arity 4, final degree 2^7, 27 queries, PoW 4/12/16, {h}")
 
 
 def host_threads():
@@ -108,7 +109,7 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(log_height, steps=1, warmup=0, budget_s=None):
+def cpu_baseline(log_height, steps=1, warmup=0, budget_s=None, hash_name="poseidon2"):
     """The oracle (C++ restatement of the reference prover, OpenMP over all host threads) proving the same workload
     shape.  With `budget_s` the number of timed proofs is cut (never below 1) so that the run ends inside the budget;
     the number actually timed is returned and reported."""
@@ -124,6 +125,10 @@ def cpu_baseline(log_height, steps=1, warmup=0, budget_s=None):
     params = W.miden_pcs_params()
     wl = W.Workload([log_height] * 3)
     ch = W.initial_challenger(params, H.oracle_observe)
+    ob.lib().orc_set_hash.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+    if hash_name == "blake3":
+        init = W.initial_hash_challenger(params)
+        ob.lib().orc_set_hash(1, init, len(init))
     times, t_start, timed_target = [], time.perf_counter(), steps
     i = 0
     while len(times) < timed_target:
@@ -140,6 +145,7 @@ def cpu_baseline(log_height, steps=1, warmup=0, budget_s=None):
             if done_w < warmup and left < (warmup - done_w + 1) * dt:
                 warmup = done_w                       # no time for more warm-up proofs
             timed_target = max(1, min(timed_target, len(times) + int(left // dt)))
+    ob.lib().orc_set_hash(0, None, 0)
     mean = sum(times) / len(times)
     return {"value": wl.cells / mean, "unit": UNIT, "cores": n_thr, "kind": "port",
             "sample": f"synthetic 2^{log_height} x (51,22,16), full prove, {len(times)} timed run(s) after {warmup} warm-up, {mean:.2f} s each, "
@@ -154,12 +160,12 @@ def run_reference(args, rank):
         return
     lh = args.ref_log_height if args.ref_log_height else args.log_height
     budget = float(os.environ.get("MDN_REF_BUDGET_S", "660"))     # the driver's per-N limit was 870 s in round 1
-    cb, mean, cells, timed, warm = cpu_baseline(lh, steps=args.steps, warmup=min(args.warmup, 1), budget_s=budget)
+    cb, mean, cells, timed, warm = cpu_baseline(lh, steps=args.steps, warmup=min(args.warmup, 1), budget_s=budget, hash_name=args.hash)
     line = {
         "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": timed, "warmup": warm,
         "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": workload_name(lh), "cells_per_proof": cells, "proofs_per_step": 1},
+        "config": {"workload": workload_name(lh, args.hash), "cells_per_proof": cells, "proofs_per_step": 1},
         "note": ("reference is Rust + un-vendored Plonky3 and cannot be built here; this arm times the C++ oracle port (oracle/) on the host cores, "
                  f"full 2^{lh} proofs; steps requested {args.steps}, timed {timed} inside a {budget:.0f} s budget; one warm-up proof (a CPU prover has no cold start beyond page faults)"),
         "cpu_baseline": cb,
@@ -179,6 +185,8 @@ def main():
     ap.add_argument("--ref-log-height", type=int, default=0, help="CPU arm: 0 = the same height as --log-height")
     ap.add_argument("--cpu-log-height", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hash", choices=["poseidon2", "blake3"], default="poseidon2",
+                    help="STARK hash configuration: poseidon2 (the metric's; default) or blake3 (the CLI default hasher / blake3-bench, BASELINE config 3)")
     ap.add_argument("--sharding", choices=["coset", "proof"], default="coset",
                     help="N>1: 'coset' (default) = ONE proof split over the GPUs -- LDE cosets, leaf sponge, constraints, DEEP and FRI "
                          "folds per coset, Merkle sub-trees per leaf range, peer-memory stores over NVLink (strong scaling); "
@@ -228,6 +236,9 @@ def main():
         lib.mdn_challenger_observe(C.byref(c), B.ptr(np.ascontiguousarray(felts, dtype=np.uint64)), len(felts))
 
     ch = W.initial_challenger(params, observe)
+    if args.hash == "blake3":
+        sess.set_hash(B.HASH_BLAKE3, W.initial_hash_challenger(params))
+        ch = None
 
     # device-resident copies (for `value`) and pinned host copies (for `e2e`)
     dev_t = [torch.from_numpy(t.view(np.int64)).cuda() for t in wl.traces]
@@ -287,6 +298,8 @@ def main():
             return hashlib.sha256(bytes(pf[0]) + np.ascontiguousarray(pf[1], dtype=np.uint64).tobytes()
                                   + np.ascontiguousarray(pf[2], dtype=np.uint64).tobytes()).digest()
         single = B.Session(params, local_rank)
+        if args.hash == "blake3":
+            single.set_hash(B.HASH_BLAKE3, W.initial_hash_challenger(params))
         ref = single.prove(wl.statement, dev_m, ch, None, B.FLAG_DEVICE_TRACES)
         single.close()
         mine = [digest(proof), digest(proof_e), digest(ref)]
@@ -346,7 +359,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_v / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if hash_sharded else "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(lh),
+            "config": {"workload": workload_name(lh, args.hash),
                        "cells_per_proof": cells, "proofs_per_step": proofs_per_step,
                        "sharding": ("ONE proof split over the GPUs: LDE cosets / leaf sponge / constraints / DEEP / FRI folds per coset, Merkle sub-trees per leaf range, "
                                     "peer-memory stores + device barrier over NVLink (no library collective on the data path)" if hash_sharded else "one independent proof per GPU") if world > 1 else "single GPU",
@@ -378,12 +391,19 @@ def main():
         if world == 1:
             # checker leg (oracle as verifier, outside every timed region): the last e2e proof must verify
             import helpers as H
-            rc, err = H.oracle_verify(params, wl, ch, *proof_e)
+            if args.hash == "blake3":
+                import oracle_binding as ob
+                ob.lib().orc_set_hash.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+                init = W.initial_hash_challenger(params)
+                ob.lib().orc_set_hash(1, init, len(init))
+            rc, err = H.oracle_verify(params, wl, ch if ch is not None else W.Challenger(), *proof_e)
+            if args.hash == "blake3":
+                ob.lib().orc_set_hash(0, None, 0)
             line["proof_verified_by_oracle"] = (rc == 0)
             if rc != 0:
                 line["verify_error"] = err
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(args.cpu_log_height)[0]
+            cb = cpu_baseline(args.cpu_log_height, hash_name=args.hash)[0]
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:

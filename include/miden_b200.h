@@ -202,6 +202,29 @@ typedef int (*mdn_external_check)(void* ctx, const uint64_t* challenges, uint32_
                                   const uint8_t* log_trace_heights, uint32_t n_airs, uint32_t* failed_assertion);
 int mdn_session_set_external_check(mdn_session* s, mdn_external_check fn, void* ctx);
 
+/* ---- STARK hash configuration (miden_air::config, air/src/config.rs) ----------------------------------------
+ * MDN_HASH_POSEIDON2 (default): `poseidon2_config` (:241-273) -- StatefulSponge<Poseidon2, 12, 8, 4> leaves (alignment 8),
+ *   TruncatedPermutation nodes, DuplexChallenger; the pre-bound challenger is the `mdn_challenger` argument of mdn_prove*.
+ * MDN_HASH_BLAKE3: `blake3_256_config` (:276-307), the CLI's default hasher (miden-vm/src/cli/prove.rs:51) --
+ *   ChainingHasher<Blake3> leaves (state <- blake3(state || little-endian u64 of every felt of the row); alignment 1, so
+ *   opened rows and the OOD evaluation lists carry no zero padding), blake3(left || right) nodes,
+ *   SerializingChallenger64<Felt, HashChallenger<u8, Blake3, 32>>.  Commitments are 32-byte digests carried as four
+ *   little-endian u64 per commitment in `mdn_proof.commitments`.  The pre-bound challenger is the HashChallenger state
+ *   installed with mdn_session_set_hash_challenger (after `config.challenger()` + `observe_protocol_params` that is the
+ *   input buffer: 32 bytes of relation digest + 8 parameter felts as little-endian u64, and an empty output buffer); the
+ *   `challenger` argument of mdn_prove* is ignored and may be NULL.  A preprocessed bundle belongs to the hash it was
+ *   committed under. */
+typedef enum { MDN_HASH_POSEIDON2 = 0, MDN_HASH_BLAKE3 = 1 } mdn_hash_kind;
+int mdn_session_set_hash(mdn_session* s, mdn_hash_kind kind);
+/* p3 `HashChallenger<u8, Blake3, 32>`: `input_buffer`, `output_buffer` (bytes are sampled from its back). */
+typedef struct {
+    const uint8_t* input_buffer;
+    size_t input_len;
+    const uint8_t* output_buffer;
+    size_t output_len;
+} mdn_hash_challenger;
+int mdn_session_set_hash_challenger(mdn_session* s, const mdn_hash_challenger* c);
+
 /* ---- preprocessed columns: Preprocessed::build (crates/lifted-stark/src/preprocessed.rs:63-131) -----
  * `preprocessed[i]` = `BaseAir::preprocessed_trace()` of AIR i (HOST pointer; width 0 where the AIR declares
  * none, otherwise width == airs[i].preprocessed_width).  The declared matrices are sorted by (height, AIR

@@ -36,6 +36,14 @@ class Air(C.Structure):
                 ("preprocessed_width", C.c_uint32), ("lookup", C.POINTER(Lookup))]
 
 
+class HashChallenger(C.Structure):
+    _fields_ = [("input_buffer", C.POINTER(C.c_uint8)), ("input_len", C.c_size_t),
+                ("output_buffer", C.POINTER(C.c_uint8)), ("output_len", C.c_size_t)]
+
+
+HASH_POSEIDON2, HASH_BLAKE3 = 0, 1
+
+
 class Matrix(C.Structure):
     _fields_ = [("values", u64p), ("log_height", C.c_uint32), ("width", C.c_uint32)]
 
@@ -71,7 +79,7 @@ EXPORTS = [
     "mdn_lmcs_commit", "mdn_poseidon2_permute", "mdn_get_info", "mdn_get_timings",
     "mdn_challenger_observe", "mdn_challenger_sample", "mdn_set_debug", "mdn_session_set_shard",
     "mdn_session_set_preprocessed", "mdn_session_set_jit", "mdn_jit_compile_check", "mdn_jit_status", "mdn_abi_layout",
-    "mdn_session_set_external_check",
+    "mdn_session_set_external_check", "mdn_session_set_hash", "mdn_session_set_hash_challenger",
 ]
 
 _lib = None
@@ -122,6 +130,8 @@ def lib():
         L.mdn_get_info.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t]
         L.mdn_set_debug.argtypes = [C.c_void_p, C.c_int]
         L.mdn_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHER, C.c_void_p]
+        L.mdn_session_set_hash.argtypes = [C.c_void_p, C.c_int]
+        L.mdn_session_set_hash_challenger.argtypes = [C.c_void_p, C.POINTER(HashChallenger)]
         L.mdn_session_set_external_check.argtypes = [C.c_void_p, EXTERNAL_CHECK, C.c_void_p]
         L.mdn_session_set_preprocessed.argtypes = [C.c_void_p, C.POINTER(Statement), C.POINTER(Matrix), u64p]
         L.mdn_abi_layout.restype = C.c_size_t
@@ -203,6 +213,15 @@ class Session:
             self._ext_cb = EXTERNAL_CHECK(tramp)
         self._check(lib().mdn_session_set_external_check(self._h, self._ext_cb, None))
 
+    def set_hash(self, kind: int, challenger_input: bytes = b"", challenger_output: bytes = b""):
+        """`blake3_256_config` instead of `poseidon2_config` (mdn_session_set_hash) + the pre-bound HashChallenger state."""
+        self._check(lib().mdn_session_set_hash(self._h, kind))
+        if kind == HASH_BLAKE3:
+            a = (C.c_uint8 * max(1, len(challenger_input))).from_buffer_copy(challenger_input or b"\0")
+            b = (C.c_uint8 * max(1, len(challenger_output))).from_buffer_copy(challenger_output or b"\0")
+            hc = HashChallenger(a, len(challenger_input), b, len(challenger_output))
+            self._check(lib().mdn_session_set_hash_challenger(self._h, C.byref(hc)))
+
     def set_jit(self, min_nodes: int):
         """Node threshold above which constraint programs are NVRTC-compiled (0 = interpreter only)."""
         self._check(lib().mdn_session_set_jit(self._h, min_nodes))
@@ -223,7 +242,7 @@ class Session:
         (log_trace_heights bytes, fields u64[], commitments u64[n,4])."""
         proof = Proof()
         cb = aux_builder if aux_builder is not None else C.cast(None, AUX_BUILDER)
-        self._check(lib().mdn_prove(self._h, C.byref(statement), traces, C.byref(challenger), cb, None, flags,
+        self._check(lib().mdn_prove(self._h, C.byref(statement), traces, C.byref(challenger) if challenger is not None else None, cb, None, flags,
                                     C.byref(proof)))
         return proof_to_numpy(proof)
 

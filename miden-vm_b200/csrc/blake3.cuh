@@ -16,6 +16,7 @@ using gl::u64;
 static constexpr u32 CHUNK_START = 1, CHUNK_END = 2, PARENT = 4, ROOT = 8;
 
 GL_HD u32 rotr(u32 x, int n) { return (x >> n) | (x << (32 - n)); }
+GL_HD u32 bswap(u32 x) { return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24); }
 GL_HD u32 iv(int i) {
     constexpr u32 IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
     return IV[i];

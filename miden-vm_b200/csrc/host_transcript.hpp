@@ -9,6 +9,7 @@
 //   TreeIndices / siblings      : crates/lifted-stark/src/lmcs/tree_indices.rs:34-45,113-126,197-…
 #pragma once
 #include "poseidon2.cuh"
+#include "blake3.cuh"
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -18,10 +19,38 @@ using gl::u64;
 using gl::u32;
 using gl::E2;
 
+// `hashed == true` turns the same object into p3's `SerializingChallenger64<Felt, HashChallenger<u8, Blake3, 32>>`, the
+// challenger of the Blake3_256 configuration (air/src/config.rs:292-293,304-305; p3-challenger 0.6.2 is not vendored, so
+// this restates the published crate -- parity unpinned like the duplex case):
+//   observe(felt) appends its canonical u64 as 8 little-endian bytes to the input buffer and clears the output buffer;
+//   a digest is observed as its 32 bytes; a sampled byte pops from the BACK of the output buffer, which is refilled by
+//   out = blake3(input buffer), input buffer <- out (chaining); sample() = u64::from_le_bytes(8 bytes), redrawn while >= p;
+//   sample_bits(b) = low b bits of u64::from_le_bytes(8 bytes), no rejection.
 struct Duplex {
     u64 st[12];
     u64 in[8];
     u32 in_len = 0, out_len = 0;
+    bool hashed = false;
+    std::vector<uint8_t> bin, bout;
+
+    void observe_byte(uint8_t b) { bout.clear(); bin.push_back(b); }
+    uint8_t sample_byte() {
+        if (bout.empty()) {
+            b3::Hasher h; h.init();
+            for (size_t i = 0; i + 4 <= bin.size(); i += 4) h.push((u32)bin[i] | ((u32)bin[i + 1] << 8) | ((u32)bin[i + 2] << 16) | ((u32)bin[i + 3] << 24));
+            u32 o[8]; h.finish(o);             // every observation is 8 or 32 bytes: the buffer is whole words
+            bout.resize(32);
+            for (int i = 0; i < 32; i++) bout[i] = (uint8_t)(o[i / 4] >> (8 * (i % 4)));
+            bin = bout;
+        }
+        uint8_t b = bout.back(); bout.pop_back();
+        return b;
+    }
+    u64 sample_u64_bytes() { u64 v = 0; for (int k = 0; k < 8; k++) v |= (u64)sample_byte() << (8 * k); return v; }
+    void observe_digest(const u64* d) {
+        if (hashed) { for (int i = 0; i < 4; i++) for (int k = 0; k < 8; k++) observe_byte((uint8_t)(d[i] >> (8 * k))); return; }
+        for (int i = 0; i < 4; i++) observe(d[i]);
+    }
 
     void duplex() {
         if (in_len) {
@@ -33,16 +62,18 @@ struct Duplex {
         out_len = 8;
     }
     void observe(u64 x) {
+        if (hashed) { for (int k = 0; k < 8; k++) observe_byte((uint8_t)(x >> (8 * k))); return; }
         out_len = 0;
         in[in_len++] = x;
         if (in_len == 8) duplex();
     }
     u64 sample() {
+        if (hashed) { for (;;) { u64 v = sample_u64_bytes(); if (v < gl::P) return v; } }
         if (in_len || !out_len) duplex();
         return st[--out_len];
     }
     E2 sample_ext() { u64 a = sample(); u64 b = sample(); return gl::e2(a, b); }
-    u64 sample_bits(u32 bits) { return sample() & ((1ull << bits) - 1); }
+    u64 sample_bits(u32 bits) { return (hashed ? sample_u64_bytes() : sample()) & ((1ull << bits) - 1); }
 };
 
 struct Transcript {
@@ -51,7 +82,7 @@ struct Transcript {
     std::vector<u64> commitments;   // 4 per digest
     void send_field(u64 x) { fields.push_back(x); ch.observe(x); }
     void send_ext(E2 x) { send_field(x.a); send_field(x.b); }
-    void send_commitment(const u64* d) { for (int i = 0; i < 4; i++) { commitments.push_back(d[i]); ch.observe(d[i]); } }
+    void send_commitment(const u64* d) { for (int i = 0; i < 4; i++) commitments.push_back(d[i]); ch.observe_digest(d); }
     void hint_field(u64 x) { fields.push_back(x); }
     void hint_commitment(const u64* d) { commitments.insert(commitments.end(), d, d + 4); }
 };

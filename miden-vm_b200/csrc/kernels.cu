@@ -18,6 +18,7 @@
 #ifdef MDN_NTT_V2
 #include "ntt2.cuh"               // host-checked by tests/cpp/test_ntt_v2.cpp
 #endif
+#include "blake3.cuh"
 #include <algorithm>
 #include <cstdio>
 
@@ -542,6 +543,120 @@ __global__ void k_p2_batch(u64* st, size_t n) {
 }
 void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st) {
     k_p2_batch<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(states, n);
+    COUNT_LAUNCH();
+}
+
+// =============================================================================================
+// BLAKE3 hashing: the reference's `HashFunction::Blake3_256` configuration (air/src/config.rs:276-307).
+//   leaf   : ChainingHasher -- state (32 bytes, zero at the start) <- blake3(state || little-endian u64 of every felt
+//            of the row), once per matrix in ascending height, states duplicated between heights exactly like the
+//            sponge states (crates/stateful-hasher/src/chaining.rs:31-52; lmcs/lifted_tree.rs:363-417)
+//   node   : blake3(left || right), one compression (CompressionFunctionFromHasher<Blake3, 2, 32>)
+//   digest : 32 bytes = the four u64 slots of every tree, little-endian
+// Same launch geometry, coset ranges and peer-store destinations as the Poseidon2 kernels above.
+// =============================================================================================
+__global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash_b3(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev, u32 prev_log_n,
+                                                               u64* __restrict__ states_out, PushDst dig, u32 has_dig, u32 t0, u32 nt) {
+    size_t L = (size_t)1 << (log_n + log_b);
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((size_t)nt << log_n)) return;
+    u32 t = t0 + (u32)(idx >> log_n);
+    u32 r = (u32)(idx & (((size_t)1 << log_n) - 1));
+    size_t pos = ((size_t)t << log_n) + r;
+    u64 st[4] = {0, 0, 0, 0};
+    if (prev) {
+        size_t Lp = (size_t)1 << (prev_log_n + log_b);
+        size_t pp = ((size_t)t << prev_log_n) + (r & ((1u << prev_log_n) - 1));
+#pragma unroll
+        for (int k = 0; k < 4; k++) st[k] = prev[k * Lp + pp];
+    }
+    for (int m = 0; m < a.n_mats; m++) {
+        const u64* base = a.m[m].base + pos;
+        u32 w = a.m[m].width;
+        b3::Hasher h; h.init();
+#pragma unroll
+        for (int k = 0; k < 4; k++) h.push64(st[k]);
+        for (u32 c = 0; c < w; c++) h.push64(base[(size_t)c * L]);     // LDE values are canonical
+        u32 o[8];
+        h.finish(o);
+        b3::words_to_u64(o, st);
+    }
+    if (states_out) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) states_out[k * L + pos] = st[k];
+    }
+    if (has_dig) {
+        size_t i = ((size_t)r << log_b) | t;
+        push_u2(dig, 2 * i, i, make_ulonglong2(st[0], st[1]));
+        push_u2(dig, 2 * i + 1, i, make_ulonglong2(st[2], st[3]));
+    }
+}
+void launch_leaf_hash_b3(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                         u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st) {
+    size_t cnt = (size_t)nt << log_n;
+    unsigned blocks = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
+    PushDst d = dig ? *dig : local_dst(nullptr);
+    k_leaf_hash_b3<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, d, dig ? 1u : 0u, t0, nt);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(256) k_compress_b3(const u64* __restrict__ ch, u64* __restrict__ par, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ulonglong2* c = reinterpret_cast<const ulonglong2*>(ch + i * 8);
+    ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2], b1 = c[3];
+    u64 l[4] = {a0.x, a0.y, a1.x, a1.y}, r[4] = {b0.x, b0.y, b1.x, b1.y}, o[4];
+    b3::compress2(l, r, o);
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(par + i * 4);
+    d[0] = make_ulonglong2(o[0], o[1]);
+    d[1] = make_ulonglong2(o[2], o[3]);
+}
+void launch_compress_layer_b3(const u64* children, u64* parents, size_t n_parents, cudaStream_t st) {
+    k_compress_b3<<<(unsigned)((n_parents + 255) / 256), 256, 0, st>>>(children, parents, n_parents);
+    COUNT_LAUNCH();
+}
+// FRI round leaf (fri/prover.rs:137-165): blake3(zero state || the row's 2^la extension values as 2 * 2^la little-endian u64)
+__global__ void __launch_bounds__(256) k_fri_leaf_b3(const u64* __restrict__ ev, size_t q, u32 la, PushDst dig, u32 log_b, u32 t0, u32 log_nt) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((q >> log_b) << log_nt)) return;
+    size_t i = ((idx >> log_nt) << log_b) | (t0 + (idx & ((1u << log_nt) - 1)));
+    const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
+    b3::Hasher h; h.init();
+    for (int k = 0; k < 4; k++) h.push64(0);
+    u32 a = 1u << la;
+    for (u32 j = 0; j < a; j++) {
+        ulonglong2 v = e[i + (size_t)gl::bitrev32(j, la) * q];
+        h.push64(v.x); h.push64(v.y);
+    }
+    u32 o[8]; u64 d[4];
+    h.finish(o);
+    b3::words_to_u64(o, d);
+    push_u2(dig, 2 * i, i, make_ulonglong2(d[0], d[1]));
+    push_u2(dig, 2 * i + 1, i, make_ulonglong2(d[2], d[3]));
+}
+void launch_fri_leaf_hash_b3(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st) {
+    if (rows < ((size_t)1 << log_b)) { log_b = 0; t0 = 0; nt = 1; }
+    size_t cnt = (rows >> log_b) * nt;
+    k_fri_leaf_b3<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(evals, rows, log_arity, digests, log_b, t0, log2_exact(nt));
+    COUNT_LAUNCH();
+}
+// Proof-of-work for the hash challenger: smallest w such that, after observing w (8 little-endian bytes) on top of the
+// `n_words` 32-bit words of the challenger's input buffer, the low `bits` bits of the first sampled u64 are zero.  The
+// HashChallenger samples bytes from the BACK of the 32-byte output: u64::from_le_bytes([out[31], out[30], ..., out[24]]).
+__global__ void __launch_bounds__(128) k_grind_b3(const u32* __restrict__ input, u32 n_words, u64 mask, u64 start, u64 count, u64* result) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    u64 w = start + idx;
+    b3::Hasher h; h.init();
+    for (u32 i = 0; i < n_words; i++) h.push(input[i]);
+    h.push64(w);
+    u32 o[8];
+    h.finish(o);
+    u64 v = (u64)b3::bswap(o[7]) | ((u64)b3::bswap(o[6]) << 32);   // bytes 31..24 of the output become bytes 0..7
+    if ((v & mask) == 0) atomicMin(reinterpret_cast<unsigned long long*>(result), (unsigned long long)w);
+}
+void launch_grind_b3(const u32* d_input_words, u32 n_words, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
+    u64 mask = (1ull << bits) - 1;
+    k_grind_b3<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_input_words, n_words, mask, start, count, d_result);
     COUNT_LAUNCH();
 }
 

@@ -106,6 +106,14 @@ void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, 
 void launch_fri_leaf_hash(const u64* evals /* EF interleaved */, size_t rows, u32 log_arity, const PushDst& digests,
                           u32 log_b, u32 t0, u32 nt, cudaStream_t st);
 void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
+// The same three tree kernels and the proof-of-work search for the Blake3_256 configuration (air/src/config.rs:276-307):
+// chaining leaf hasher (4-lane SoA states), blake3(left || right) nodes, hash-challenger PoW over the challenger's input
+// buffer (d_input_words, whole 32-bit words).
+void launch_leaf_hash_b3(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                         u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st);
+void launch_compress_layer_b3(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
+void launch_fri_leaf_hash_b3(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st);
+void launch_grind_b3(const u32* d_input_words, u32 n_words, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // Constraints / quotient

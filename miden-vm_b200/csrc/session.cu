@@ -202,6 +202,19 @@ struct mdn_session {
     u32 nt() const { return sharded() ? (1u << params.log_blowup) >> shard_log_g : (1u << params.log_blowup); }   // cosets of this rank
     u32 t0() const { return sharded() ? shard_rank * nt() : 0; }
     int coset_owner(u32 t) const { return sharded() ? (int)(t / nt()) : -1; }
+    // STARK hash configuration (mdn_session_set_hash): Poseidon2 sponge + duplex challenger (default) or Blake3 chaining
+    // hasher + hash challenger (air/src/config.rs:276-307).  `align` = LMCS alignment: 8 (sponge rate) or 1 (chaining).
+    int hash_kind = MDN_HASH_POSEIDON2;
+    u32 align() const { return hash_kind == MDN_HASH_BLAKE3 ? 1u : 8u; }
+    std::vector<uint8_t> hash_ch_in, hash_ch_out;          // pre-bound HashChallenger state (mdn_session_set_hash_challenger)
+    void hash_leaves(const mk::LeafArgs& a, u32 ln, u32 lb, const u64* prev, u32 prev_log, u64* states_out, const mk::PushDst* dig, u32 tb, u32 tn) {
+        if (hash_kind == MDN_HASH_BLAKE3) mk::launch_leaf_hash_b3(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
+        else mk::launch_leaf_hash(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
+    }
+    void compress_layer(const u64* children, u64* parents, size_t n) {
+        if (hash_kind == MDN_HASH_BLAKE3) mk::launch_compress_layer_b3(children, parents, n, stream);
+        else mk::launch_compress_layer(children, parents, n, stream);
+    }
     mdn_external_check external_check = nullptr; void* external_ctx = nullptr;   // Statement::eval_external (mdn_session_set_external_check)
     void shard_map_slab(char* base, size_t size);
     void shard_unmap_slabs();
@@ -584,7 +597,9 @@ void mdn_session::build_tree(Committed& c) {
         size_t j = i;
         mk::LeafArgs args; args.n_mats = 0;
         while (j < c.mats.size() && c.mats[j].log_n == c.mats[i].log_n) {
-            if (c.mats[j].width) {
+            // a zero-width matrix is a no-op for the sponge (an empty absorb leaves the state untouched) but not for the
+            // chaining hasher, which re-hashes its state (crates/stateful-hasher/src/chaining.rs:43-46)
+            if (c.mats[j].width || hash_kind == MDN_HASH_BLAKE3) {
                 if (args.n_mats == 8) fail(MDN_ERR_UNSUPPORTED, "more than 8 matrices of one height in a tree");
                 args.m[args.n_mats++] = mk::LeafMat{c.mats[j].lde, c.mats[j].width, 0};
             }
@@ -599,7 +614,7 @@ void mdn_session::build_tree(Committed& c) {
             size_t Lg = (size_t)tn << ln;
             for (int q = 0; q < args.n_mats; q++) { leaf_bytes += (double)Lg * args.m[q].width * 8.0; perms += Lg * ((args.m[q].width + 7) / 8); }
             leaf_bytes += last ? (double)Lg * 32.0 : (double)Lg * 96.0;
-            mk::launch_leaf_hash(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? &dig : nullptr, tb, tn, stream);
+            hash_leaves(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? &dig : nullptr, tb, tn);
         }
         prev = out.p; prev_log = ln;
         i = j;
@@ -608,21 +623,21 @@ void mdn_session::build_tree(Committed& c) {
     if (!split) {
         ProfScope ps(prof, PC_COMPRESS);
         perms += L - 1;
-        for (u32 d = depth; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
+        for (u32 d = depth; d-- > 0;) compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d);
     } else {
         {
             ProfScope ps(prof, PC_COMPRESS);
             for (u32 d = depth; d-- > lg;) {
                 size_t cnt = (size_t)1 << (d - lg), start = (size_t)shard_rank << (d - lg);
                 perms += cnt;
-                mk::launch_compress_layer(c.tree.layer(d + 1) + 2 * start * 4, c.tree.layer(d) + start * 4, cnt, stream);
+                compress_layer(c.tree.layer(d + 1) + 2 * start * 4, c.tree.layer(d) + start * 4, cnt);
             }
         }
         u64* mine = c.tree.layer(lg) + (size_t)shard_rank * 4;
         mk::launch_push(mine, peers_of(mine), shard_rank, shard_world, 4, stream);
         shard_barrier();
         ProfScope ps(prof, PC_COMPRESS);
-        for (u32 d = lg; d-- > 0;) mk::launch_compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d, stream);
+        for (u32 d = lg; d-- > 0;) compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d);
     }
     CUDA_OK(cudaMemcpyAsync(c.root, c.tree.layer(0), 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -634,6 +649,30 @@ void mdn_session::build_tree(Committed& c) {
 u64 mdn_session::grind(u32 bits) {
     if (bits == 0) { tr.fields.push_back(0); return 0; }
     Duplex& ch = tr.ch;
+    if (ch.hashed) {
+        // hash challenger: a candidate w is checked by hashing (input buffer || w as 8 little-endian bytes) and reading
+        // the low bits of the first sampled u64; the buffer is whole 32-bit words (every observation is 8 or 32 bytes)
+        if (ch.bin.size() % 4) fail(MDN_ERR_INVALID_ARG, "hash challenger input buffer is not a whole number of words");
+        u32 nw = (u32)(ch.bin.size() / 4);
+        DevBuf d; d.alloc((nw + 1) / 2 + 2, stream);
+        u64 none = ~0ull;
+        if (nw) CUDA_OK(cudaMemcpyAsync(d.p + 1, ch.bin.data(), ch.bin.size(), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d.p, &none, sizeof none, cudaMemcpyHostToDevice, stream));
+        u64 start = 0, found = ~0ull;
+        u64 batch = std::max<u64>(1ull << 14, std::min<u64>(1ull << 20, 4ull << bits));
+        ProfScope ps(prof, PC_GRIND);
+        while (found == ~0ull) {
+            if (start >= gl::P) fail(MDN_ERR_INVALID_ARG, "proof-of-work search exhausted");
+            mk::launch_grind_b3((const u32*)(d.p + 1), nw, bits, start, batch, d.p, stream);
+            CUDA_OK(cudaMemcpyAsync(&found, d.p, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(cudaStreamSynchronize(stream));
+            start += batch;
+        }
+        ch.observe(found);
+        if (ch.sample_bits(bits) != 0) fail(MDN_ERR_CUDA, "device proof-of-work witness failed the host check");
+        tr.fields.push_back(found);
+        return found;
+    }
     if (ch.in_len >= 8) fail(MDN_ERR_INVALID_ARG, "challenger buffer overflow");
     u64 base[12];
     for (int i = 0; i < 12; i++) base[i] = ch.st[i];
@@ -794,7 +833,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     mk::reset_launch_count();
     prof.st = stream; prof.reset(); leaf_bytes = ntt_bytes = 0; perms = 0;
     if (!d_flag.p) { ArenaScope persistent(nullptr); d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
-    if (!st || !traces || !chal) fail(MDN_ERR_INVALID_ARG, "null argument");
+    if (!st || !traces || (!chal && hash_kind == MDN_HASH_POSEIDON2)) fail(MDN_ERR_INVALID_ARG, "null argument");
     if (st->n_airs == 0 || st->n_airs > 256) fail(MDN_ERR_INVALID_ARG, "AIR count must be in 1..=256");
     if (params.log_folding_arity < 1 || params.log_folding_arity > 3) fail(MDN_ERR_INVALID_ARG, "invalid folding arity: log_arity %u (must be 1, 2, or 3)", params.log_folding_arity);
     u32 lb = params.log_blowup;
@@ -966,11 +1005,16 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
 
     // challenger: caller's pre-bound state, then Statement::observe + observe_shape (mod.rs:290-291)
     Duplex& ch = tr.ch;
-    for (int i = 0; i < 12; i++) ch.st[i] = chal->sponge_state[i];
-    if (chal->input_len > 7 || chal->output_len > 8) fail(MDN_ERR_INVALID_ARG, "malformed challenger state");
-    for (u32 i = 0; i < chal->input_len; i++) ch.in[i] = chal->input_buffer[i];
-    ch.in_len = chal->input_len; ch.out_len = chal->output_len;
-    if (has_prep) for (int q = 0; q < 4; q++) ch.observe(prep_c.root[q]);   // preprocessed commitment first (mod.rs:282-286)
+    if (hash_kind == MDN_HASH_BLAKE3) {
+        ch.hashed = true; ch.bin = hash_ch_in; ch.bout = hash_ch_out;      // mdn_session_set_hash_challenger
+    } else {
+        if (!chal) fail(MDN_ERR_INVALID_ARG, "null challenger");
+        for (int i = 0; i < 12; i++) ch.st[i] = chal->sponge_state[i];
+        if (chal->input_len > 7 || chal->output_len > 8) fail(MDN_ERR_INVALID_ARG, "malformed challenger state");
+        for (u32 i = 0; i < chal->input_len; i++) ch.in[i] = chal->input_buffer[i];
+        ch.in_len = chal->input_len; ch.out_len = chal->output_len;
+    }
+    if (has_prep) ch.observe_digest(prep_c.root);   // preprocessed commitment first (mod.rs:282-286)
     for (u32 i = 0; i < st->n_observe_felts; i++) ch.observe(st->observe_felts[i]);
     ch.observe(k);
     for (u32 i = 0; i < k; i++) ch.observe(log_heights[i]);
@@ -1523,7 +1567,7 @@ void mdn_session::finish() {
     u32 W = 0;
     for (int g = 0; g < ng; g++)
         for (size_t m = 0; m < groups[g]->mats.size(); m++) {
-            u32 w = groups[g]->mats[m].width, aw = (w + 7) / 8 * 8;
+            u32 w = groups[g]->mats[m].width, aw = (w + align() - 1) / align() * align();   // Lmcs alignment: 8 for the sponge, 1 for the chaining hasher
             aligned_off.push_back(W);
             for (int p = 0; p < 2; p++) {
                 for (u32 c = 0; c < w; c++) {
@@ -1619,26 +1663,27 @@ void mdn_session::finish() {
         {
             ProfScope ps(prof, PC_FRI);
             perms += (q * (la == 3 ? 2 : 1) + q - 1) / (in_sh ? shard_world : 1);
-            mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
+            if (hash_kind == MDN_HASH_BLAKE3) mk::launch_fri_leaf_hash_b3(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
+            else mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
         }
         if (in_sh) shard_barrier();
         if (!split) {
             ProfScope ps(prof, PC_FRI);
-            for (u32 d = t.depth; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
+            for (u32 d = t.depth; d-- > 0;) compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d);
         } else {
             const u32 lg = shard_log_g;
             {
                 ProfScope ps(prof, PC_FRI);
                 for (u32 d = t.depth; d-- > lg;) {
                     size_t cnt = (size_t)1 << (d - lg), start = (size_t)shard_rank << (d - lg);
-                    mk::launch_compress_layer(t.layer(d + 1) + 2 * start * 4, t.layer(d) + start * 4, cnt, stream);
+                    compress_layer(t.layer(d + 1) + 2 * start * 4, t.layer(d) + start * 4, cnt);
                 }
             }
             u64* mine = t.layer(lg) + (size_t)shard_rank * 4;
             mk::launch_push(mine, peers_of(mine), shard_rank, shard_world, 4, stream);
             shard_barrier();
             ProfScope ps(prof, PC_FRI);
-            for (u32 d = lg; d-- > 0;) mk::launch_compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d, stream);
+            for (u32 d = lg; d-- > 0;) compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d);
         }
         u64 root[4];
         CUDA_OK(cudaMemcpyAsync(root, t.layer(0), sizeof root, cudaMemcpyDeviceToHost, stream));
@@ -1705,7 +1750,7 @@ void mdn_session::finish() {
                 size_t t = im & (B - 1), rr = im >> lb;
                 size_t pos = (t << cm.log_n) + rr, Lm = (size_t)1 << ldm;
                 for (u32 col = 0; col < cm.width; col++) { ptrs.push_back(cm.lde + (size_t)col * Lm + pos); owner.push_back(replicated ? -1 : coset_owner((u32)t)); }
-                plan.push_back(Emit{0, cm.width, (size_t)((cm.width + 7) / 8 * 8 - cm.width)});
+                plan.push_back(Emit{0, cm.width, (size_t)((cm.width + align() - 1) / align() * align() - cm.width)});
             }
         for (auto& ds : hostfs::missing_siblings(leafs)) {
             // split tree: a node below the sub-root level exists only on the rank owning its leaf range
@@ -2103,6 +2148,22 @@ int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_all
         { std::vector<u64> one(1, 0), got(world); if (fn(ctx, one.data(), got.data(), 1) != 0) fail(MDN_ERR_INVALID_ARG, "all-gather callback failed"); }
     } catch (const MdnError& e) { s->error = e.what(); return e.code; }
     catch (const std::exception& e) { s->error = e.what(); return MDN_ERR_INVALID_ARG; }
+    return MDN_OK;
+}
+
+int mdn_session_set_hash(mdn_session* s, mdn_hash_kind kind) {
+    if (!s) return MDN_ERR_INVALID_ARG;
+    if (kind != MDN_HASH_POSEIDON2 && kind != MDN_HASH_BLAKE3) { s->error = "unknown hash configuration"; return MDN_ERR_UNSUPPORTED; }
+    if (s->in_proof) { s->error = "mdn_session_set_hash called inside a proof"; return MDN_ERR_INVALID_ARG; }
+    if (s->has_prep && kind != s->hash_kind) { s->error = "the preprocessed bundle was committed under the other hash: remove it first"; return MDN_ERR_INVALID_ARG; }
+    s->hash_kind = kind;
+    return MDN_OK;
+}
+int mdn_session_set_hash_challenger(mdn_session* s, const mdn_hash_challenger* c) {
+    if (!s || !c || (c->input_len && !c->input_buffer) || (c->output_len && !c->output_buffer)) return MDN_ERR_INVALID_ARG;
+    if (c->input_len % 4 || c->output_len > 32) { s->error = "hash challenger: the input buffer must be whole 32-bit words and the output buffer at most 32 bytes"; return MDN_ERR_INVALID_ARG; }
+    s->hash_ch_in.assign(c->input_buffer, c->input_buffer + c->input_len);
+    s->hash_ch_out.assign(c->output_buffer, c->output_buffer + c->output_len);
     return MDN_OK;
 }
 

@@ -128,3 +128,13 @@ def initial_challenger(params: PcsParams, observe_fn) -> Challenger:
                       params.log_blowup, params.log_final_degree, 1 << params.log_folding_arity, 0], dtype=np.uint64)
     observe_fn(c, felts)
     return c
+
+
+def initial_hash_challenger(params: PcsParams) -> bytes:
+    """`blake3_256_config(..).challenger()` + `observe_protocol_params` (air/src/config.rs:299-307, 188-198): the
+    HashChallenger's input buffer after observing the relation digest and the eight parameter felts, each as its
+    canonical u64 in little-endian bytes; nothing has been sampled, so the output buffer is empty."""
+    import struct
+    felts = list(RELATION_DIGEST) + [params.num_queries, params.query_pow_bits, params.deep_pow_bits, params.folding_pow_bits,
+                                     params.log_blowup, params.log_final_degree, 1 << params.log_folding_arity, 0]
+    return b"".join(struct.pack("<Q", int(f)) for f in felts)

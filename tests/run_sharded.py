@@ -68,23 +68,33 @@ def main():
     cases.append(("tiny: zero FRI rounds", W.miden_pcs_params(), W.Workload([4, 6], widths=(9, 9), aux_widths=(1, 1)), None))
     cases.append(("second shape on the same sessions", W.miden_pcs_params(), W.Workload([log_h - 1, log_h - 1], widths=(20, 9), aux_widths=(2, 1)), None))
 
+    # the Blake3_256 configuration through the same partition (digest stores, sub-trees and openings are hash-agnostic)
+    cases.append(("blake3: miden-shape mixed heights", W.miden_pcs_params(), W.Workload([log_h - 1, log_h - 2, log_h - 3]), None, "blake3"))
+    wl3, builder3 = test_airs.fib_product_workload([8, 6], lqd=1)
+    cases.append(("blake3: host aux builder", W.fast_pcs_params(), wl3, builder3, "blake3"))
+
     sessions = {}     # params tuple -> (single, split): sessions are reused so that arena reuse across shapes is exercised
 
-    def sess_for(params):
-        key = tuple(getattr(params, f) for f, _ in params._fields_)
+    def sess_for(params, hash_name="poseidon2"):
+        key = tuple(getattr(params, f) for f, _ in params._fields_) + (hash_name,)
         if key not in sessions:
             single = B.Session(params, local)
             split = B.Session(params, local)
+            if hash_name == "blake3":
+                for s_ in (single, split):
+                    s_.set_hash(B.HASH_BLAKE3, W.initial_hash_challenger(params))
             split.set_shard(rank, world, allgather)
             for s_ in (single, split):
                 lib.mdn_set_debug(s_.handle, 1 if os.environ.get("SHARD_DEBUG_STAGES") else 0)
             sessions[key] = (single, split)
         return sessions[key]
 
-    for name, params, wl, aux in cases:
+    for case in cases:
+        name, params, wl, aux = case[:4]
+        hash_name = case[4] if len(case) > 4 else "poseidon2"
         cb = B.AUX_BUILDER(aux) if aux is not None else None
-        ch = W.initial_challenger(params, observe)
-        single, split = sess_for(params)
+        ch = W.initial_challenger(params, observe) if hash_name == "poseidon2" else None
+        single, split = sess_for(params, hash_name)
         if getattr(wl, "preprocessed", None) is not None:
             single.set_preprocessed(wl.statement, wl.preprocessed_matrices)
             split.set_preprocessed(wl.statement, wl.preprocessed_matrices)
