@@ -373,7 +373,11 @@ def main():
                     "ms_per_step": total_e / args.steps * 1e3, "per_step_ms": [round(x * 1e3, 2) for x in steps_e], "api": "mdn_prove (include/miden_b200.h) with pinned host RowMajorMatrix buffers"},
             "gpu_launches": (int(tim_v.kernel_launches) + int(tim_e.kernel_launches)) * args.steps,   # kernels of the K value steps + K e2e steps
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon2 leaf sponge, main trace)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_fwd_contig + k_fwd_strided + k_intt_* (coset LDE: the dominant kernel class under Blake3)", "achieved": ntt_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": None, "peak_source": f"{peak_kind} copy bandwidth",
+                         "note": "instruction-bound (ncu r2b: issue 61-65 %, ALU pipe 63-69 %, FMA-heavy 51-66 %; ~280 instructions per point per pass), see DESIGN.md section 5"}
+            if args.hash == "blake3" else
+                        {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon2 leaf sponge, main trace)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_kind} copy bandwidth",
                          "note": "integer-ALU bound by construction (14-16k instructions per permutation per 64 input bytes); HBM fraction is low on purpose, see `issue`",
                          "permutations_per_s": perms_per_s, "issue": issue},

@@ -20,6 +20,7 @@
 #pragma once
 #include "poseidon2_fast2.cuh"
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace ntt2 {
 using gl::u64;
@@ -42,10 +43,37 @@ GL_HD u32 tile_words(u32 m, u32 log_cols) {
     u32 n = 1u << (m + log_cols);
     return log_cols ? n : n + (n >> 3) + 1;
 }
-// words of shared memory of the four block functions
-GL_HD size_t smem_words_contig_fwd(u32 n2) { return (size_t)tile_words(n2, 0) + ((size_t)1 << n2); }
-GL_HD size_t smem_words_contig_inv(u32 n2) { return (size_t)tile_words(n2, 0) + ((size_t)1 << n2) / 2 + 1; }
-GL_HD size_t smem_words_strided(u32 n1, u32 log_c) { return (size_t)tile_words(n1, log_c) + ((size_t)1 << n1) / 2 + 1; }
+// Shared memory of the four block functions: [tile | table (16-byte aligned: it is the destination of a bulk copy) |
+// mbarrier].  tw_off = offset of the table in words.
+GL_HD u32 tw_off(u32 m, u32 log_cols) { return (tile_words(m, log_cols) + 1u) & ~1u; }
+GL_HD size_t smem_words_contig_fwd(u32 n2) { return (size_t)tw_off(n2, 0) + ((size_t)1 << n2) + 2; }
+GL_HD size_t smem_words_contig_inv(u32 n2) { return (size_t)tw_off(n2, 0) + ((size_t)1 << n2) / 2 + 4; }
+GL_HD size_t smem_words_strided(u32 n1, u32 log_c) { return (size_t)tw_off(n1, log_c) + ((size_t)1 << n1) / 2 + 4; }
+
+// Stage `words` u64 of a table into shared memory.  On the device: one bulk asynchronous copy (cp.async.bulk -> mbarrier)
+// issued by thread 0 when the table is big enough and 16-byte aligned, overlapping the tile loads that follow; the
+// matching table_wait() must come before the first use.  Host / emulator / small tables: a plain strided loop.
+struct TableLoad { bool async; };
+GL_HD TableLoad table_load(u64* dst, const u64* src, u32 words, u64* bar) {
+#if defined(__CUDA_ARCH__)
+    const u32 bytes = (words * 8u + 15u) & ~15u;      // the tables carry at least one spare word behind them
+    if (words >= 64 && ((((size_t)src) | ((size_t)dst)) & 15) == 0) {
+        if (threadIdx.x == 0) { tma::mbar_init(bar, 1); }
+        __syncthreads();
+        if (threadIdx.x == 0) { tma::expect_tx(bar, bytes); tma::bulk_g2s(dst, src, bytes, bar); }
+        return TableLoad{true};
+    }
+#endif
+    (void)bar;
+    NTT2_FOR(i, words) dst[i] = src[i];
+    return TableLoad{false};
+}
+GL_HD void table_wait(TableLoad t, u64* bar) {
+#if defined(__CUDA_ARCH__)
+    if (t.async) tma::wait(bar, 0);
+#endif
+    (void)t; (void)bar;
+}
 
 // Twiddle of stage s (span 2^s), butterfly index j < 2^s, of a size-2^m transform.
 //   plain table : tw[j << (m-1-s)]      = w_{2^(s+1)}^j                          (2^(m-1) entries)
@@ -159,14 +187,15 @@ GL_HD u64 w_pow(const u64* hi, const u64* lo, u32 lo_bits, u64 e) {
 // ---- inverse, step 1: strided tile [N1][C] of column `by`, columns j2_0 .. j2_0 + C --------------------
 GL_HD void intt_strided_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_stride, const mk::NttTables& T, u32 log_c) {
     u32 C = 1u << log_c, N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tile_words(T.n1, log_c);
+    u64* x = sm; u64* tw = sm + tw_off(T.n1, log_c); u64* bar = tw + N1 / 2 + 2;
     u64* col = cols + (size_t)by * col_stride;
     u32 j2_0 = bx * C;
-    NTT2_FOR(i, N1 / 2) tw[i] = T.twi_n1[i];
+    TableLoad tl = table_load(tw, T.twi_n1, N1 / 2, bar);
     NTT2_FOR(idx, N1 * C) {
         u32 j1 = idx >> log_c, cc = idx & (C - 1);
         x[tile_off(j1, cc, log_c)] = col[(size_t)j1 * N2 + j2_0 + cc];
     }
+    table_wait(tl, bar);
     NTT2_SYNC();
     smem_dif(x, tw, T.n1, log_c);
     NTT2_FOR(idx, N1 * C) {
@@ -180,10 +209,11 @@ GL_HD void intt_strided_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_str
 // ---- inverse, step 3 (or the whole transform when n1 == 0): contiguous chunk bx of column by ------------
 GL_HD void intt_contig_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_stride, const mk::NttTables& T) {
     u32 N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tile_words(T.n2, 0);
+    u64* x = sm; u64* tw = sm + tw_off(T.n2, 0); u64* bar = tw + N2 / 2 + 2;
     u64* chunk = cols + (size_t)by * col_stride + (size_t)bx * N2;
-    NTT2_FOR(i, N2 / 2) tw[i] = T.twi_n2[i];
+    TableLoad tl = table_load(tw, T.twi_n2, N2 / 2, bar);
     NTT2_FOR(i, N2) x[tile_off(i, 0, 0)] = chunk[i];
+    table_wait(tl, bar);
     NTT2_SYNC();
     smem_dif(x, tw, T.n2, 0);
     NTT2_FOR(i, N2) chunk[i] = glf::canon_cc(x[tile_off(i, 0, 0)]);
@@ -192,7 +222,7 @@ GL_HD void intt_contig_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_stri
 static constexpr u32 FWD_LANES = 128;   // lanes of the inter-pass twiddle progression (independent of blockDim)
 GL_HD void fwd_contig_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, const mk::NttTables& T, const mk::PremulTables& Pm) {
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tile_words(T.n2, 0);
+    u64* x = sm; u64* tw = sm + tw_off(T.n2, 0); u64* bar = tw + N2;
     mk::FwdItem it = items[by];
     u32 p_hi = bx;
     u32 j1 = gl::bitrev32(p_hi, T.n1);
@@ -200,8 +230,9 @@ GL_HD void fwd_contig_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, c
     u64* dst = it.dst + (size_t)p_hi * N2;
     u64 fb = Pm.tab_b[(size_t)it.base * N1 + j1];              // g^j1 / N
     const u64* tc = Pm.tab_c + (size_t)it.base * N2;           // staged twiddles of G = g^N1
-    NTT2_FOR(i, N2 - 1) tw[i] = tc[i];
+    TableLoad tl = table_load(tw, tc, N2, bar);              // N2 - 1 staged twiddles + the unused last slot
     NTT2_FOR(i, N2) x[tile_off(i, 0, 0)] = src[i];
+    table_wait(tl, bar);
     NTT2_SYNC();
     smem_dit<true>(x, tw, T.n2, 0);
     // dst[k2] = x[k2] * fb * w_N^(j1 * k2): lane l walks k2 = l, l + LANES, ... multiplying by w_N^(j1 * LANES)
@@ -222,14 +253,15 @@ GL_HD void fwd_contig_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, c
 // ---- forward, step 3: strided tile [N1][C], DIT along p_hi, in place ----------------------------------------
 GL_HD void fwd_strided_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, const mk::NttTables& T, u32 log_c) {
     u32 C = 1u << log_c, N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tile_words(T.n1, log_c);
+    u64* x = sm; u64* tw = sm + tw_off(T.n1, log_c); u64* bar = tw + N1 / 2 + 2;
     u64* col = items[by].dst;
     u32 k2_0 = bx * C;
-    NTT2_FOR(i, N1 / 2) tw[i] = T.tw_n1[i];
+    TableLoad tl = table_load(tw, T.tw_n1, N1 / 2, bar);
     NTT2_FOR(idx, N1 * C) {
         u32 p_hi = idx >> log_c, cc = idx & (C - 1);
         x[tile_off(p_hi, cc, log_c)] = col[(size_t)p_hi * N2 + k2_0 + cc];
     }
+    table_wait(tl, bar);
     NTT2_SYNC();
     smem_dit<false>(x, tw, T.n1, log_c);
     NTT2_FOR(idx, N1 * C) {

@@ -36,7 +36,10 @@ inline NttHost build_ntt(u32 n) {
     h.lo_bits = (n + 1) / 2;
     u32 n1 = h.n1, n2 = h.n2, lo_bits = h.lo_bits;
     u64 w = gl::two_adic_generator(n), wi = gl::inv(w);
-    auto push = [&](const std::vector<u64>& v) { size_t off = h.data.size(); h.data.insert(h.data.end(), v.begin(), v.end()); return off; };
+    auto push = [&](const std::vector<u64>& v) {   // every table starts on a 16-byte boundary: it may be the source of a bulk copy (tma.cuh)
+        if (h.data.size() & 1) h.data.push_back(0);
+        size_t off = h.data.size(); h.data.insert(h.data.end(), v.begin(), v.end()); return off;
+    };
     u64 w1 = gl::two_adic_generator(n1), w2 = gl::two_adic_generator(n2);
     h.o_tw1 = push(powers(w1, n1 ? (size_t)1 << (n1 - 1) : 1));
     h.o_tw2 = push(powers(w2, n2 ? (size_t)1 << (n2 - 1) : 1));
