@@ -374,49 +374,70 @@ void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, con
 #else   // MDN_NTT_V2: block functions of ntt2.cuh (host-checked by tests/cpp/test_ntt_v2.cpp) ------------------------
 // ptxas chooses the register count (48-64); forcing 2 or 3 resident blocks was measured and loses 5 % (profiles/r2_tuning.md)
 #define NTT_BOUNDS __launch_bounds__(NTT_THREADS)
+// Kernels are instantiated with the split (n1, n2) as compile-time constants for the trace heights that matter
+// (2^16 .. 2^22: NTT_SPECIALISED below) and once with run-time sizes (<-1, -1>) for everything else.
+template <int N1C, int N2C>
 __global__ void NTT_BOUNDS k_intt_strided(u64* cols, size_t col_stride, NttTables T, u32 log_c) {
     extern __shared__ u64 sm[];
-    ntt2::intt_strided_block(blockIdx.x, blockIdx.y, sm, cols, col_stride, T, log_c);
+    ntt2::intt_strided_block<N1C, N2C>(blockIdx.x, blockIdx.y, sm, cols, col_stride, T, log_c);
 }
+template <int N2C>
 __global__ void NTT_BOUNDS k_intt_contig(u64* cols, size_t col_stride, NttTables T) {
     extern __shared__ u64 sm[];
-    ntt2::intt_contig_block(blockIdx.x, blockIdx.y, sm, cols, col_stride, T);
+    ntt2::intt_contig_block<N2C>(blockIdx.x, blockIdx.y, sm, cols, col_stride, T);
 }
-void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, cudaStream_t st) {
-    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+template <int N1C, int N2C>
+__global__ void NTT_BOUNDS k_fwd_contig(const FwdItem* __restrict__ items, NttTables T, PremulTables Pm) {
+    extern __shared__ u64 sm[];
+    ntt2::fwd_contig_block<N1C, N2C>(blockIdx.x, blockIdx.y, sm, items, T, Pm);
+}
+template <int N1C, int N2C>
+__global__ void NTT_BOUNDS k_fwd_strided(const FwdItem* __restrict__ items, NttTables T, u32 log_c) {
+    extern __shared__ u64 sm[];
+    ntt2::fwd_strided_block<N1C, N2C>(blockIdx.x, blockIdx.y, sm, items, T, log_c);
+}
+// X(n1, n2) for every specialised split: split_n() of heights 16 .. 22
+#define NTT_SPECIALISED(X) X(8, 8) X(8, 9) X(9, 9) X(9, 10) X(10, 10) X(10, 11) X(11, 11)
+
+template <int N1C, int N2C>
+static void launch_intt_t(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, u32 log_c, cudaStream_t st) {
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2, C = 1u << log_c;
     if (T.n1 > 0) {
-        u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
-        u32 C = 1u << log_c;
         size_t smem = ntt2::smem_words_strided(T.n1, log_c) * sizeof(u64);
-        cudaFuncSetAttribute(k_intt_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_intt_strided<<<dim3(N2 / C, n_cols), ntt_threads(T.n1, log_c), smem, st>>>(cols, col_stride, T, log_c);
+        cudaFuncSetAttribute(k_intt_strided<N1C, N2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_intt_strided<N1C, N2C><<<dim3(N2 / C, n_cols), ntt_threads(T.n1, log_c), smem, st>>>(cols, col_stride, T, log_c);
         COUNT_LAUNCH();
     }
     size_t smem = ntt2::smem_words_contig_inv(T.n2) * sizeof(u64);
-    k_intt_contig<<<dim3(N1, n_cols), ntt_threads(T.n2, 0), smem, st>>>(cols, col_stride, T);
+    k_intt_contig<N2C><<<dim3(N1, n_cols), ntt_threads(T.n2, 0), smem, st>>>(cols, col_stride, T);
     COUNT_LAUNCH();
 }
-__global__ void NTT_BOUNDS k_fwd_contig(const FwdItem* __restrict__ items, NttTables T, PremulTables Pm) {
-    extern __shared__ u64 sm[];
-    ntt2::fwd_contig_block(blockIdx.x, blockIdx.y, sm, items, T, Pm);
+void launch_intt(u64* cols, size_t col_stride, u32 n_cols, const NttTables& T, cudaStream_t st) {
+    u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
+#define X(a, b) if (T.n1 == a && T.n2 == b) { launch_intt_t<a, b>(cols, col_stride, n_cols, T, log_c, st); return; }
+    NTT_SPECIALISED(X)
+#undef X
+    launch_intt_t<-1, -1>(cols, col_stride, n_cols, T, log_c, st);
 }
-__global__ void NTT_BOUNDS k_fwd_strided(const FwdItem* __restrict__ items, NttTables T, u32 log_c) {
-    extern __shared__ u64 sm[];
-    ntt2::fwd_strided_block(blockIdx.x, blockIdx.y, sm, items, T, log_c);
-}
-void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, const PremulTables& Pm, cudaStream_t st) {
-    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
+template <int N1C, int N2C>
+static void launch_fwd_t(const FwdItem* d_items, u32 n_items, const NttTables& T, const PremulTables& Pm, u32 log_c, cudaStream_t st) {
+    u32 N1 = 1u << T.n1, N2 = 1u << T.n2, C = 1u << log_c;
     size_t smem = ntt2::smem_words_contig_fwd(T.n2) * sizeof(u64);
-    k_fwd_contig<<<dim3(N1, n_items), ntt_threads(T.n2, 0), smem, st>>>(d_items, T, Pm);
+    k_fwd_contig<N1C, N2C><<<dim3(N1, n_items), ntt_threads(T.n2, 0), smem, st>>>(d_items, T, Pm);
     COUNT_LAUNCH();
     if (T.n1 > 0) {
-        u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
-        u32 C = 1u << log_c;
         size_t smem2 = ntt2::smem_words_strided(T.n1, log_c) * sizeof(u64);
-        cudaFuncSetAttribute(k_fwd_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        k_fwd_strided<<<dim3(N2 / C, n_items), ntt_threads(T.n1, log_c), smem2, st>>>(d_items, T, log_c);
+        cudaFuncSetAttribute(k_fwd_strided<N1C, N2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        k_fwd_strided<N1C, N2C><<<dim3(N2 / C, n_items), ntt_threads(T.n1, log_c), smem2, st>>>(d_items, T, log_c);
         COUNT_LAUNCH();
     }
+}
+void launch_fwd_ntt(const FwdItem* d_items, u32 n_items, const NttTables& T, const PremulTables& Pm, cudaStream_t st) {
+    u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;
+#define X(a, b) if (T.n1 == a && T.n2 == b) { launch_fwd_t<a, b>(d_items, n_items, T, Pm, log_c, st); return; }
+    NTT_SPECIALISED(X)
+#undef X
+    launch_fwd_t<-1, -1>(d_items, n_items, T, Pm, log_c, st);
 }
 #endif  // MDN_NTT_V2
 

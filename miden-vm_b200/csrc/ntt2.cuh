@@ -180,14 +180,39 @@ GL_HD void smem_dif(u64* x, const u64* tw, u32 m, u32 log_cols) {
     }
 }
 
+// The same two schedules with the transform size and the tile shape as compile-time constants: every shift, mask and
+// table stride of the index arithmetic folds away (ncu r2b: a quarter of the executed instructions of the passes were
+// LEA / SHF / IMAD address arithmetic on run-time m, b, log_cols).  The kernels of the common sizes are instantiated
+// from these (kernels.cu); other sizes keep the run-time schedules above.  Same rounds, same order, same results.
+template <bool STAGED, int M, int LC, int B = 0>
+GL_HD void smem_dit_t(u64* x, const u64* tw) {
+    if constexpr (B < M) {
+        constexpr int left = M - B;
+        constexpr int R = (left >= 3 && left != 4) ? 3 : ((left == 4 || left == 2) ? 2 : 1);
+        dit_round<R, STAGED, (B == 0) && !STAGED>(x, tw, (u32)M, (u32)B, (u32)LC);
+        smem_dit_t<STAGED, M, LC, B + R>(x, tw);
+    }
+}
+template <int M, int LC, int TOP = M>
+GL_HD void smem_dif_t(u64* x, const u64* tw) {
+    if constexpr (TOP > 0) {
+        constexpr int R = (TOP >= 3 && TOP != 4) ? 3 : ((TOP == 4 || TOP == 2) ? 2 : 1);
+        dif_round<R, (TOP - R) == 0>(x, tw, (u32)M, (u32)(TOP - R), (u32)LC);
+        smem_dif_t<M, LC, TOP - R>(x, tw);
+    }
+}
+
 GL_HD u64 w_pow(const u64* hi, const u64* lo, u32 lo_bits, u64 e) {
     return glf::mul(hi[e >> lo_bits], lo[e & ((1ull << lo_bits) - 1)]);
 }
 
 // ---- inverse, step 1: strided tile [N1][C] of column `by`, columns j2_0 .. j2_0 + C --------------------
-GL_HD void intt_strided_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_stride, const mk::NttTables& T, u32 log_c) {
-    u32 C = 1u << log_c, N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tw_off(T.n1, log_c); u64* bar = tw + N1 / 2 + 2;
+template <int N1C = -1, int N2C = -1>
+GL_HD void intt_strided_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_stride, const mk::NttTables& T, u32 log_c_rt) {
+    const u32 n1 = N1C >= 0 ? (u32)N1C : T.n1, n2 = N2C >= 0 ? (u32)N2C : T.n2;
+    const u32 log_c = N1C >= 0 && N2C >= 0 ? (u32)(N1C >= 12 ? 0 : (12 - N1C < N2C ? 12 - N1C : N2C)) : log_c_rt;
+    u32 C = 1u << log_c, N1 = 1u << n1, N2 = 1u << n2;
+    u64* x = sm; u64* tw = sm + tw_off(n1, log_c); u64* bar = tw + N1 / 2 + 2;
     u64* col = cols + (size_t)by * col_stride;
     u32 j2_0 = bx * C;
     TableLoad tl = table_load(tw, T.twi_n1, N1 / 2, bar);
@@ -197,35 +222,40 @@ GL_HD void intt_strided_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_str
     }
     table_wait(tl, bar);
     NTT2_SYNC();
-    smem_dif(x, tw, T.n1, log_c);
+    if constexpr (N1C >= 0 && N2C >= 0) smem_dif_t<N1C, (N1C >= 12 ? 0 : (12 - N1C < N2C ? 12 - N1C : N2C))>(x, tw);
+    else smem_dif(x, tw, n1, log_c);
     NTT2_FOR(idx, N1 * C) {
         u32 slot = idx >> log_c, cc = idx & (C - 1);
-        u32 k1 = gl::bitrev32(slot, T.n1);
+        u32 k1 = gl::bitrev32(slot, n1);
         u32 j2 = j2_0 + cc;
         u64 f = w_pow(T.wi_hi, T.wi_lo, T.lo_bits, (u64)j2 * k1);
         col[(size_t)slot * N2 + j2] = glf::cmul(x[tile_off(slot, cc, log_c)], f);
     }
 }
 // ---- inverse, step 3 (or the whole transform when n1 == 0): contiguous chunk bx of column by ------------
+template <int N2C = -1>
 GL_HD void intt_contig_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_stride, const mk::NttTables& T) {
-    u32 N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tw_off(T.n2, 0); u64* bar = tw + N2 / 2 + 2;
+    const u32 n2 = N2C >= 0 ? (u32)N2C : T.n2;
+    u32 N2 = 1u << n2;
+    u64* x = sm; u64* tw = sm + tw_off(n2, 0); u64* bar = tw + N2 / 2 + 2;
     u64* chunk = cols + (size_t)by * col_stride + (size_t)bx * N2;
     TableLoad tl = table_load(tw, T.twi_n2, N2 / 2, bar);
     NTT2_FOR(i, N2) x[tile_off(i, 0, 0)] = chunk[i];
     table_wait(tl, bar);
     NTT2_SYNC();
-    smem_dif(x, tw, T.n2, 0);
+    if constexpr (N2C >= 0) smem_dif_t<N2C, 0>(x, tw); else smem_dif(x, tw, n2, 0);
     NTT2_FOR(i, N2) chunk[i] = glf::canon_cc(x[tile_off(i, 0, 0)]);
 }
 // ---- forward, step 1: contiguous chunk p_hi = bx of work item by, staged coset twiddles ------------------
 static constexpr u32 FWD_LANES = 128;   // lanes of the inter-pass twiddle progression (independent of blockDim)
+template <int N1C = -1, int N2C = -1>
 GL_HD void fwd_contig_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, const mk::NttTables& T, const mk::PremulTables& Pm) {
-    u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tw_off(T.n2, 0); u64* bar = tw + N2;
+    const u32 n1 = N1C >= 0 ? (u32)N1C : T.n1, n2 = N2C >= 0 ? (u32)N2C : T.n2, n = N1C >= 0 && N2C >= 0 ? (u32)(N1C + N2C) : T.n;
+    u32 N1 = 1u << n1, N2 = 1u << n2;
+    u64* x = sm; u64* tw = sm + tw_off(n2, 0); u64* bar = tw + N2;
     mk::FwdItem it = items[by];
     u32 p_hi = bx;
-    u32 j1 = gl::bitrev32(p_hi, T.n1);
+    u32 j1 = gl::bitrev32(p_hi, n1);
     const u64* src = it.src + (size_t)p_hi * N2;
     u64* dst = it.dst + (size_t)p_hi * N2;
     u64 fb = Pm.tab_b[(size_t)it.base * N1 + j1];              // g^j1 / N
@@ -234,26 +264,29 @@ GL_HD void fwd_contig_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, c
     NTT2_FOR(i, N2) x[tile_off(i, 0, 0)] = src[i];
     table_wait(tl, bar);
     NTT2_SYNC();
-    smem_dit<true>(x, tw, T.n2, 0);
+    if constexpr (N2C >= 0) smem_dit_t<true, N2C, 0>(x, tw); else smem_dit<true>(x, tw, n2, 0);
     // dst[k2] = x[k2] * fb * w_N^(j1 * k2): lane l walks k2 = l, l + LANES, ... multiplying by w_N^(j1 * LANES)
     u32 lanes = N2 < FWD_LANES ? N2 : FWD_LANES;
     NTT2_FOR(l, lanes) {
         u64 f = fb, step = 1;
-        if (T.n1 > 0) {
-            u64 mask = ((u64)1 << T.n) - 1;
+        if (n1 > 0) {
+            u64 mask = ((u64)1 << n) - 1;
             f = glf::mul(fb, w_pow(T.w_hi, T.w_lo, T.lo_bits, ((u64)j1 * l) & mask));
             step = w_pow(T.w_hi, T.w_lo, T.lo_bits, ((u64)j1 * lanes) & mask);
         }
         for (u32 k2 = l; k2 < N2; k2 += lanes) {
             dst[k2] = glf::cmul(x[tile_off(k2, 0, 0)], f);
-            if (T.n1 > 0) f = glf::mul(f, step);
+            if (n1 > 0) f = glf::mul(f, step);
         }
     }
 }
 // ---- forward, step 3: strided tile [N1][C], DIT along p_hi, in place ----------------------------------------
-GL_HD void fwd_strided_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, const mk::NttTables& T, u32 log_c) {
-    u32 C = 1u << log_c, N1 = 1u << T.n1, N2 = 1u << T.n2;
-    u64* x = sm; u64* tw = sm + tw_off(T.n1, log_c); u64* bar = tw + N1 / 2 + 2;
+template <int N1C = -1, int N2C = -1>
+GL_HD void fwd_strided_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, const mk::NttTables& T, u32 log_c_rt) {
+    const u32 n1 = N1C >= 0 ? (u32)N1C : T.n1, n2 = N2C >= 0 ? (u32)N2C : T.n2;
+    const u32 log_c = N1C >= 0 && N2C >= 0 ? (u32)(N1C >= 12 ? 0 : (12 - N1C < N2C ? 12 - N1C : N2C)) : log_c_rt;
+    u32 C = 1u << log_c, N1 = 1u << n1, N2 = 1u << n2;
+    u64* x = sm; u64* tw = sm + tw_off(n1, log_c); u64* bar = tw + N1 / 2 + 2;
     u64* col = items[by].dst;
     u32 k2_0 = bx * C;
     TableLoad tl = table_load(tw, T.tw_n1, N1 / 2, bar);
@@ -263,7 +296,8 @@ GL_HD void fwd_strided_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, 
     }
     table_wait(tl, bar);
     NTT2_SYNC();
-    smem_dit<false>(x, tw, T.n1, log_c);
+    if constexpr (N1C >= 0 && N2C >= 0) smem_dit_t<false, N1C, (N1C >= 12 ? 0 : (12 - N1C < N2C ? 12 - N1C : N2C))>(x, tw);
+    else smem_dit<false>(x, tw, n1, log_c);
     NTT2_FOR(idx, N1 * C) {
         u32 k1 = idx >> log_c, cc = idx & (C - 1);
         col[(size_t)k1 * N2 + k2_0 + cc] = glf::canon_cc(x[tile_off(k1, cc, log_c)]);

@@ -49,28 +49,46 @@ static std::vector<u64> naive_dft(const std::vector<u64>& a, u64 w) {
     return o;
 }
 
-static void run_intt(std::vector<u64>& col, const mk::NttTables& T, std::vector<u64>& sm) {
+// `specialised` = the instantiation with the split as compile-time constants that kernels.cu launches for this size
+// (NTT_SPECIALISED there); otherwise the run-time schedules.  Both must give the same words.
+template <int N1C, int N2C>
+static void run_intt_t(std::vector<u64>& col, const mk::NttTables& T, std::vector<u64>& sm) {
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
     size_t N = (size_t)1 << T.n;
     if (T.n1 > 0) {
         u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;      // launch_intt (kernels.cu)
         sm.assign(ntt2::smem_words_strided(T.n1, log_c), 0xDEADBEEFDEADBEEFull);
-        for (u32 bx = 0; bx < (N2 >> log_c); bx++) ntt2::intt_strided_block(bx, 0, sm.data(), col.data(), N, T, log_c);
+        for (u32 bx = 0; bx < (N2 >> log_c); bx++) ntt2::intt_strided_block<N1C, N2C>(bx, 0, sm.data(), col.data(), N, T, log_c);
     }
     sm.assign(ntt2::smem_words_contig_inv(T.n2), 0xDEADBEEFDEADBEEFull);
-    for (u32 bx = 0; bx < N1; bx++) ntt2::intt_contig_block(bx, 0, sm.data(), col.data(), N, T);
+    for (u32 bx = 0; bx < N1; bx++) ntt2::intt_contig_block<N2C>(bx, 0, sm.data(), col.data(), N, T);
 }
-static void run_fwd(const std::vector<mk::FwdItem>& items, const mk::NttTables& T, const mk::PremulTables& Pm, std::vector<u64>& sm) {
+template <int N1C, int N2C>
+static void run_fwd_t(const std::vector<mk::FwdItem>& items, const mk::NttTables& T, const mk::PremulTables& Pm, std::vector<u64>& sm) {
     u32 N1 = 1u << T.n1, N2 = 1u << T.n2;
     sm.assign(ntt2::smem_words_contig_fwd(T.n2), 0xDEADBEEFDEADBEEFull);
     for (u32 by = 0; by < items.size(); by++)
-        for (u32 bx = 0; bx < N1; bx++) ntt2::fwd_contig_block(bx, by, sm.data(), items.data(), T, Pm);
+        for (u32 bx = 0; bx < N1; bx++) ntt2::fwd_contig_block<N1C, N2C>(bx, by, sm.data(), items.data(), T, Pm);
     if (T.n1 > 0) {
         u32 log_c = T.n1 >= 12 ? 0 : 12 - T.n1; if (log_c > T.n2) log_c = T.n2;      // launch_fwd_ntt (kernels.cu)
         sm.assign(ntt2::smem_words_strided(T.n1, log_c), 0xDEADBEEFDEADBEEFull);
         for (u32 by = 0; by < items.size(); by++)
-            for (u32 bx = 0; bx < (N2 >> log_c); bx++) ntt2::fwd_strided_block(bx, by, sm.data(), items.data(), T, log_c);
+            for (u32 bx = 0; bx < (N2 >> log_c); bx++) ntt2::fwd_strided_block<N1C, N2C>(bx, by, sm.data(), items.data(), T, log_c);
     }
+}
+#define NTT_SPECIALISED(X) X(8, 8) X(8, 9) X(9, 9) X(9, 10) X(10, 10) X(10, 11) X(11, 11)
+static bool g_generic_only = false;
+static void run_intt(std::vector<u64>& col, const mk::NttTables& T, std::vector<u64>& sm) {
+#define X(a, b) if (!g_generic_only && T.n1 == a && T.n2 == b) { run_intt_t<a, b>(col, T, sm); return; }
+    NTT_SPECIALISED(X)
+#undef X
+    run_intt_t<-1, -1>(col, T, sm);
+}
+static void run_fwd(const std::vector<mk::FwdItem>& items, const mk::NttTables& T, const mk::PremulTables& Pm, std::vector<u64>& sm) {
+#define X(a, b) if (!g_generic_only && T.n1 == a && T.n2 == b) { run_fwd_t<a, b>(items, T, Pm, sm); return; }
+    NTT_SPECIALISED(X)
+#undef X
+    run_fwd_t<-1, -1>(items, T, Pm, sm);
 }
 
 static void test_size(u32 n, u32 log_blowup) {
@@ -143,6 +161,10 @@ int main(int argc, char** argv) {
     u32 max_n = argc > 1 ? (u32)atoi(argv[1]) : 16;
     for (u32 n = 1; n <= 22; n++) test_table_layout(n);
     for (u32 n = 1; n <= max_n; n++) test_size(n, n % 3 == 0 ? 2 : 3);
+    // sizes with a specialised instantiation once more through the run-time schedules
+    g_generic_only = true;
+    for (u32 n = 16; n <= max_n; n++) test_size(n, 3);
+    g_generic_only = false;
     if (fails) { printf("NTT_V2_FAILED %d\n", fails); return 1; }
     printf("NTT_V2_OK up to 2^%u\n", max_n);
     return 0;

@@ -22,5 +22,5 @@ def test_ntt_v2_block_functions_on_host():
     transform and all cosets of the LDE for 2^1 .. 2^16 (both the single-pass and the two-pass split) against a
     textbook transform; also pins the table layout the first-generation kernels read."""
     subprocess.check_call(["make", "-s", "-C", CPP, "test_ntt_v2"])
-    r = subprocess.run([os.path.join(CPP, "test_ntt_v2"), "16"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([os.path.join(CPP, "test_ntt_v2"), "19"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "NTT_V2_OK" in r.stdout, r.stdout + r.stderr
