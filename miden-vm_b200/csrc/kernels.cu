@@ -1012,6 +1012,25 @@ void launch_ood_reduce(const u64* partial, u32 n_cols, u32 n_chunks, u64* out, c
 // =============================================================================================
 // DEEP quotient
 // =============================================================================================
+// 160-bit accumulator of unreduced 64 x 64 -> 128-bit products
+struct Acc160 { u64 lo, mid; u32 hi; };
+__device__ __forceinline__ void acc_mul(Acc160& A, u64 x, u64 y) {
+    unsigned __int128 q = (unsigned __int128)x * y;
+    u64 ql = (u64)q, qh = (u64)(q >> 64);
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(A.lo), "+l"(A.mid), "+r"(A.hi) : "l"(ql), "l"(qh));
+#else
+    unsigned __int128 s0 = (unsigned __int128)A.lo + ql;
+    unsigned __int128 s1 = (unsigned __int128)A.mid + qh + (u64)(s0 >> 64);
+    A.lo = (u64)s0; A.mid = (u64)s1; A.hi += (u32)(s1 >> 64);
+#endif
+}
+// lo + mid * 2^64 + hi * 2^128 mod p, canonical.  2^64 = 2^32 - 1 and 2^96 = -1, so 2^128 = -2^32: the first two words go
+// through the ordinary 128-bit reduction, and hi * 2^32 (< p for every hi < 2^32) is subtracted.
+__device__ __forceinline__ u64 acc_reduce(const Acc160& A) {
+    u64 r = glf::canon_cc(glf::red128(A.lo, A.mid));
+    return glf::csub(r, (u64)A.hi << 32);
+}
 struct DeepKArgs {
     const DeepMat* m; int n_mats;
     u32 log_n, log_b;
@@ -1030,7 +1049,12 @@ __global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
     if (pos >= ((size_t)a.nt << a.log_n)) return;
     pos += (size_t)a.t0 << a.log_n;
     u32 t = (u32)(pos >> a.log_n), r = (u32)(pos & (((size_t)1 << a.log_n) - 1));
-    E2 fr = gl::e2(0, 0);
+    // f_red(x) = sum_i alpha^(W-1-i) col_i(x): two base-field dot products (one per extension coordinate of the alpha
+    // powers).  The 128-bit products are accumulated UNREDUCED in 160-bit accumulators and reduced once at the end
+    // (at most 2^32 terms fit; a proof has a few hundred columns): a column costs two wide multiplications and two
+    // three-word additions instead of two modular multiplications and their reductions (ncu r2b: the kernel was bound by
+    // the integer pipes at ~85 instructions per column, not by HBM).
+    Acc160 fa{0, 0, 0}, fb{0, 0, 0};
     for (int m = 0; m < a.n_mats; m++) {
         const DeepMat M = a.m[m];
         size_t Lm = (size_t)1 << (M.log_n + a.log_b);
@@ -1041,19 +1065,17 @@ __global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
         for (; c + 4 <= M.width; c += 4) {
             u64 v0 = base[(size_t)c * Lm], v1 = base[(size_t)(c + 1) * Lm];
             u64 v2 = base[(size_t)(c + 2) * Lm], v3 = base[(size_t)(c + 3) * Lm];
-            glf::W wa = glf::wide(glf::mul(ap[2 * c], v0)), wb = glf::wide(glf::mul(ap[2 * c + 1], v0));
-            glf::wadd(wa, glf::mul(ap[2 * c + 2], v1)); glf::wadd(wb, glf::mul(ap[2 * c + 3], v1));
-            glf::wadd(wa, glf::mul(ap[2 * c + 4], v2)); glf::wadd(wb, glf::mul(ap[2 * c + 5], v2));
-            glf::wadd(wa, glf::mul(ap[2 * c + 6], v3)); glf::wadd(wb, glf::mul(ap[2 * c + 7], v3));
-            glf::wadd(wa, fr.a); glf::wadd(wb, fr.b);
-            fr.a = glf::canon_cc(glf::wred(wa)); fr.b = glf::canon_cc(glf::wred(wb));
+            acc_mul(fa, ap[2 * c], v0); acc_mul(fb, ap[2 * c + 1], v0);
+            acc_mul(fa, ap[2 * c + 2], v1); acc_mul(fb, ap[2 * c + 3], v1);
+            acc_mul(fa, ap[2 * c + 4], v2); acc_mul(fb, ap[2 * c + 5], v2);
+            acc_mul(fa, ap[2 * c + 6], v3); acc_mul(fb, ap[2 * c + 7], v3);
         }
         for (; c < M.width; c++) {
             u64 v = base[(size_t)c * Lm];
-            fr.a = gl::add(fr.a, gl::mul(ap[2 * c], v));
-            fr.b = gl::add(fr.b, gl::mul(ap[2 * c + 1], v));
+            acc_mul(fa, ap[2 * c], v); acc_mul(fb, ap[2 * c + 1], v);
         }
     }
+    E2 fr = gl::e2(acc_reduce(fa), acc_reduce(fb));
     u64 x = gl::mul(gl::mul(a.shift, gl::pow(a.w_l, t)), w_pow(a.w_hi, a.w_lo, a.lo_bits, r));
     E2 d0 = gl::e2(gl::sub(a.z0.a, x), a.z0.b), d1 = gl::e2(gl::sub(a.z1.a, x), a.z1.b);
     E2 inv = gl::e2_inv(gl::e2_mul(d0, d1));
