@@ -86,7 +86,7 @@ static const char PRELUDE_FMUL_G1[] = R"CUDA(__device__ __forceinline__ u64 fmul
 }
 )CUDA";
 // second-generation multiplication (poseidon2_fast2.cuh: one 128-bit product, the carry folded by an IMAD.WIDE);
-// opt-in with MDN_JIT_ARITH=2 until it has been measured on the constraint kernels (tools/realistic_air_probe.py)
+// the default since it was measured on the constraint kernels (tools/realistic_air_probe.py, profiles/r2_tuning.md)
 static const char PRELUDE_FMUL_G2[] = R"CUDA(__device__ __forceinline__ u64 fmul(u64 x, u64 y) {
     unsigned __int128 q = (unsigned __int128)x * y;
     u64 lo = (u64)q, hi = (u64)(q >> 64);
@@ -138,7 +138,7 @@ struct GenInfo { uint32_t n_constraints = 0; bool uses_sel = false; uint32_t n_c
 // Leaves (trace cells, constants, challenges ...) are re-materialised in every chunk that reads them; arithmetic
 // values that live across a chunk boundary travel through two small per-thread arrays (Sb: base, Se: extension)
 // whose slots are assigned by chunk-granular liveness.
-inline bool jit_arith2() { const char* e = getenv("MDN_JIT_ARITH"); return e && atoi(e) == 2; }
+inline bool jit_arith2() { const char* e = getenv("MDN_JIT_ARITH"); return !(e && atoi(e) == 1); }   // default since r2: 44.2 -> 39.9 ms on the 7.3 k-node probe (profiles/r2_tuning.md); MDN_JIT_ARITH=1 restores the first generation
 inline uint32_t chunk_nodes() { const char* e = getenv("MDN_JIT_CHUNK"); uint32_t v = e ? (uint32_t)atoi(e) : 0; return v ? v : 512; }
 
 // lookup == true: `w` is a lowered LookupAir ("MLKP": 4-word interactions instead of constraint ids) and the

@@ -1062,6 +1062,7 @@ __global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
         const u64* base = M.base + pm;
         const u64* ap = sm_apow + 2 * M.alpha_off;
         u32 c = 0;
+        // four independent column loads in flight per thread (eight measured slower: 3.30 against 3.13 ms at 2^20)
         for (; c + 4 <= M.width; c += 4) {
             u64 v0 = base[(size_t)c * Lm], v1 = base[(size_t)(c + 1) * Lm];
             u64 v2 = base[(size_t)(c + 2) * Lm], v3 = base[(size_t)(c + 3) * Lm];
