@@ -1051,21 +1051,30 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
         CUDA_OK(cudaStreamWaitEvent(copy_stream, copy_ev[7], 0));
         mk::PeerPtrs bad{};
         for (u32 g = 0; g < shard_world; g++) bad.p[g] = sync_flags.p[g] + 16;
-        for (u32 j = 0; j < k; j++) {
+        // smallest matrix first, and the LDE of a matrix is queued as soon as every rank's slice of it has arrived, so
+        // the copies of the later matrices (copy stream) hide behind the LDE of the earlier ones, as on one GPU
+        std::vector<u32> by_size(k);
+        for (u32 j = 0; j < k; j++) by_size[j] = j;
+        std::stable_sort(by_size.begin(), by_size.end(), [&](u32 a, u32 b) { return staging[a].n < staging[b].n; });
+        for (u32 q = 0; q < k; q++) {
+            const u32 j = by_size[q];
             const mdn_matrix& m = traces[order[j]];
             CommittedMat& cm = main_c.mats[j];
             const bool whole = cm.log_n < lg + 5;
             size_t rows = slice_rows(cm.log_n), row0 = whole ? 0 : rows * shard_rank;
             host_to_device(staging[j].p, m.values + row0 * cm.width, rows * cm.width);
-            CUDA_OK(cudaEventRecord(copy_ev[j % 7], copy_stream));
-            CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[j % 7], 0));
-            ProfScope ps(prof, PC_TRANSPOSE);
-            if (whole) mk::launch_transpose_rm_to_cm(staging[j].p, cm.coef, 1u << cm.log_n, cm.width, (u32*)d_flag.p, stream);
-            else mk::launch_transpose_slice_push(staging[j].p, peers_of(cm.coef), bad, shard_world, (u32)row0, (u32)rows, 1u << cm.log_n, cm.width, stream);
+            CUDA_OK(cudaEventRecord(copy_ev[q % 7], copy_stream));
+            CUDA_OK(cudaStreamWaitEvent(stream, copy_ev[q % 7], 0));
+            {
+                ProfScope ps(prof, PC_TRANSPOSE);
+                if (whole) mk::launch_transpose_rm_to_cm(staging[j].p, cm.coef, 1u << cm.log_n, cm.width, (u32*)d_flag.p, stream);
+                else mk::launch_transpose_slice_push(staging[j].p, peers_of(cm.coef), bad, shard_world, (u32)row0, (u32)rows, 1u << cm.log_n, cm.width, stream);
+            }
+            shard_barrier();                   // every rank's slice of this matrix has arrived everywhere
+            if (q + 1 == k) CUDA_OK(cudaEventRecord(ev[1], stream));
+            keep_raw_main(j);
+            lde_matrix(cm);
         }
-        shard_barrier();                       // every rank's slices have arrived everywhere
-        CUDA_OK(cudaEventRecord(ev[1], stream));
-        for (u32 j = 0; j < k; j++) { keep_raw_main(j); lde_matrix(main_c.mats[j]); }
     } else if (!on_device) {
         for (u32 j = 0; j < k; j++) staging[j].alloc(((size_t)1 << main_c.mats[j].log_n) * main_c.mats[j].width, stream);
         CUDA_OK(cudaEventRecord(copy_ev[7], stream));
