@@ -652,6 +652,50 @@ def test_staged_api_matches_one_shot(sess_fast):
     assert lib.mdn_prove_finish(h, C.byref(proof)) != 0
 
 
+def test_external_assertions_hook(sess_fast):
+    """`Statement::eval_external` (mdn_session_set_external_check): called once per proof, after the aux traces exist --
+    here the LogUp aux trace is built ON THE DEVICE, so its committed final reaches the host only through this call --
+    and before the aux commitment; a failing assertion aborts the proof with MDN_ERR_EXTERNAL_ASSERTION
+    (`ProverError::ExternalAssertionFailed`, prover/mod.rs:383-395) and the session stays usable."""
+    import test_airs
+    params = W.fast_pcs_params()
+    wl, _ = test_airs.logup_workload(6, device=True)
+    ch = W.initial_challenger(params, prod_observe)
+    calls = []
+
+    def ok(chal, aux_values, heights):
+        calls.append((chal.copy(), [a.copy() for a in aux_values], heights))
+        return None
+    sess_fast.set_external_check(ok)
+    try:
+        heights, fields, comms = sess_fast.prove(wl.statement, wl.matrices, ch)
+        assert len(calls) == 1
+        chal, aux_values, hs = calls[0]
+        assert len(chal) == 4 and hs == bytes(wl.log_heights) and len(aux_values) == 1 and len(aux_values[0]) == 2
+        assert np.array_equal(aux_values[0], fields[:2])        # the device-built final is what gets committed next
+        sess_fast.set_external_check(lambda c, a, h: 0)         # assertion 0 evaluates to non-zero
+        with pytest.raises(B.ProverError, match=r"\[-7\] external assertion 0 failed"):
+            sess_fast.prove(wl.statement, wl.matrices, ch)
+    finally:
+        sess_fast.set_external_check(None)
+    again = sess_fast.prove(wl.statement, wl.matrices, ch)
+    assert np.array_equal(again[1], fields) and np.array_equal(again[2], comms)
+
+
+def test_non_canonical_statement_values_rejected(sess_fast):
+    """Public values and observed statement felts must be canonical (< p), like every other input."""
+    params = W.fast_pcs_params()
+    ch = W.initial_challenger(params, prod_observe)
+    wl = W.Workload([5], widths=(9,), aux_widths=(1,), public_values=(1, 2))
+    wl.public_values[1] = np.uint64(P)
+    with pytest.raises(B.ProverError, match=r"\[-1\] public value 1"):
+        sess_fast.prove(wl.statement, wl.matrices, ch)
+    wl.public_values[1] = 2
+    wl.observe_felts[0] = np.uint64(2**64 - 1)
+    with pytest.raises(B.ProverError, match=r"\[-1\] observed statement felt 0"):
+        sess_fast.prove(wl.statement, wl.matrices, ch)
+
+
 def test_two_sessions_are_independent():
     params = W.fast_pcs_params()
     a, b = B.Session(params, 0), B.Session(params, 0)
