@@ -591,22 +591,22 @@ void mdn_session::build_tree(Committed& c) {
     mk::PushDst dig = push_dst(c.tree.layer(depth), sh ? (split ? mk::PUSH_OWNER : mk::PUSH_ALL) : mk::PUSH_LOCAL, depth - (split ? lg : 0));
     shard_barrier();   // the tree buffer is a fresh allocation: no rank may still be using the memory under its old identity
     DevBuf states_a, states_b;
+    // One launch absorbs up to 8 matrices of one height (launch-argument space); a taller pile of equal-height matrices
+    // is absorbed in several launches that hand the sponge states on through the SoA state buffers, exactly like the
+    // hand-over between height groups.
     const u64* prev = nullptr; u32 prev_log = 0;
     size_t i = 0;
     while (i < c.mats.size()) {
         size_t j = i;
         mk::LeafArgs args; args.n_mats = 0;
-        while (j < c.mats.size() && c.mats[j].log_n == c.mats[i].log_n) {
+        const u32 ln = c.mats[i].log_n;
+        while (j < c.mats.size() && c.mats[j].log_n == ln && args.n_mats < 8) {
             // a zero-width matrix is a no-op for the sponge (an empty absorb leaves the state untouched) but not for the
             // chaining hasher, which re-hashes its state (crates/stateful-hasher/src/chaining.rs:43-46)
-            if (c.mats[j].width || hash_kind == MDN_HASH_BLAKE3) {
-                if (args.n_mats == 8) fail(MDN_ERR_UNSUPPORTED, "more than 8 matrices of one height in a tree");
-                args.m[args.n_mats++] = mk::LeafMat{c.mats[j].lde, c.mats[j].width, 0};
-            }
+            if (c.mats[j].width || hash_kind == MDN_HASH_BLAKE3) args.m[args.n_mats++] = mk::LeafMat{c.mats[j].lde, c.mats[j].width, 0};
             j++;
         }
         bool last = (j == c.mats.size());
-        u32 ln = c.mats[i].log_n;
         DevBuf& out = (prev == states_a.p && prev) ? states_b : states_a;
         if (!last) out.alloc((size_t)12 << (ln + lb), stream);
         {
@@ -842,17 +842,6 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     if (st->n_observe_felts && !st->observe_felts) fail(MDN_ERR_INVALID_ARG, "observe_felts is NULL");
     for (u32 i = 0; i < st->n_public_values; i++) if (st->public_values[i] >= gl::P) fail(MDN_ERR_INVALID_ARG, "public value %u is not a canonical field element (>= p)", i);
     for (u32 i = 0; i < st->n_observe_felts; i++) if (st->observe_felts[i] >= gl::P) fail(MDN_ERR_INVALID_ARG, "observed statement felt %u is not a canonical field element (>= p)", i);
-    // limits of this backend, checked before any device work: 8 matrices of one height per tree (leaf-sponge launch
-    // arguments); the DEEP kernel takes its matrices in batches, so their number is not limited
-    {
-        std::map<u32, u32> per_height_main, per_height_aux;
-        for (u32 i = 0; i < st->n_airs; i++) {
-            if (st->airs[i].width) per_height_main[traces[i].log_height]++;
-            if (st->airs[i].aux_width) per_height_aux[traces[i].log_height]++;
-        }
-        for (auto* mp : {&per_height_main, &per_height_aux})
-            for (auto& kv : *mp) if (kv.second > 8) fail(MDN_ERR_UNSUPPORTED, "%u traces of height 2^%u in one commitment (at most 8 matrices of one height per tree)", kv.second, kv.first);
-    }
     bool on_device = (flags & MDN_FLAG_DEVICE_TRACES) != 0;
     if (shard_world > 1) {
         if (!use_arena) fail(MDN_ERR_UNSUPPORTED, "a proof split over several ranks needs the proof arena (unset MDN_NO_ARENA)");

@@ -129,6 +129,14 @@ def test_prove_bit_exact_mixed_heights(sess_fast):
     _compare_proofs(sess_fast, W.fast_pcs_params(), W.Workload([6, 8, 5], widths=(11, 9, 10), aux_widths=(2, 0, 1)))
 
 
+def test_prove_many_airs_of_one_height(sess_fast):
+    # more equal-height matrices than one leaf-sponge launch takes (8): the states are handed on between launches;
+    # 11 + 2 AIRs, so both the main and the aux tree chain launches and a second height group follows
+    k = 13
+    lhs = [5] * 11 + [7, 7]
+    _compare_proofs(sess_fast, W.fast_pcs_params(), W.Workload(lhs, widths=(9,) * k, aux_widths=(1,) * k))
+
+
 def test_prove_bit_exact_miden_shape_small(sess):
     _compare_proofs(sess, W.miden_pcs_params(), W.Workload([8, 7, 6]))
 
