@@ -50,6 +50,29 @@ GL_HD size_t smem_words_contig_fwd(u32 n2) { return (size_t)tw_off(n2, 0) + ((si
 GL_HD size_t smem_words_contig_inv(u32 n2) { return (size_t)tw_off(n2, 0) + ((size_t)1 << n2) / 2 + 4; }
 GL_HD size_t smem_words_strided(u32 n1, u32 log_c) { return (size_t)tw_off(n1, log_c) + ((size_t)1 << n1) / 2 + 4; }
 
+// Contiguous chunk <-> padded tile with 128-bit global accesses (two words per thread per access; chunks are 16-byte
+// aligned whenever they hold at least two words because every column and chunk length is a power of two).
+GL_HD void load_chunk(u64* x, const u64* src, u32 n) {
+#if defined(__CUDA_ARCH__)
+    if (n >= 2 && (((size_t)src) & 15) == 0) {
+        const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
+        NTT2_FOR(i, n / 2) { ulonglong2 v = s2[i]; x[tile_off(2 * i, 0, 0)] = v.x; x[tile_off(2 * i + 1, 0, 0)] = v.y; }
+        return;
+    }
+#endif
+    NTT2_FOR(i, n) x[tile_off(i, 0, 0)] = src[i];
+}
+GL_HD void store_chunk_canon(u64* dst, const u64* x, u32 n) {
+#if defined(__CUDA_ARCH__)
+    if (n >= 2 && (((size_t)dst) & 15) == 0) {
+        ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+        NTT2_FOR(i, n / 2) d2[i] = make_ulonglong2(glf::canon_cc(x[tile_off(2 * i, 0, 0)]), glf::canon_cc(x[tile_off(2 * i + 1, 0, 0)]));
+        return;
+    }
+#endif
+    NTT2_FOR(i, n) dst[i] = glf::canon_cc(x[tile_off(i, 0, 0)]);
+}
+
 // Stage `words` u64 of a table into shared memory.  On the device: one bulk asynchronous copy (cp.async.bulk -> mbarrier)
 // issued by thread 0 when the table is big enough and 16-byte aligned, overlapping the tile loads that follow; the
 // matching table_wait() must come before the first use.  Host / emulator / small tables: a plain strided loop.
@@ -240,11 +263,11 @@ GL_HD void intt_contig_block(u32 bx, u32 by, u64* sm, u64* cols, size_t col_stri
     u64* x = sm; u64* tw = sm + tw_off(n2, 0); u64* bar = tw + N2 / 2 + 2;
     u64* chunk = cols + (size_t)by * col_stride + (size_t)bx * N2;
     TableLoad tl = table_load(tw, T.twi_n2, N2 / 2, bar);
-    NTT2_FOR(i, N2) x[tile_off(i, 0, 0)] = chunk[i];
+    load_chunk(x, chunk, N2);
     table_wait(tl, bar);
     NTT2_SYNC();
     if constexpr (N2C >= 0) smem_dif_t<N2C, 0>(x, tw); else smem_dif(x, tw, n2, 0);
-    NTT2_FOR(i, N2) chunk[i] = glf::canon_cc(x[tile_off(i, 0, 0)]);
+    store_chunk_canon(chunk, x, N2);
 }
 // ---- forward, step 1: contiguous chunk p_hi = bx of work item by, staged coset twiddles ------------------
 static constexpr u32 FWD_LANES = 128;   // lanes of the inter-pass twiddle progression (independent of blockDim)
@@ -261,7 +284,7 @@ GL_HD void fwd_contig_block(u32 bx, u32 by, u64* sm, const mk::FwdItem* items, c
     u64 fb = Pm.tab_b[(size_t)it.base * N1 + j1];              // g^j1 / N
     const u64* tc = Pm.tab_c + (size_t)it.base * N2;           // staged twiddles of G = g^N1
     TableLoad tl = table_load(tw, tc, N2, bar);              // N2 - 1 staged twiddles + the unused last slot
-    NTT2_FOR(i, N2) x[tile_off(i, 0, 0)] = src[i];
+    load_chunk(x, src, N2);
     table_wait(tl, bar);
     NTT2_SYNC();
     if constexpr (N2C >= 0) smem_dit_t<true, N2C, 0>(x, tw); else smem_dit<true>(x, tw, n2, 0);
