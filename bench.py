@@ -33,6 +33,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "trace cells/sec proved"
 UNIT = "cells/s"
+HASH_IDS = {"poseidon2": 0, "blake3": 1, "keccak": 2}     # mdn_hash_kind / orc_set_hash
 
 
 def load_peaks():
@@ -95,7 +96,8 @@ class ClockSampler(threading.Thread):
 
 def workload_name(lh, hash_name="poseidon2"):
     """`config.workload` of BOTH arms (the driver compares the two lines' configs)."""
-    h = "Poseidon2 LMCS + duplex challenger" if hash_name == "poseidon2" else "Blake3_256 LMCS (chaining hasher) + hash challenger"
+    h = {"poseidon2": "Poseidon2 LMCS + duplex challenger", "blake3": "Blake3_256 LMCS (chaining hasher) + hash challenger",
+         "keccak": "Keccak LMCS (stateful sponge, rate 17) + Keccak-256 hash challenger"}[hash_name]
     return (f"synthetic 2^{lh} x (51,22,16) Miden-shaped prove (DummyMidenAir degree-9 constraint, zero aux 4/3/1 EF cols), "
             f"96-bit params: blowup 8, FRI arity 4, final degree 2^7, 27 queries, PoW 4/12/16, {h}")
 
@@ -126,9 +128,9 @@ def cpu_baseline(log_height, steps=1, warmup=0, budget_s=None, hash_name="poseid
     wl = W.Workload([log_height] * 3)
     ch = W.initial_challenger(params, H.oracle_observe)
     ob.lib().orc_set_hash.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
-    if hash_name == "blake3":
+    if hash_name != "poseidon2":
         init = W.initial_hash_challenger(params)
-        ob.lib().orc_set_hash(1, init, len(init))
+        ob.lib().orc_set_hash(HASH_IDS[hash_name], init, len(init))
     times, t_start, timed_target = [], time.perf_counter(), steps
     i = 0
     while len(times) < timed_target:
@@ -185,8 +187,8 @@ def main():
     ap.add_argument("--ref-log-height", type=int, default=0, help="CPU arm: 0 = the same height as --log-height")
     ap.add_argument("--cpu-log-height", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hash", choices=["poseidon2", "blake3"], default="poseidon2",
-                    help="STARK hash configuration: poseidon2 (the metric's; default) or blake3 (the CLI default hasher / blake3-bench, BASELINE config 3)")
+    ap.add_argument("--hash", choices=["poseidon2", "blake3", "keccak"], default="poseidon2",
+                    help="STARK hash configuration: poseidon2 (the metric's; default), blake3 (the CLI default hasher / blake3-bench, BASELINE config 3) or keccak")
     ap.add_argument("--sharding", choices=["coset", "proof"], default="coset",
                     help="N>1: 'coset' (default) = ONE proof split over the GPUs -- LDE cosets, leaf sponge, constraints, DEEP and FRI "
                          "folds per coset, Merkle sub-trees per leaf range, peer-memory stores over NVLink (strong scaling); "
@@ -236,8 +238,8 @@ def main():
         lib.mdn_challenger_observe(C.byref(c), B.ptr(np.ascontiguousarray(felts, dtype=np.uint64)), len(felts))
 
     ch = W.initial_challenger(params, observe)
-    if args.hash == "blake3":
-        sess.set_hash(B.HASH_BLAKE3, W.initial_hash_challenger(params))
+    if args.hash != "poseidon2":
+        sess.set_hash(HASH_IDS[args.hash], W.initial_hash_challenger(params))
         ch = None
 
     # device-resident copies (for `value`) and pinned host copies (for `e2e`)
@@ -298,8 +300,8 @@ def main():
             return hashlib.sha256(bytes(pf[0]) + np.ascontiguousarray(pf[1], dtype=np.uint64).tobytes()
                                   + np.ascontiguousarray(pf[2], dtype=np.uint64).tobytes()).digest()
         single = B.Session(params, local_rank)
-        if args.hash == "blake3":
-            single.set_hash(B.HASH_BLAKE3, W.initial_hash_challenger(params))
+        if args.hash != "poseidon2":
+            single.set_hash(HASH_IDS[args.hash], W.initial_hash_challenger(params))
         ref = single.prove(wl.statement, dev_m, ch, None, B.FLAG_DEVICE_TRACES)
         single.close()
         mine = [digest(proof), digest(proof_e), digest(ref)]
@@ -373,10 +375,10 @@ def main():
                     "ms_per_step": total_e / args.steps * 1e3, "per_step_ms": [round(x * 1e3, 2) for x in steps_e], "api": "mdn_prove (include/miden_b200.h) with pinned host RowMajorMatrix buffers"},
             "gpu_launches": (int(tim_v.kernel_launches) + int(tim_e.kernel_launches)) * args.steps,   # kernels of the K value steps + K e2e steps
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_fwd_contig + k_fwd_strided + k_intt_* (coset LDE: the dominant kernel class under Blake3)", "achieved": ntt_gbs, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_fwd_contig + k_fwd_strided + k_intt_* (coset LDE: the dominant kernel class under the byte-oriented hashes)", "achieved": ntt_gbs, "peak": peak,
                          "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": None, "peak_source": f"{peak_kind} copy bandwidth",
                          "note": "instruction-bound (ncu r2b: issue 61-65 %, ALU pipe 63-69 %, FMA-heavy 51-66 %; ~280 instructions per point per pass), see DESIGN.md section 5"}
-            if args.hash == "blake3" else
+            if args.hash != "poseidon2" else
                         {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon2 leaf sponge, main trace)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_kind} copy bandwidth",
                          "note": "integer-ALU bound by construction (14-16k instructions per permutation per 64 input bytes); HBM fraction is low on purpose, see `issue`",
@@ -395,13 +397,13 @@ def main():
         if world == 1:
             # checker leg (oracle as verifier, outside every timed region): the last e2e proof must verify
             import helpers as H
-            if args.hash == "blake3":
+            if args.hash != "poseidon2":
                 import oracle_binding as ob
                 ob.lib().orc_set_hash.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
                 init = W.initial_hash_challenger(params)
-                ob.lib().orc_set_hash(1, init, len(init))
+                ob.lib().orc_set_hash(HASH_IDS[args.hash], init, len(init))
             rc, err = H.oracle_verify(params, wl, ch if ch is not None else W.Challenger(), *proof_e)
-            if args.hash == "blake3":
+            if args.hash != "poseidon2":
                 ob.lib().orc_set_hash(0, None, 0)
             line["proof_verified_by_oracle"] = (rc == 0)
             if rc != 0:

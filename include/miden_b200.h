@@ -213,10 +213,15 @@ int mdn_session_set_external_check(mdn_session* s, mdn_external_check fn, void* 
  *   installed with mdn_session_set_hash_challenger (after `config.challenger()` + `observe_protocol_params` that is the
  *   input buffer: 32 bytes of relation digest + 8 parameter felts as little-endian u64, and an empty output buffer); the
  *   `challenger` argument of mdn_prove* is ignored and may be NULL.  A preprocessed bundle belongs to the hash it was
- *   committed under. */
-typedef enum { MDN_HASH_POSEIDON2 = 0, MDN_HASH_BLAKE3 = 1 } mdn_hash_kind;
+ *   committed under.
+ * MDN_HASH_KECCAK: `keccak_config` (:309-353) -- SerializingStatefulSponge<StatefulSponge<KeccakF, 25, 17, 4>> leaves (the
+ *   overwrite-mode sponge over the canonical u64 of every felt; alignment 17: opened rows and the OOD lists are zero-padded
+ *   to multiples of 17), PaddingFreeSponge<KeccakF, 25, 17, 4> nodes, SerializingChallenger64<Felt, HashChallenger<u8,
+ *   Keccak256Hash, 32>>.  Digests are four u64 lanes; the challenger is installed like the Blake3 one (its input buffer must
+ *   be whole 64-bit words, which `observe_slice(&relation_digest)` + `observe_protocol_params` always gives). */
+typedef enum { MDN_HASH_POSEIDON2 = 0, MDN_HASH_BLAKE3 = 1, MDN_HASH_KECCAK = 2 } mdn_hash_kind;
 int mdn_session_set_hash(mdn_session* s, mdn_hash_kind kind);
-/* p3 `HashChallenger<u8, Blake3, 32>`: `input_buffer`, `output_buffer` (bytes are sampled from its back). */
+/* p3 `HashChallenger<u8, Blake3 | Keccak256Hash, 32>`: `input_buffer`, `output_buffer` (bytes are sampled from its back). */
 typedef struct {
     const uint8_t* input_buffer;
     size_t input_len;

@@ -10,6 +10,7 @@
 #pragma once
 #include "poseidon2.cuh"
 #include "blake3.cuh"
+#include "keccak.cuh"
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -19,8 +20,9 @@ using gl::u64;
 using gl::u32;
 using gl::E2;
 
-// `hashed == true` turns the same object into p3's `SerializingChallenger64<Felt, HashChallenger<u8, Blake3, 32>>`, the
-// challenger of the Blake3_256 configuration (air/src/config.rs:292-293,304-305; p3-challenger 0.6.2 is not vendored, so
+// `hashed == true` turns the same object into p3's `SerializingChallenger64<Felt, HashChallenger<u8, H, 32>>`, the
+// challenger of the Blake3_256 (H = Blake3) and Keccak (H = Keccak-256) configurations (air/src/config.rs:292-293,304-305,
+// 335-336,350-351; p3-challenger 0.6.2 is not vendored, so
 // this restates the published crate -- parity unpinned like the duplex case):
 //   observe(felt) appends its canonical u64 as 8 little-endian bytes to the input buffer and clears the output buffer;
 //   a digest is observed as its 32 bytes; a sampled byte pops from the BACK of the output buffer, which is refilled by
@@ -31,11 +33,19 @@ struct Duplex {
     u64 in[8];
     u32 in_len = 0, out_len = 0;
     bool hashed = false;
+    bool keccak = false;      // hashed only: H = Keccak-256 (the Keccak configuration, air/src/config.rs:335-336) instead of Blake3
     std::vector<uint8_t> bin, bout;
 
     void observe_byte(uint8_t b) { bout.clear(); bin.push_back(b); }
     uint8_t sample_byte() {
-        if (bout.empty()) {
+        if (bout.empty() && keccak) {
+            kk::Hash256 h; h.init();           // every observation is 8 or 32 bytes: the buffer is whole 64-bit words
+            for (size_t i = 0; i + 8 <= bin.size(); i += 8) { u64 w = 0; for (int k = 0; k < 8; k++) w |= (u64)bin[i + k] << (8 * k); h.push64(w); }
+            u64 o[4]; h.finish(o);
+            bout.resize(32);
+            for (int i = 0; i < 32; i++) bout[i] = (uint8_t)(o[i / 8] >> (8 * (i % 8)));
+            bin = bout;
+        } else if (bout.empty()) {
             b3::Hasher h; h.init();
             for (size_t i = 0; i + 4 <= bin.size(); i += 4) h.push((u32)bin[i] | ((u32)bin[i + 1] << 8) | ((u32)bin[i + 2] << 16) | ((u32)bin[i + 3] << 24));
             u32 o[8]; h.finish(o);             // every observation is 8 or 32 bytes: the buffer is whole words

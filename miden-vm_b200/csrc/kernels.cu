@@ -19,6 +19,7 @@
 #include "ntt2.cuh"               // host-checked by tests/cpp/test_ntt_v2.cpp
 #endif
 #include "blake3.cuh"
+#include "keccak.cuh"
 #include <algorithm>
 #include <cstdio>
 
@@ -678,6 +679,122 @@ __global__ void __launch_bounds__(128) k_grind_b3(const u32* __restrict__ input,
 void launch_grind_b3(const u32* d_input_words, u32 n_words, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
     u64 mask = (1ull << bits) - 1;
     k_grind_b3<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_input_words, n_words, mask, start, count, d_result);
+    COUNT_LAUNCH();
+}
+
+// =============================================================================================
+// Keccak hashing: the reference's `HashFunction::Keccak` configuration (air/src/config.rs:309-353).
+//   leaf   : the same overwrite-mode stateful sponge as Poseidon2 (crates/stateful-hasher/src/field_sponge.rs:41-59) over 25 u64
+//            lanes with rate 17, fed the canonical u64 of every felt (serializing_sponge.rs:72-86); alignment 17
+//   node   : PaddingFreeSponge<KeccakF, 25, 17, 4> on the 8 words of two digests -- one permutation
+//   digest : lanes 0..4 = the four u64 slots of every tree
+// 25 lanes of state travel between height groups (SoA [25][B << log_n]).  Bit-wise work on the ALU pipe only: nothing of the
+// Goldilocks multiplier is involved, so these kernels are an independent load on the SM from the NTT / constraint kernels.
+// =============================================================================================
+__global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash_kk(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev, u32 prev_log_n,
+                                                               u64* __restrict__ states_out, PushDst dig, u32 has_dig, u32 t0, u32 nt) {
+    size_t L = (size_t)1 << (log_n + log_b);
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((size_t)nt << log_n)) return;
+    u32 t = t0 + (u32)(idx >> log_n);
+    u32 r = (u32)(idx & (((size_t)1 << log_n) - 1));
+    size_t pos = ((size_t)t << log_n) + r;
+    u64 st[25];
+    if (prev) {
+        size_t Lp = (size_t)1 << (prev_log_n + log_b);
+        size_t pp = ((size_t)t << prev_log_n) + (r & ((1u << prev_log_n) - 1));
+#pragma unroll
+        for (int k = 0; k < 25; k++) st[k] = prev[k * Lp + pp];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 25; k++) st[k] = 0;
+    }
+    for (int m = 0; m < a.n_mats; m++) {
+        const u64* base = a.m[m].base + pos;
+        u32 w = a.m[m].width;
+        for (u32 c0 = 0; c0 < w; c0 += 17) {
+#pragma unroll
+            for (u32 k = 0; k < 17; k++) st[k] = (c0 + k < w) ? base[(size_t)(c0 + k) * L] : 0ull;     // LDE values are canonical
+            kk::permute(st);
+        }
+    }
+    if (states_out) {
+#pragma unroll
+        for (int k = 0; k < 25; k++) states_out[k * L + pos] = st[k];
+    }
+    if (has_dig) {
+        size_t i = ((size_t)r << log_b) | t;
+        push_u2(dig, 2 * i, i, make_ulonglong2(st[0], st[1]));
+        push_u2(dig, 2 * i + 1, i, make_ulonglong2(st[2], st[3]));
+    }
+}
+void launch_leaf_hash_kk(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                         u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st) {
+    size_t cnt = (size_t)nt << log_n;
+    unsigned blocks = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
+    PushDst d = dig ? *dig : local_dst(nullptr);
+    k_leaf_hash_kk<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, d, dig ? 1u : 0u, t0, nt);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(128) k_compress_kk(const u64* __restrict__ ch, u64* __restrict__ par, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ulonglong2* c = reinterpret_cast<const ulonglong2*>(ch + i * 8);
+    ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2], b1 = c[3];
+    u64 l[4] = {a0.x, a0.y, a1.x, a1.y}, r[4] = {b0.x, b0.y, b1.x, b1.y}, o[4];
+    kk::compress2(l, r, o);
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(par + i * 4);
+    d[0] = make_ulonglong2(o[0], o[1]);
+    d[1] = make_ulonglong2(o[2], o[3]);
+}
+void launch_compress_layer_kk(const u64* children, u64* parents, size_t n_parents, cudaStream_t st) {
+    k_compress_kk<<<(unsigned)((n_parents + 127) / 128), 128, 0, st>>>(children, parents, n_parents);
+    COUNT_LAUNCH();
+}
+// FRI round leaf (fri/prover.rs:137-165): the sponge from the zero state over the row's 2^la extension values (2 * 2^la lanes)
+__global__ void __launch_bounds__(128) k_fri_leaf_kk(const u64* __restrict__ ev, size_t q, u32 la, PushDst dig, u32 log_b, u32 t0, u32 log_nt) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((q >> log_b) << log_nt)) return;
+    size_t i = ((idx >> log_nt) << log_b) | (t0 + (idx & ((1u << log_nt) - 1)));
+    const ulonglong2* e = reinterpret_cast<const ulonglong2*>(ev);
+    u64 st[25];
+#pragma unroll
+    for (int k = 0; k < 25; k++) st[k] = 0;
+    u32 n = 2u << la;                       // lanes in the row (4, 8 or 16: one chunk of the rate)
+#pragma unroll
+    for (u32 j = 0; j < 8; j++) {
+        if (2 * j < n) {
+            ulonglong2 v = e[i + (size_t)gl::bitrev32(j, la) * q];
+            st[2 * j] = v.x; st[2 * j + 1] = v.y;
+        }
+    }
+    kk::permute(st);
+    push_u2(dig, 2 * i, i, make_ulonglong2(st[0], st[1]));
+    push_u2(dig, 2 * i + 1, i, make_ulonglong2(st[2], st[3]));
+}
+void launch_fri_leaf_hash_kk(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st) {
+    if (rows < ((size_t)1 << log_b)) { log_b = 0; t0 = 0; nt = 1; }
+    size_t cnt = (rows >> log_b) * nt;
+    k_fri_leaf_kk<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(evals, rows, log_arity, digests, log_b, t0, log2_exact(nt));
+    COUNT_LAUNCH();
+}
+// Proof-of-work for the Keccak-256 hash challenger: like k_grind_b3, over whole 64-bit words of the input buffer; the first
+// sampled u64 is u64::from_le_bytes([out[31], ..., out[24]]) = lane 3 of the output with its bytes reversed.
+__global__ void __launch_bounds__(128) k_grind_kk(const u64* __restrict__ input, u32 n_words, u64 mask, u64 start, u64 count, u64* result) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    u64 w = start + idx;
+    kk::Hash256 h; h.init();
+    for (u32 i = 0; i < n_words; i++) h.push64(input[i]);
+    h.push64(w);
+    u64 o[4];
+    h.finish(o);
+    u64 v = ((u64)b3::bswap((u32)o[3]) << 32) | (u64)b3::bswap((u32)(o[3] >> 32));
+    if ((v & mask) == 0) atomicMin(reinterpret_cast<unsigned long long*>(result), (unsigned long long)w);
+}
+void launch_grind_kk(const u64* d_input_words, u32 n_words, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
+    u64 mask = (1ull << bits) - 1;
+    k_grind_kk<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_input_words, n_words, mask, start, count, d_result);
     COUNT_LAUNCH();
 }
 

@@ -114,6 +114,12 @@ void launch_leaf_hash_b3(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64
 void launch_compress_layer_b3(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
 void launch_fri_leaf_hash_b3(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st);
 void launch_grind_b3(const u32* d_input_words, u32 n_words, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st);
+// the Keccak configuration: same contracts; the states between height groups are SoA [25][B << log_n]
+void launch_leaf_hash_kk(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                         u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st);
+void launch_compress_layer_kk(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
+void launch_fri_leaf_hash_kk(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st);
+void launch_grind_kk(const u64* d_input_words, u32 n_words, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // Constraints / quotient

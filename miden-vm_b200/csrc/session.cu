@@ -205,14 +205,17 @@ struct mdn_session {
     // STARK hash configuration (mdn_session_set_hash): Poseidon2 sponge + duplex challenger (default) or Blake3 chaining
     // hasher + hash challenger (air/src/config.rs:276-307).  `align` = LMCS alignment: 8 (sponge rate) or 1 (chaining).
     int hash_kind = MDN_HASH_POSEIDON2;
-    u32 align() const { return hash_kind == MDN_HASH_BLAKE3 ? 1u : 8u; }
+    u32 align() const { return hash_kind == MDN_HASH_BLAKE3 ? 1u : hash_kind == MDN_HASH_KECCAK ? 17u : 8u; }
+    u32 state_words() const { return hash_kind == MDN_HASH_KECCAK ? 25u : 12u; }      // leaf state handed on between height groups
     std::vector<uint8_t> hash_ch_in, hash_ch_out;          // pre-bound HashChallenger state (mdn_session_set_hash_challenger)
     void hash_leaves(const mk::LeafArgs& a, u32 ln, u32 lb, const u64* prev, u32 prev_log, u64* states_out, const mk::PushDst* dig, u32 tb, u32 tn) {
         if (hash_kind == MDN_HASH_BLAKE3) mk::launch_leaf_hash_b3(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
+        else if (hash_kind == MDN_HASH_KECCAK) mk::launch_leaf_hash_kk(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
         else mk::launch_leaf_hash(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
     }
     void compress_layer(const u64* children, u64* parents, size_t n) {
         if (hash_kind == MDN_HASH_BLAKE3) mk::launch_compress_layer_b3(children, parents, n, stream);
+        else if (hash_kind == MDN_HASH_KECCAK) mk::launch_compress_layer_kk(children, parents, n, stream);
         else mk::launch_compress_layer(children, parents, n, stream);
     }
     mdn_external_check external_check = nullptr; void* external_ctx = nullptr;   // Statement::eval_external (mdn_session_set_external_check)
@@ -525,7 +528,7 @@ void mdn_session::upload_matrix(const mdn_matrix& m, bool on_device, u64* dst_cm
 //   build_aligned_tree (:178; lmcs/lifted_tree.rs:202-284)
 void mdn_session::lde_matrix(CommittedMat& m) {
     if (!m.width) return;
-    u32 lb = params.log_blowup, B = 1u << lb;
+    u32 lb = params.log_blowup;
     size_t N = (size_t)1 << m.log_n, L = N << lb;
     NttPlan& plan = ntt(m.log_n);
     PremulPlan& pm = premul_trace(m.log_n);
@@ -543,7 +546,6 @@ void mdn_session::lde_matrix(CommittedMat& m) {
     // this rank's cosets only (all B of them on one GPU); column groups sized so a group's LDE (the fwd passes'
     // working set) stays L2-resident
     const u32 tb = t0(), tn = nt();
-    (void)B;
     size_t col_bytes = (size_t)tn * N * sizeof(u64);
     u32 group = (u32)std::max<size_t>(1, (48u << 20) / col_bytes);
     std::vector<mk::FwdItem> items;
@@ -608,12 +610,13 @@ void mdn_session::build_tree(Committed& c) {
         }
         bool last = (j == c.mats.size());
         DevBuf& out = (prev == states_a.p && prev) ? states_b : states_a;
-        if (!last) out.alloc((size_t)12 << (ln + lb), stream);
+        if (!last) out.alloc((size_t)state_words() << (ln + lb), stream);
         {
             ProfScope ps(prof, PC_LEAF);
             size_t Lg = (size_t)tn << ln;
-            for (int q = 0; q < args.n_mats; q++) { leaf_bytes += (double)Lg * args.m[q].width * 8.0; perms += Lg * ((args.m[q].width + 7) / 8); }
-            leaf_bytes += last ? (double)Lg * 32.0 : (double)Lg * 96.0;
+            const u32 rate = hash_kind == MDN_HASH_KECCAK ? 17 : 8;
+            for (int q = 0; q < args.n_mats; q++) { leaf_bytes += (double)Lg * args.m[q].width * 8.0; perms += Lg * ((args.m[q].width + rate - 1) / rate); }
+            leaf_bytes += last ? (double)Lg * 32.0 : (double)Lg * 8.0 * state_words();
             hash_leaves(args, ln, lb, prev, prev_log, last ? nullptr : out.p, last ? &dig : nullptr, tb, tn);
         }
         prev = out.p; prev_log = ln;
@@ -652,7 +655,7 @@ u64 mdn_session::grind(u32 bits) {
     if (ch.hashed) {
         // hash challenger: a candidate w is checked by hashing (input buffer || w as 8 little-endian bytes) and reading
         // the low bits of the first sampled u64; the buffer is whole 32-bit words (every observation is 8 or 32 bytes)
-        if (ch.bin.size() % 4) fail(MDN_ERR_INVALID_ARG, "hash challenger input buffer is not a whole number of words");
+        if (ch.bin.size() % (ch.keccak ? 8 : 4)) fail(MDN_ERR_INVALID_ARG, "hash challenger input buffer is not a whole number of words");
         u32 nw = (u32)(ch.bin.size() / 4);
         DevBuf d; d.alloc((nw + 1) / 2 + 2, stream);
         u64 none = ~0ull;
@@ -663,7 +666,8 @@ u64 mdn_session::grind(u32 bits) {
         ProfScope ps(prof, PC_GRIND);
         while (found == ~0ull) {
             if (start >= gl::P) fail(MDN_ERR_INVALID_ARG, "proof-of-work search exhausted");
-            mk::launch_grind_b3((const u32*)(d.p + 1), nw, bits, start, batch, d.p, stream);
+            if (ch.keccak) mk::launch_grind_kk(d.p + 1, nw / 2, bits, start, batch, d.p, stream);
+            else mk::launch_grind_b3((const u32*)(d.p + 1), nw, bits, start, batch, d.p, stream);
             CUDA_OK(cudaMemcpyAsync(&found, d.p, sizeof(u64), cudaMemcpyDeviceToHost, stream));
             CUDA_OK(cudaStreamSynchronize(stream));
             start += batch;
@@ -994,8 +998,9 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
 
     // challenger: caller's pre-bound state, then Statement::observe + observe_shape (mod.rs:290-291)
     Duplex& ch = tr.ch;
-    if (hash_kind == MDN_HASH_BLAKE3) {
-        ch.hashed = true; ch.bin = hash_ch_in; ch.bout = hash_ch_out;      // mdn_session_set_hash_challenger
+    if (hash_kind != MDN_HASH_POSEIDON2) {
+        ch.hashed = true; ch.keccak = (hash_kind == MDN_HASH_KECCAK); ch.bin = hash_ch_in; ch.bout = hash_ch_out;      // mdn_session_set_hash_challenger
+        if (ch.keccak && ch.bin.size() % 8) fail(MDN_ERR_INVALID_ARG, "Keccak hash challenger: the input buffer must be whole 64-bit words");
     } else {
         if (!chal) fail(MDN_ERR_INVALID_ARG, "null challenger");
         for (int i = 0; i < 12; i++) ch.st[i] = chal->sponge_state[i];
@@ -1662,6 +1667,7 @@ void mdn_session::finish() {
             ProfScope ps(prof, PC_FRI);
             perms += (q * (la == 3 ? 2 : 1) + q - 1) / (in_sh ? shard_world : 1);
             if (hash_kind == MDN_HASH_BLAKE3) mk::launch_fri_leaf_hash_b3(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
+            else if (hash_kind == MDN_HASH_KECCAK) mk::launch_fri_leaf_hash_kk(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
             else mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
         }
         if (in_sh) shard_barrier();
@@ -2151,7 +2157,7 @@ int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_all
 
 int mdn_session_set_hash(mdn_session* s, mdn_hash_kind kind) {
     if (!s) return MDN_ERR_INVALID_ARG;
-    if (kind != MDN_HASH_POSEIDON2 && kind != MDN_HASH_BLAKE3) { s->error = "unknown hash configuration"; return MDN_ERR_UNSUPPORTED; }
+    if (kind != MDN_HASH_POSEIDON2 && kind != MDN_HASH_BLAKE3 && kind != MDN_HASH_KECCAK) { s->error = "unknown hash configuration"; return MDN_ERR_UNSUPPORTED; }
     if (s->in_proof) { s->error = "mdn_session_set_hash called inside a proof"; return MDN_ERR_INVALID_ARG; }
     if (s->has_prep && kind != s->hash_kind) { s->error = "the preprocessed bundle was committed under the other hash: remove it first"; return MDN_ERR_INVALID_ARG; }
     s->hash_kind = kind;

@@ -182,20 +182,23 @@ void orc_lmcs_commit(const orc_matrix* mats, uint32_t n, uint64_t root[4], uint6
     }
 }
 
-// STARK hash configuration of every later call (0 = Poseidon2, the default; 1 = Blake3_256) and, for Blake3, the
+// STARK hash configuration of every later call (0 = Poseidon2, the default; 1 = Blake3_256; 2 = Keccak) and, for the two byte-oriented ones, the
 // pre-bound challenger = the bytes its HashChallenger input buffer holds after `config.challenger()` +
 // `observe_protocol_params` (air/src/config.rs:299-307,188-198); the `orc_challenger*` argument is then ignored.
 static std::vector<uint8_t> g_hash_challenger_input;
 int orc_set_hash(int kind, const uint8_t* challenger_input, size_t n) {
-    if (kind != 0 && kind != 1) return -1;
-    hash_kind() = kind ? H_BLAKE3 : H_POSEIDON2;
+    if (kind < 0 || kind > 2) return -1;
+    hash_kind() = kind == 2 ? H_KECCAK : kind ? H_BLAKE3 : H_POSEIDON2;
     g_hash_challenger_input.assign(challenger_input, challenger_input + (challenger_input ? n : 0));
     return 0;
 }
+// Keccak-256 (pad = 1) / SHA3-256 (pad = 6) of a byte string, and the permutation on 25 lanes
+void orc_keccak256(const uint8_t* p, size_t n, uint8_t pad, uint8_t out[32]) { auto h = keccak::hash256(p, n, pad); memcpy(out, h.data(), 32); }
+void orc_keccak_f(uint64_t st[25]) { std::array<u64, 25> a; memcpy(a.data(), st, 200); keccak::permute(a); memcpy(st, a.data(), 200); }
 void orc_blake3(const uint8_t* p, size_t n, uint8_t out[32]) { auto h = blake3::hash(p, n); memcpy(out, h.data(), 32); }
 
 static Challenger to_challenger(const orc_challenger* c) {
-    if (hash_kind() == H_BLAKE3) return Challenger::from_bytes(g_hash_challenger_input.data(), g_hash_challenger_input.size());
+    if (hash_kind() != H_POSEIDON2) return Challenger::from_bytes(g_hash_challenger_input.data(), g_hash_challenger_input.size());
     Challenger ch;
     for (int i = 0; i < 12; i++) ch.st[i] = Fp(c->sponge_state[i]);
     for (uint32_t i = 0; i < c->input_len; i++) ch.in_buf[i] = Fp(c->input_buffer[i]);
@@ -210,7 +213,7 @@ void orc_challenger_script(orc_challenger* c, const uint32_t* ops, const uint64_
     for (int i = 0; i < 12; i++) ch.st[i] = Fp(c->sponge_state[i]);
     for (uint32_t i = 0; i < c->input_len; i++) ch.in_buf[i] = Fp(c->input_buffer[i]);
     ch.in_len = c->input_len; ch.out_len = c->output_len;
-    if (hash_kind() == H_BLAKE3) ch = to_challenger(c);      // the hash challenger starts from the bytes given to orc_set_hash
+    if (hash_kind() != H_POSEIDON2) ch = to_challenger(c);      // the hash challenger starts from the bytes given to orc_set_hash
     for (size_t i = 0; i < n; i++) {
         switch (ops[i]) {
             case 0: ch.observe(Fp(args[i])); out[i] = 0; break;

@@ -13,6 +13,7 @@
 #include "poseidon2_x8.hpp"
 #include <algorithm>
 #include <map>
+#include <type_traits>
 
 namespace orc {
 
@@ -29,14 +30,14 @@ struct LmcsTree {
     unsigned depth() const { return log2_strict(height()); }
     const Digest& root() const { return layers[0][0]; }
 
-    static LmcsTree build(std::vector<Matrix> mats, size_t alignment) {
-        LmcsTree t;
-        t.alignment = alignment;
-        t.leaves = std::move(mats);
-        size_t H = t.leaves.back().height;
-        std::vector<State> states(H);
-        size_t active = t.leaves.front().height;
-        for (const Matrix& m : t.leaves) {
+    // leaf states per height group (nearest-neighbour duplication between heights), squeezed in domain order; `St` is the
+    // state of the configured stateful hasher (12 felts: Poseidon2 sponge / Blake3 chaining state in the first 4; 25 lanes: Keccak)
+    template <class St>
+    static std::vector<Digest> leaf_digests(const std::vector<Matrix>& leaves) {
+        size_t H = leaves.back().height;
+        std::vector<St> states(H, St{});
+        size_t active = leaves.front().height;
+        for (const Matrix& m : leaves) {
             size_t h = m.height;
             assert(h >= active && (h & (h - 1)) == 0);
             if (h > active) {   // nearest-neighbour duplication of the running states
@@ -44,13 +45,17 @@ struct LmcsTree {
                 for (size_t i = active; i-- > 0;)
                     for (size_t k = 0; k < f; k++) states[i * f + k] = states[i];
             }
+            bool done = false;
 #if ORC_HAVE_X8
-            if (h >= 8 && x8_available() && hash_kind() == H_POSEIDON2) {   // 8 leaves per AVX-512 permutation
+            if constexpr (std::is_same_v<St, State>) {
+                if (h >= 8 && x8_available() && hash_kind() == H_POSEIDON2) {   // 8 leaves per AVX-512 permutation
 #pragma omp parallel for schedule(static) if (h > 256)
-                for (size_t r8 = 0; r8 < h / 8; r8++) sponge_absorb_x8(&states[8 * r8], m.row(8 * r8), m.width, m.width);
-            } else
+                    for (size_t r8 = 0; r8 < h / 8; r8++) sponge_absorb_x8(&states[8 * r8], m.row(8 * r8), m.width, m.width);
+                    done = true;
+                }
+            }
 #endif
-            {
+            if (!done) {
 #pragma omp parallel for schedule(static) if (h > 256)
                 for (size_t r = 0; r < h; r++) sponge_absorb(states[r], m.row(r), m.width);
             }
@@ -59,6 +64,16 @@ struct LmcsTree {
         unsigned lg = log2_strict(H);
         std::vector<Digest> layer(H);
         for (size_t i = 0; i < H; i++) layer[i] = sponge_squeeze(states[reverse_bits64(i, lg)]);
+        return layer;
+    }
+
+    static LmcsTree build(std::vector<Matrix> mats, size_t alignment) {
+        LmcsTree t;
+        t.alignment = alignment;
+        t.leaves = std::move(mats);
+        size_t H = t.leaves.back().height;
+        unsigned lg = log2_strict(H);
+        std::vector<Digest> layer = hash_kind() == H_KECCAK ? leaf_digests<KeccakState>(t.leaves) : leaf_digests<State>(t.leaves);
         t.layers.assign(lg + 1, {});
         t.layers[lg] = std::move(layer);
         for (unsigned d = lg; d-- > 0;) {
@@ -156,10 +171,16 @@ inline std::map<size_t, std::vector<Fp>> lmcs_open_batch(const Digest& root, con
     for (size_t i : ti.idx) {
         std::vector<Fp> r(total);
         for (auto& x : r) x = ch.hint_field();
-        State st{};
         size_t off = 0;
-        for (size_t w : widths) { sponge_absorb(st, r.data() + off, w); off += w; }
-        cur_hash.push_back(sponge_squeeze(st));
+        if (hash_kind() == H_KECCAK) {
+            KeccakState st{};
+            for (size_t w : widths) { sponge_absorb(st, r.data() + off, w); off += w; }
+            cur_hash.push_back(sponge_squeeze(st));
+        } else {
+            State st{};
+            for (size_t w : widths) { sponge_absorb(st, r.data() + off, w); off += w; }
+            cur_hash.push_back(sponge_squeeze(st));
+        }
         rows[i] = std::move(r);
     }
     for (unsigned d = ti.depth; d > 0; d--) {

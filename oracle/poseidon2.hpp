@@ -7,6 +7,7 @@
 #pragma once
 #include "field.hpp"
 #include "blake3.hpp"
+#include "keccak.hpp"
 #include <array>
 #include <vector>
 
@@ -66,10 +67,19 @@ using Digest = std::array<Fp, 4>;
 //                the row), crates/stateful-hasher/src/chaining.rs:31-52,161-169), blake3(left || right) nodes
 //                (CompressionFunctionFromHasher<Blake3, 2, 32>), SerializingChallenger64<HashChallenger<u8, Blake3, 32>>
 //                (:276-307).  A 32-byte digest travels as four raw little-endian u64 in a `Digest`.
+//   H_KECCAK   : SerializingStatefulSponge<StatefulSponge<KeccakF, 25, 17, 4>> leaves (the overwrite-mode sponge over the
+//                canonical u64 of every felt, alignment lcm(8, 17*8)/8 = 17, crates/stateful-hasher/src/serializing_sponge.rs:72-86,
+//                163-200), PaddingFreeSponge<KeccakF, 25, 17, 4> nodes (zero state, the 8 words of the two digests overwrite
+//                lanes 0..8, one permutation, lanes 0..4), SerializingChallenger64<HashChallenger<u8, Keccak256Hash, 32>>
+//                (:309-353).  A digest is four u64 lanes, carried raw in a `Digest`.
 // One process-wide switch: the oracle is test infrastructure with a single client at a time.
-enum HashKind { H_POSEIDON2 = 0, H_BLAKE3 = 1 };
+enum HashKind { H_POSEIDON2 = 0, H_BLAKE3 = 1, H_KECCAK = 2 };
 inline HashKind& hash_kind() { static HashKind k = H_POSEIDON2; return k; }
-inline size_t lmcs_alignment() { return hash_kind() == H_BLAKE3 ? 1 : 8; }
+inline size_t lmcs_alignment() { return hash_kind() == H_BLAKE3 ? 1 : hash_kind() == H_KECCAK ? 17 : 8; }
+// the 32-byte hash of the byte-oriented challengers
+inline std::array<uint8_t, 32> hash32(const uint8_t* p, size_t n) { return hash_kind() == H_KECCAK ? keccak::hash256(p, n) : blake3::hash(p, n); }
+inline std::array<uint8_t, 32> hash32(const std::vector<uint8_t>& v) { return hash32(v.data(), v.size()); }
+using KeccakState = std::array<u64, 25>;
 
 inline void digest_to_bytes(const Fp* d, uint8_t* out) { for (int i = 0; i < 4; i++) for (int k = 0; k < 8; k++) out[8 * i + k] = (uint8_t)(d[i].v >> (8 * k)); }
 inline void bytes_to_digest(const uint8_t* b, Fp* d) {
@@ -110,6 +120,13 @@ inline void sponge_absorb(State& st, const Fp* in, size_t n) {
     sponge_absorb_generic<Fp, 12, 8>(st, in, n, [](State& s) { poseidon2_permute(s); });
 }
 inline Digest sponge_squeeze(const State& st) { return Digest{st[0], st[1], st[2], st[3]}; }
+// the Keccak leaf sponge: 25 u64 lanes, rate 17, the row's felts as canonical u64
+inline void sponge_absorb(KeccakState& st, const Fp* in, size_t n) {
+    std::vector<u64> w(n);
+    for (size_t i = 0; i < n; i++) w[i] = in[i].v;
+    sponge_absorb_generic<u64, 25, 17>(st, w.data(), n, [](KeccakState& s) { keccak::permute(s); });
+}
+inline Digest sponge_squeeze(const KeccakState& st) { return Digest{Fp::raw(st[0]), Fp::raw(st[1]), Fp::raw(st[2]), Fp::raw(st[3])}; }
 
 // 2-to-1 compression = p3 TruncatedPermutation<_, 2, 4, 12>: perm([l | r | 0000])[0..4]
 // (air/src/config.rs:217; equality with Poseidon2::merge shown by poseidon2/test.rs:208-230).
@@ -120,6 +137,12 @@ inline Digest compress2(const Digest& l, const Digest& r) {
         auto h = blake3::hash(buf, 64);
         Digest d; bytes_to_digest(h.data(), d.data());
         return d;
+    }
+    if (hash_kind() == H_KECCAK) {
+        KeccakState k{};
+        for (int i = 0; i < 4; i++) { k[i] = l[i].v; k[4 + i] = r[i].v; }
+        keccak::permute(k);
+        return sponge_squeeze(k);
     }
     State s;
     for (int i = 0; i < 4; i++) { s[i] = l[i]; s[4 + i] = r[i]; s[8 + i] = Fp(); }

@@ -25,7 +25,7 @@
 
 namespace orc {
 
-// In H_BLAKE3 mode the same struct is p3's `SerializingChallenger64<Felt, HashChallenger<u8, Blake3, 32>>`
+// In H_BLAKE3 / H_KECCAK mode (H = Blake3 / Keccak-256, air/src/config.rs:335-336,350-351) the same struct is p3's `SerializingChallenger64<Felt, HashChallenger<u8, Blake3, 32>>`
 // (air/src/config.rs:292-293,304-305; p3-challenger 0.6.2, un-vendored -- PARITY UNPINNED, restated from the published crate):
 //   HashChallenger: observe(byte) clears the output buffer and appends to the input buffer; sample(): if the output buffer
 //   is empty, flush = { out = H(input buffer); output buffer = out; input buffer = out (chaining) }, then POP FROM THE BACK;
@@ -43,7 +43,7 @@ struct Challenger {
     void observe_byte(uint8_t b) { bout.clear(); bin.push_back(b); }
     uint8_t sample_byte() {
         if (bout.empty()) {
-            auto h = blake3::hash(bin);
+            auto h = hash32(bin);
             bout.assign(h.begin(), h.end());
             bin.assign(h.begin(), h.end());
         }
@@ -68,23 +68,23 @@ struct Challenger {
         out_len = 8;
     }
     void observe(Fp x) {
-        if (hash_kind() == H_BLAKE3) { for (int k = 0; k < 8; k++) observe_byte((uint8_t)(x.v >> (8 * k))); return; }
+        if (hash_kind() != H_POSEIDON2) { for (int k = 0; k < 8; k++) observe_byte((uint8_t)(x.v >> (8 * k))); return; }
         out_len = 0;
         in_buf[in_len++] = x;
         if (in_len == 8) duplex();
     }
     void observe_digest(const Digest& d) {
-        if (hash_kind() == H_BLAKE3) { uint8_t b[32]; digest_to_bytes(d.data(), b); for (int i = 0; i < 32; i++) observe_byte(b[i]); return; }
+        if (hash_kind() != H_POSEIDON2) { uint8_t b[32]; digest_to_bytes(d.data(), b); for (int i = 0; i < 32; i++) observe_byte(b[i]); return; }
         for (int i = 0; i < 4; i++) observe(d[i]);
     }
     Fp sample() {
-        if (hash_kind() == H_BLAKE3) { for (;;) { u64 v = sample_u64_bytes(); if (v < P) return Fp::raw(v); } }
+        if (hash_kind() != H_POSEIDON2) { for (;;) { u64 v = sample_u64_bytes(); if (v < P) return Fp::raw(v); } }
         if (in_len > 0 || out_len == 0) duplex();
         return st[--out_len];
     }
     Ef sample_ext() { Fp a = sample(); Fp b = sample(); return Ef(a, b); }  // channel.rs:54-56
     u64 sample_bits(unsigned bits) {
-        if (hash_kind() == H_BLAKE3) return sample_u64_bytes() & ((u64(1) << bits) - 1);
+        if (hash_kind() != H_POSEIDON2) return sample_u64_bytes() & ((u64(1) << bits) - 1);
         u64 v = sample().v;
         return v & ((u64(1) << bits) - 1);
     }

@@ -73,6 +73,10 @@ def main():
     wl3, builder3 = test_airs.fib_product_workload([8, 6], lqd=1)
     cases.append(("blake3: host aux builder", W.fast_pcs_params(), wl3, builder3, "blake3"))
 
+    # the Keccak configuration: 25-lane states between height groups, alignment 17 in the openings
+    cases.append(("keccak: miden-shape mixed heights", W.miden_pcs_params(), W.Workload([log_h - 1, log_h - 2, log_h - 3]), None, "keccak"))
+    cases.append(("keccak: preprocessed columns", W.fast_pcs_params(), test_airs.preprocessed_workload((6, 8), (True, True)), None, "keccak"))
+
     sessions = {}     # params tuple -> (single, split): sessions are reused so that arena reuse across shapes is exercised
 
     def sess_for(params, hash_name="poseidon2"):
@@ -80,9 +84,9 @@ def main():
         if key not in sessions:
             single = B.Session(params, local)
             split = B.Session(params, local)
-            if hash_name == "blake3":
+            if hash_name != "poseidon2":
                 for s_ in (single, split):
-                    s_.set_hash(B.HASH_BLAKE3, W.initial_hash_challenger(params))
+                    s_.set_hash({"blake3": B.HASH_BLAKE3, "keccak": B.HASH_KECCAK}[hash_name], W.initial_hash_challenger(params))
             split.set_shard(rank, world, allgather)
             for s_ in (single, split):
                 lib.mdn_set_debug(s_.handle, 1 if os.environ.get("SHARD_DEBUG_STAGES") else 0)

@@ -56,6 +56,17 @@ def test_blake3_configuration_on_the_emulator():
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
 
 
+def test_keccak_configuration_on_the_emulator():
+    """The Keccak configuration (stateful sponge with rate 17 / alignment 17 and 25 lanes of state between height groups,
+    PaddingFreeSponge nodes, Keccak-256 hash challenger and proof-of-work): the -m gpu cases of tests/test_keccak.py on the
+    emulator, bit-exact against the oracle in Keccak mode."""
+    lib = _build("")
+    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_keccak.py"), "-q", "-m", "gpu", "-k", "not 2_16",
+                        "-p", "no:cacheprovider", "--timeout", "600"], env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+
+
 @pytest.mark.parametrize("world,min_log", [(2, None), (4, 2), (8, None)])
 def test_one_proof_split_over_ranks_on_the_emulator(world, min_log):
     """ONE proof split over `world` ranks (mdn_session_set_shard: LDE cosets, leaf sponge, constraints, quotient chunks,
