@@ -145,6 +145,24 @@ pub type MdnExternalCheck = Option<
 
 pub enum MdnSession {}
 
+/// `mdn_hash_kind` (include/miden_b200.h): which `miden_air::config` constructor the session follows.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum HashKind {
+    Poseidon2 = 0,
+    Blake3 = 1,
+    Keccak = 2,
+}
+
+/// `mdn_hash_challenger`: p3 `HashChallenger<u8, H, 32>`'s two buffers.
+#[repr(C)]
+pub struct MdnHashChallenger {
+    pub input_buffer: *const u8,
+    pub input_len: usize,
+    pub output_buffer: *const u8,
+    pub output_len: usize,
+}
+
 unsafe extern "C" {
     pub fn mdn_session_create(params: *const MdnPcsParams, cuda_device: c_int, out: *mut *mut MdnSession) -> c_int;
     pub fn mdn_session_destroy(s: *mut MdnSession);
@@ -183,6 +201,8 @@ unsafe extern "C" {
     ) -> c_int;
     pub fn mdn_session_set_shard(s: *mut MdnSession, rank: u32, world: u32, f: MdnAllgather, ctx: *mut c_void) -> c_int;
     pub fn mdn_session_set_external_check(s: *mut MdnSession, f: MdnExternalCheck, ctx: *mut c_void) -> c_int;
+    pub fn mdn_session_set_hash(s: *mut MdnSession, kind: c_int) -> c_int;
+    pub fn mdn_session_set_hash_challenger(s: *mut MdnSession, c: *const MdnHashChallenger) -> c_int;
     pub fn mdn_session_set_jit(s: *mut MdnSession, min_nodes: u32) -> c_int;
     pub fn mdn_jit_compile_check(program: *const u32, program_words: u32, err: *mut *const c_char) -> c_longlong;
     pub fn mdn_get_timings(s: *mut MdnSession, out: *mut MdnTimings) -> c_int;

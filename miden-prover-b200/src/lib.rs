@@ -83,6 +83,25 @@ impl GpuSession {
         )
     }
 
+    /// Switch the session to another of the reference's STARK hash configurations (`miden_air::config`): `input_buffer` is
+    /// the `HashChallenger`'s input buffer after `config.challenger()` + `observe_protocol_params` (32 bytes of relation
+    /// digest + 8 parameter felts as little-endian u64); ignored for [`HashKind::Poseidon2`], whose duplex challenger is
+    /// the argument of [`GpuStarkProver::prove`].
+    pub fn set_hash(&mut self, kind: HashKind, input_buffer: &[u8]) -> Result<(), ExecutionError> {
+        let rc = unsafe { mdn_session_set_hash(self.raw, kind as c_int) };
+        if rc != MDN_OK {
+            return Err(ExecutionError::ProvingError(last_error(self.raw)));
+        }
+        if !matches!(kind, HashKind::Poseidon2) {
+            let hc = MdnHashChallenger { input_buffer: input_buffer.as_ptr(), input_len: input_buffer.len(), output_buffer: ptr::null(), output_len: 0 };
+            let rc = unsafe { mdn_session_set_hash_challenger(self.raw, &hc) };
+            if rc != MDN_OK {
+                return Err(ExecutionError::ProvingError(last_error(self.raw)));
+            }
+        }
+        Ok(())
+    }
+
     /// Split every proof of this session over `world` processes (one per GPU of an NVLink box): every rank calls
     /// [`GpuStarkProver::prove`] with the same statement and traces and gets the byte-identical proof.  `allgather`
     /// is only the bootstrap transport of the CUDA IPC handles (64 bytes per rank when a proof arena slab is created);
@@ -185,6 +204,52 @@ impl<'s> GpuStarkProver<'s> {
     where
         MA: MultiAir<Felt, QuadFelt>,
     {
+        let ch = challenger_state(challenger);
+        let raw = self.prove_raw(statement, Some(&ch))?;
+        // StarkProofData { log_trace_heights, transcript: TranscriptData { fields, commitments } }
+        // (crates/lifted-stark/src/proof.rs:57-63; crates/stark-transcript/src/data.rs:11-15).  Its fields are
+        // crate-private, so the bytes are produced from a mirror with the identical serde shape and the same wincode
+        // configuration prove_stark uses; a `StarkProofData::from_parts` in lifted-stark would make this a move.
+        let commitments: Vec<[Felt; 4]> = raw.commitments.iter().map(|c| c.map(Felt::new_unchecked)).collect();
+        let wire = ProofWire { log_trace_heights: raw.log_trace_heights, transcript: TranscriptData::new(raw.fields, commitments) };
+        serialize_wire(&wire)
+    }
+
+    /// The Blake3_256 configuration (`HashFunction::Blake3_256`, air/src/config.rs:276-307) after
+    /// `session.set_hash(HashKind::Blake3, &input_buffer)`: commitments are `[u8; 32]`, the four little-endian u64 of a digest.
+    pub fn prove_blake3<MA: MultiAir<Felt, QuadFelt>>(&mut self, statement: &ProverStatement<Felt, QuadFelt, MA>) -> Result<Vec<u8>, ExecutionError> {
+        let raw = self.prove_raw(statement, None)?;
+        let commitments: Vec<[u8; 32]> = raw
+            .commitments
+            .iter()
+            .map(|c| {
+                let mut b = [0u8; 32];
+                for (i, w) in c.iter().enumerate() {
+                    b[8 * i..8 * i + 8].copy_from_slice(&w.to_le_bytes());
+                }
+                b
+            })
+            .collect();
+        serialize_wire(&ProofWireBytes { log_trace_heights: raw.log_trace_heights, transcript: TranscriptData::new(raw.fields, commitments) })
+    }
+
+    /// The Keccak configuration (`HashFunction::Keccak`, air/src/config.rs:309-353) after
+    /// `session.set_hash(HashKind::Keccak, &input_buffer)`: commitments are `[u64; 4]` lanes.
+    pub fn prove_keccak<MA: MultiAir<Felt, QuadFelt>>(&mut self, statement: &ProverStatement<Felt, QuadFelt, MA>) -> Result<Vec<u8>, ExecutionError> {
+        let raw = self.prove_raw(statement, None)?;
+        serialize_wire(&ProofWireLanes { log_trace_heights: raw.log_trace_heights, transcript: TranscriptData::new(raw.fields, raw.commitments) })
+    }
+
+    /// One proof on the device, hash-configuration agnostic: `challenger` is the duplex state for Poseidon2 and `None` for
+    /// the byte-oriented configurations, whose pre-bound `HashChallenger` was installed with [`GpuSession::set_hash`].
+    fn prove_raw<MA>(
+        &mut self,
+        statement: &ProverStatement<Felt, QuadFelt, MA>,
+        challenger: Option<&MdnChallenger>,
+    ) -> Result<RawProof, ExecutionError>
+    where
+        MA: MultiAir<Felt, QuadFelt>,
+    {
         let traces: &[RowMajorMatrix<Felt>] = statement.traces();
         let st = statement.statement();
         let k = traces.len();
@@ -240,7 +305,7 @@ impl<'s> GpuStarkProver<'s> {
             observe_felts: observe_felts.as_ptr(),
             n_observe_felts: observe_felts.len() as u32,
         };
-        let ch = challenger_state(challenger);
+        let ch: *const MdnChallenger = challenger.map_or(ptr::null(), |c| c as *const MdnChallenger);
 
         // (d) host callbacks: build_aux_trace for AIRs without a lowered lookup; eval_external for the statement
         let mut ctx = CallbackCtx { statement };
@@ -251,7 +316,7 @@ impl<'s> GpuStarkProver<'s> {
         unsafe { mdn_session_set_external_check(self.session.raw, Some(external_trampoline::<MA>), ctx_ptr) };
 
         let mut proof = core::mem::MaybeUninit::<MdnProof>::uninit();
-        let rc = unsafe { mdn_prove(self.session.raw, &mdn_st, mats.as_ptr(), &ch, aux_cb, ctx_ptr, 0, proof.as_mut_ptr()) };
+        let rc = unsafe { mdn_prove(self.session.raw, &mdn_st, mats.as_ptr(), ch, aux_cb, ctx_ptr, 0, proof.as_mut_ptr()) };
         unsafe { mdn_session_set_external_check(self.session.raw, None, ptr::null_mut()) };
         if rc != MDN_OK {
             // ProverError -> ExecutionError::ProvingError(String) (prover/src/lib.rs:336-345)
@@ -259,21 +324,27 @@ impl<'s> GpuStarkProver<'s> {
         }
         let proof = unsafe { proof.assume_init() };
 
-        // (e) StarkProofData { log_trace_heights, transcript: TranscriptData { fields, commitments } }
-        //     (crates/lifted-stark/src/proof.rs:57-63; crates/stark-transcript/src/data.rs:11-15).  Its fields are
-        //     crate-private, so the bytes are produced from a mirror with the identical serde shape and the same wincode
-        //     configuration prove_stark uses; a `StarkProofData::from_parts` in lifted-stark would make this a move.
-        let heights = unsafe { core::slice::from_raw_parts(proof.log_trace_heights, proof.n_heights) }.to_vec();
+        // (e) the proof streams, copied out of the session's buffers (valid until the next call on the session)
+        let log_trace_heights = unsafe { core::slice::from_raw_parts(proof.log_trace_heights, proof.n_heights) }.to_vec();
         let fields: Vec<Felt> = unsafe { core::slice::from_raw_parts(proof.fields, proof.n_fields) }.iter().map(|&v| Felt::new_unchecked(v)).collect();
-        let commitments: Vec<[Felt; 4]> = unsafe { core::slice::from_raw_parts(proof.commitments, 4 * proof.n_commitments) }
+        let commitments: Vec<[u64; 4]> = unsafe { core::slice::from_raw_parts(proof.commitments, 4 * proof.n_commitments) }
             .chunks_exact(4)
-            .map(|c| [Felt::new_unchecked(c[0]), Felt::new_unchecked(c[1]), Felt::new_unchecked(c[2]), Felt::new_unchecked(c[3])])
+            .map(|c| [c[0], c[1], c[2], c[3]])
             .collect();
-        let wire = ProofWire { log_trace_heights: heights, transcript: TranscriptData::new(fields, commitments) };
-        let cfg = wincode::config::Configuration::default();
-        <wincode::SerdeCompat<ProofWire> as wincode::config::Serialize<_>>::serialize(&wire, cfg)
-            .map_err(|e| ExecutionError::ProvingError(e.to_string()))
+        Ok(RawProof { log_trace_heights, fields, commitments })
     }
+}
+
+/// `StarkProofData`'s three streams as the C ABI returns them; a commitment is four u64 whatever the hash configuration.
+struct RawProof {
+    log_trace_heights: Vec<u8>,
+    fields: Vec<Felt>,
+    commitments: Vec<[u64; 4]>,
+}
+
+fn serialize_wire<T: Serialize>(wire: &T) -> Result<Vec<u8>, ExecutionError> {
+    let cfg = wincode::config::Configuration::default();
+    <wincode::SerdeCompat<T> as wincode::config::Serialize<_>>::serialize(wire, cfg).map_err(|e| ExecutionError::ProvingError(e.to_string()))
 }
 
 /// Serde mirror of `StarkProofData<Felt, QuadFelt, SC>` for the Poseidon2 configuration (`Commitment = [Felt; 4]`
@@ -282,6 +353,18 @@ impl<'s> GpuStarkProver<'s> {
 struct ProofWire {
     log_trace_heights: Vec<u8>,
     transcript: TranscriptData<Felt, [Felt; 4]>,
+}
+/// The same for the Blake3_256 configuration (`Commitment = [u8; 32]`, air/src/config.rs:282-289) ...
+#[derive(Serialize)]
+struct ProofWireBytes {
+    log_trace_heights: Vec<u8>,
+    transcript: TranscriptData<Felt, [u8; 32]>,
+}
+/// ... and for the Keccak configuration (`Commitment = [u64; 4]`, air/src/config.rs:325-332).
+#[derive(Serialize)]
+struct ProofWireLanes {
+    log_trace_heights: Vec<u8>,
+    transcript: TranscriptData<Felt, [u64; 4]>,
 }
 
 // CALLBACKS
