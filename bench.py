@@ -346,7 +346,7 @@ def main():
         try:
             ipp2 = (tj.get("thread_instructions_per_permutation") if os.path.exists(tf) else None) or 13673
             instr_per_perm = {1: (15960, "ncu inst_executed of the first-generation kernel (round-1 capture r1i)"),
-                              2: (round(ipp2), "ncu smsp__inst_executed x 32 / permutations of the k_leaf_hash capture of the shipped second-generation kernel (profiles/leaf_sponge_traffic.json, profiles/r2b_kernels.json)")}[build[0]]
+                              2: (round(ipp2), "ncu smsp__inst_executed x 32 / permutations of the k_leaf_hash capture of the shipped second-generation kernel (profiles/leaf_sponge_traffic.json, profiles/r2m_kernels.json)")}[build[0]]
             clk = sampler.summary()
             sm_mhz = clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965
             perms_per_s = tim_v.permutations / ((km[2] + km[3]) * 1e-3) if km[2] + km[3] > 0 else None
@@ -377,7 +377,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_fwd_contig + k_fwd_strided + k_intt_* (coset LDE: the dominant kernel class under the byte-oriented hashes)", "achieved": ntt_gbs, "peak": peak,
                          "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": None, "peak_source": f"{peak_kind} copy bandwidth",
-                         "note": "instruction-bound (ncu r2b: issue 61-65 %, ALU pipe 63-69 %, FMA-heavy 51-66 %; ~280 instructions per point per pass), see DESIGN.md section 5"}
+                         "note": "instruction-bound (ncu r2m: issue 54-70 %, ALU pipe 59-69 %, FMA-heavy 47-69 %; ~250 instructions per point per pass), see DESIGN.md section 5"}
             if args.hash != "poseidon2" else
                         {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon2 leaf sponge, main trace)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_kind} copy bandwidth",

@@ -218,8 +218,11 @@ int mdn_session_set_external_check(mdn_session* s, mdn_external_check fn, void* 
  *   overwrite-mode sponge over the canonical u64 of every felt; alignment 17: opened rows and the OOD lists are zero-padded
  *   to multiples of 17), PaddingFreeSponge<KeccakF, 25, 17, 4> nodes, SerializingChallenger64<Felt, HashChallenger<u8,
  *   Keccak256Hash, 32>>.  Digests are four u64 lanes; the challenger is installed like the Blake3 one (its input buffer must
- *   be whole 64-bit words, which `observe_slice(&relation_digest)` + `observe_protocol_params` always gives). */
-typedef enum { MDN_HASH_POSEIDON2 = 0, MDN_HASH_BLAKE3 = 1, MDN_HASH_KECCAK = 2 } mdn_hash_kind;
+ *   be whole 64-bit words, which `observe_slice(&relation_digest)` + `observe_protocol_params` always gives).
+ * MDN_HASH_RPO / MDN_HASH_RPX: `rpo_config` / `rpx_config` (:225-248) -- the Poseidon2 configuration with the permutation
+ *   replaced (`alg_config<P>` is generic in it, :255-273): same LMCS, alignment, duplex challenger (pass the `mdn_challenger`
+ *   built with that permutation) and proof layout.  Functional coverage: an RPO permutation costs ~9x a Poseidon2 one. */
+typedef enum { MDN_HASH_POSEIDON2 = 0, MDN_HASH_BLAKE3 = 1, MDN_HASH_KECCAK = 2, MDN_HASH_RPO = 3, MDN_HASH_RPX = 4 } mdn_hash_kind;
 int mdn_session_set_hash(mdn_session* s, mdn_hash_kind kind);
 /* p3 `HashChallenger<u8, Blake3 | Keccak256Hash, 32>`: `input_buffer`, `output_buffer` (bytes are sampled from its back). */
 typedef struct {

@@ -41,7 +41,7 @@ class HashChallenger(C.Structure):
                 ("output_buffer", C.POINTER(C.c_uint8)), ("output_len", C.c_size_t)]
 
 
-HASH_POSEIDON2, HASH_BLAKE3, HASH_KECCAK = 0, 1, 2
+HASH_POSEIDON2, HASH_BLAKE3, HASH_KECCAK, HASH_RPO, HASH_RPX = 0, 1, 2, 3, 4
 
 
 class Matrix(C.Structure):
@@ -216,7 +216,7 @@ class Session:
     def set_hash(self, kind: int, challenger_input: bytes = b"", challenger_output: bytes = b""):
         """`blake3_256_config` / `keccak_config` instead of `poseidon2_config` (mdn_session_set_hash) + the pre-bound HashChallenger state."""
         self._check(lib().mdn_session_set_hash(self._h, kind))
-        if kind != HASH_POSEIDON2:
+        if kind in (HASH_BLAKE3, HASH_KECCAK):
             a = (C.c_uint8 * max(1, len(challenger_input))).from_buffer_copy(challenger_input or b"\0")
             b = (C.c_uint8 * max(1, len(challenger_output))).from_buffer_copy(challenger_output or b"\0")
             hc = HashChallenger(a, len(challenger_input), b, len(challenger_output))

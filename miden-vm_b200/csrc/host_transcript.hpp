@@ -11,6 +11,7 @@
 #include "poseidon2.cuh"
 #include "blake3.cuh"
 #include "keccak.cuh"
+#include "rescue.cuh"
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -32,6 +33,7 @@ struct Duplex {
     u64 st[12];
     u64 in[8];
     u32 in_len = 0, out_len = 0;
+    int perm = 0;             // duplex mode: the permutation -- 0 Poseidon2, 3 RPO, 4 RPX (`alg_config<P>`, air/src/config.rs:255-273)
     bool hashed = false;
     bool keccak = false;      // hashed only: H = Keccak-256 (the Keccak configuration, air/src/config.rs:335-336) instead of Blake3
     std::vector<uint8_t> bin, bout;
@@ -68,7 +70,9 @@ struct Duplex {
             st[8] = gl::add(st[8], in_len);
             in_len = 0;
         }
-        p2::permute(st);
+        if (perm == 3) rsc::rpo_permute(st);
+        else if (perm == 4) rsc::rpx_permute(st);
+        else p2::permute(st);
         out_len = 8;
     }
     void observe(u64 x) {

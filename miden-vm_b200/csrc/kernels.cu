@@ -20,6 +20,7 @@
 #endif
 #include "blake3.cuh"
 #include "keccak.cuh"
+#include "rescue.cuh"
 #include <algorithm>
 #include <cstdio>
 
@@ -35,6 +36,8 @@ void upload_constants() {
     cudaMemcpyToSymbol(p2::D_RC_EXT_INITIAL, p2::P2_RC_EXT_INITIAL, sizeof(u64) * 48);
     cudaMemcpyToSymbol(p2::D_RC_INTERNAL, p2::P2_RC_INTERNAL, sizeof(u64) * 22);
     cudaMemcpyToSymbol(p2::D_RC_EXT_TERMINAL, p2::P2_RC_EXT_TERMINAL, sizeof(u64) * 48);
+    cudaMemcpyToSymbol(rsc::D_ARK1, rsc::RESCUE_ARK1, sizeof(u64) * 84);
+    cudaMemcpyToSymbol(rsc::D_ARK2, rsc::RESCUE_ARK2, sizeof(u64) * 84);
 }
 
 // =============================================================================================
@@ -453,7 +456,21 @@ static constexpr int HASH_THREADS = 128;     // 64 and 256 threads per block mea
 #define HASH_MIN_BLOCKS 6
 #endif
 
-__global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_leaf_hash(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev,
+// The permutation of the algebraic configurations (air/src/config.rs:225-273: one LMCS / challenger type, generic in P):
+// PERM_P2 = Poseidon2 (the metric's; lazy representatives, canonicalised on store), PERM_RPO / PERM_RPX = rescue.cuh (canonical in,
+// canonical out; functional coverage of `rpo_config` / `rpx_config`, ~9x / ~5x the field multiplications of Poseidon2).
+enum { PERM_P2 = 0, PERM_RPO = 3, PERM_RPX = 4 };     // = mdn_hash_kind
+template <int PERM>
+__device__ __forceinline__ void alg_permute(u64* s) {
+    if constexpr (PERM == PERM_RPO) rsc::rpo_permute(s);
+    else if constexpr (PERM == PERM_RPX) rsc::rpx_permute(s);
+    else p2f::permute(s);
+}
+#define ALG_BOUNDS(PERM) __launch_bounds__(HASH_THREADS, (PERM) == PERM_P2 ? HASH_MIN_BLOCKS : 1)
+#define ALG_DISPATCH(perm, CALL) do { if ((perm) == PERM_RPO) { CALL(PERM_RPO); } else if ((perm) == PERM_RPX) { CALL(PERM_RPX); } else { CALL(PERM_P2); } } while (0)
+
+template <int PERM>
+__global__ void ALG_BOUNDS(PERM) k_leaf_hash(LeafArgs a, u32 log_n, u32 log_b, const u64* __restrict__ prev,
                                                             u32 prev_log_n, u64* __restrict__ states_out,
                                                             PushDst dig, u32 has_dig, u32 t0, u32 nt) {
     // all rows of cosets t0 .. t0 + nt (the whole tree when t0 = 0, nt = B; this rank's cosets when one proof is
@@ -480,7 +497,7 @@ __global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_leaf_hash(Lea
         for (u32 c0 = 0; c0 < w; c0 += 8) {
 #pragma unroll
             for (u32 k = 0; k < 8; k++) s[k] = (c0 + k < w) ? base[(size_t)(c0 + k) * L] : 0ull;
-            p2f::permute(s);
+            alg_permute<PERM>(s);
         }
     }
     if (states_out) {
@@ -493,34 +510,49 @@ __global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_leaf_hash(Lea
         push_u2(dig, 2 * i + 1, i, make_ulonglong2(glf::canon(s[2]), glf::canon(s[3])));
     }
 }
-void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
-                      u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st) {
+template <int PERM>
+static void launch_leaf_hash_t(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                               u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st) {
     size_t cnt = (size_t)nt << log_n;
     unsigned blocks = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
     PushDst d = dig ? *dig : local_dst(nullptr);
-    k_leaf_hash<<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, d, dig ? 1u : 0u, t0, nt);
+    k_leaf_hash<PERM><<<blocks, HASH_THREADS, 0, st>>>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, d, dig ? 1u : 0u, t0, nt);
     COUNT_LAUNCH();
 }
+void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
+                      u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st, int perm) {
+#define X(PM) launch_leaf_hash_t<PM>(a, log_n, log_blowup, prev_states, prev_log_n, states_out, dig, t0, nt, st)
+    ALG_DISPATCH(perm, X);
+#undef X
+}
 
-__global__ void __launch_bounds__(HASH_THREADS, HASH_MIN_BLOCKS) k_compress(const u64* __restrict__ ch, u64* __restrict__ par, size_t n) {
+template <int PERM>
+__global__ void ALG_BOUNDS(PERM) k_compress(const u64* __restrict__ ch, u64* __restrict__ par, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(ch + i * 8);
     ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2], b1 = c[3];
     u64 s[12] = {a0.x, a0.y, a1.x, a1.y, b0.x, b0.y, b1.x, b1.y, 0, 0, 0, 0};
-    p2f::permute(s);
+    alg_permute<PERM>(s);
     ulonglong2* d = reinterpret_cast<ulonglong2*>(par + i * 4);
     d[0] = make_ulonglong2(glf::canon(s[0]), glf::canon(s[1]));
     d[1] = make_ulonglong2(glf::canon(s[2]), glf::canon(s[3]));
 }
-void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st) {
+template <int PERM>
+static void launch_compress_layer_t(const u64* children, u64* parents, size_t n_parents, cudaStream_t st) {
     unsigned blocks = (unsigned)((n_parents + HASH_THREADS - 1) / HASH_THREADS);
-    k_compress<<<blocks, HASH_THREADS, 0, st>>>(children, parents, n_parents);
+    k_compress<PERM><<<blocks, HASH_THREADS, 0, st>>>(children, parents, n_parents);
     COUNT_LAUNCH();
+}
+void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st, int perm) {
+#define X(PM) launch_compress_layer_t<PM>(children, parents, n_parents, st)
+    ALG_DISPATCH(perm, X);
+#undef X
 }
 
 // FRI round leaf: physical row of 2^la extension values [f[i + bitrev_la(j) * q]]_j (fri/prover.rs:137-165),
 // flattened to 2 * 2^la felts and absorbed with the rate-8 sponge (unaligned tree).
+template <int PERM>
 __global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict__ ev, size_t q, u32 la, PushDst dig, u32 log_b, u32 t0, u32 log_nt) {
     // thread -> leaf i with (i mod B) in [t0, t0 + nt): the leaves whose 2^la values (stride q, a multiple of B) this rank holds
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,18 +571,24 @@ __global__ void __launch_bounds__(HASH_THREADS) k_fri_leaf(const u64* __restrict
                 s[2 * j] = v.x; s[2 * j + 1] = v.y;
             } else { s[2 * j] = 0; s[2 * j + 1] = 0; }
         }
-        p2f::permute(s);
+        alg_permute<PERM>(s);
     }
     push_u2(dig, 2 * i, i, make_ulonglong2(glf::canon(s[0]), glf::canon(s[1])));
     push_u2(dig, 2 * i + 1, i, make_ulonglong2(glf::canon(s[2]), glf::canon(s[3])));
 }
 static inline u32 log2_exact(u32 v) { u32 l = 0; while ((1u << l) < v) l++; return l; }
-void launch_fri_leaf_hash(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st) {
+template <int PERM>
+static void launch_fri_leaf_hash_t(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st) {
     if (rows < ((size_t)1 << log_b)) { log_b = 0; t0 = 0; nt = 1; }      // tiny layers are never split
     size_t cnt = (rows >> log_b) * nt;
     unsigned blocks = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
-    k_fri_leaf<<<blocks, HASH_THREADS, 0, st>>>(evals, rows, log_arity, digests, log_b, t0, log2_exact(nt));
+    k_fri_leaf<PERM><<<blocks, HASH_THREADS, 0, st>>>(evals, rows, log_arity, digests, log_b, t0, log2_exact(nt));
     COUNT_LAUNCH();
+}
+void launch_fri_leaf_hash(const u64* evals, size_t rows, u32 log_arity, const PushDst& digests, u32 log_b, u32 t0, u32 nt, cudaStream_t st, int perm) {
+#define X(PM) launch_fri_leaf_hash_t<PM>(evals, rows, log_arity, digests, log_b, t0, nt, st)
+    ALG_DISPATCH(perm, X);
+#undef X
 }
 
 __global__ void k_p2_batch(u64* st, size_t n) {
@@ -1260,6 +1298,7 @@ void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, cons
 // =============================================================================================
 // Proof-of-work grinding
 // =============================================================================================
+template <int PERM>
 __global__ void __launch_bounds__(128) k_grind(const u64* __restrict__ st12, u32 in_len, u64 mask, u64 start, u64 count,
                                                u64* result) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1274,13 +1313,19 @@ __global__ void __launch_bounds__(128) k_grind(const u64* __restrict__ st12, u32
         else if (k > in_len) s[k] = 0;
     }
     s[8] = gl::add(s[8], (u64)(in_len + 1));
-    p2f::permute(s);
+    alg_permute<PERM>(s);
     if ((glf::canon(s[7]) & mask) == 0) atomicMin(reinterpret_cast<unsigned long long*>(result), (unsigned long long)w);
 }
-void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
+template <int PERM>
+static void launch_grind_t(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st) {
     u64 mask = (1ull << bits) - 1;
-    k_grind<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_state12, in_len, mask, start, count, d_result);
+    k_grind<PERM><<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_state12, in_len, mask, start, count, d_result);
     COUNT_LAUNCH();
+}
+void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result, cudaStream_t st, int perm) {
+#define X(PM) launch_grind_t<PM>(d_state12, in_len, bits, start, count, d_result, st)
+    ALG_DISPATCH(perm, X);
+#undef X
 }
 
 __global__ void k_compare(const u64* __restrict__ a, const u64* __restrict__ b, size_t n, u32* flag) {

@@ -97,14 +97,15 @@ struct LeafArgs { LeafMat m[8]; int n_mats; };
 //   digests_out  : tree leaf layer (4 u64 per leaf, indexed by DOMAIN index r*B + t), or NULL
 //   t0, nt       : only cosets t0 .. t0 + nt are hashed (all rows of each); leaf r*B + t goes to dig (PushDst:
 //                  local layer, the rank owning the leaf's sub-tree, or every rank); dig == NULL: no digests
+// `perm` selects the permutation of the algebraic configurations: 0 Poseidon2, 3 RPO, 4 RPX (= mdn_hash_kind; rescue.cuh)
 void launch_leaf_hash(const LeafArgs& a, u32 log_n, u32 log_blowup, const u64* prev_states, u32 prev_log_n,
-                      u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st);
+                      u64* states_out, const PushDst* dig, u32 t0, u32 nt, cudaStream_t st, int perm = 0);
 // parent[i] = perm(child[2i] | child[2i+1] | 0000)[0..4]
-void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st);
+void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, cudaStream_t st, int perm = 0);
 // FRI round leaves: leaf i' (< quarter) = sponge([f[i'], f[i'+2q], f[i'+q], f[i'+3q]]) (8 felts, one block).
 // Only leaves i' with (i' mod 2^log_b) in [t0, t0 + nt) are hashed (t0 = 0, nt = 2^log_b: all).
 void launch_fri_leaf_hash(const u64* evals /* EF interleaved */, size_t rows, u32 log_arity, const PushDst& digests,
-                          u32 log_b, u32 t0, u32 nt, cudaStream_t st);
+                          u32 log_b, u32 t0, u32 nt, cudaStream_t st, int perm = 0);
 void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
 // The same three tree kernels and the proof-of-work search for the Blake3_256 configuration (air/src/config.rs:276-307):
 // chaining leaf hasher (4-lane SoA states), blake3(left || right) nodes, hash-challenger PoW over the challenger's input
@@ -210,7 +211,7 @@ void launch_fri_fold(const u64* evals, u32 log_dom, u32 log_arity, E2 beta, cons
 //   the rate holding whatever the sponge holds; the kernel writes w at rate[in_len], zero-fills
 //   rate[in_len+1..8), adds (in_len+1) to st[8] and permutes.
 void launch_grind(const u64* d_state12, u32 in_len, u32 bits, u64 start, u64 count, u64* d_result /* init ~0 */,
-                  cudaStream_t st);
+                  cudaStream_t st, int perm = 0);
 
 // sets *flag |= 4 when a[i] != b[i] for some i < n (self-check of the NVRTC constraint kernels)
 void launch_compare(const u64* a, const u64* b, size_t n, u32* flag, cudaStream_t st);

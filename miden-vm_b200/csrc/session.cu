@@ -206,17 +206,19 @@ struct mdn_session {
     // hasher + hash challenger (air/src/config.rs:276-307).  `align` = LMCS alignment: 8 (sponge rate) or 1 (chaining).
     int hash_kind = MDN_HASH_POSEIDON2;
     u32 align() const { return hash_kind == MDN_HASH_BLAKE3 ? 1u : hash_kind == MDN_HASH_KECCAK ? 17u : 8u; }
+    bool byte_hash() const { return hash_kind == MDN_HASH_BLAKE3 || hash_kind == MDN_HASH_KECCAK; }     // hash challenger, not the duplex one
+    int perm() const { return byte_hash() ? 0 : hash_kind; }                                             // rescue.cuh permutations share the Poseidon2 kernels
     u32 state_words() const { return hash_kind == MDN_HASH_KECCAK ? 25u : 12u; }      // leaf state handed on between height groups
     std::vector<uint8_t> hash_ch_in, hash_ch_out;          // pre-bound HashChallenger state (mdn_session_set_hash_challenger)
     void hash_leaves(const mk::LeafArgs& a, u32 ln, u32 lb, const u64* prev, u32 prev_log, u64* states_out, const mk::PushDst* dig, u32 tb, u32 tn) {
         if (hash_kind == MDN_HASH_BLAKE3) mk::launch_leaf_hash_b3(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
         else if (hash_kind == MDN_HASH_KECCAK) mk::launch_leaf_hash_kk(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
-        else mk::launch_leaf_hash(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream);
+        else mk::launch_leaf_hash(a, ln, lb, prev, prev_log, states_out, dig, tb, tn, stream, perm());
     }
     void compress_layer(const u64* children, u64* parents, size_t n) {
         if (hash_kind == MDN_HASH_BLAKE3) mk::launch_compress_layer_b3(children, parents, n, stream);
         else if (hash_kind == MDN_HASH_KECCAK) mk::launch_compress_layer_kk(children, parents, n, stream);
-        else mk::launch_compress_layer(children, parents, n, stream);
+        else mk::launch_compress_layer(children, parents, n, stream, perm());
     }
     mdn_external_check external_check = nullptr; void* external_ctx = nullptr;   // Statement::eval_external (mdn_session_set_external_check)
     void shard_map_slab(char* base, size_t size);
@@ -690,7 +692,7 @@ u64 mdn_session::grind(u32 bits) {
     ProfScope ps(prof, PC_GRIND);
     while (found == ~0ull) {
         if (start >= gl::P) fail(MDN_ERR_INVALID_ARG, "proof-of-work search exhausted");
-        mk::launch_grind(d.p, ch.in_len, bits, start, batch, d.p + 12, stream);
+        mk::launch_grind(d.p, ch.in_len, bits, start, batch, d.p + 12, stream, perm());
         CUDA_OK(cudaMemcpyAsync(&found, d.p + 12, sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
         start += batch;
@@ -837,7 +839,7 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
     mk::reset_launch_count();
     prof.st = stream; prof.reset(); leaf_bytes = ntt_bytes = 0; perms = 0;
     if (!d_flag.p) { ArenaScope persistent(nullptr); d_flag.alloc(1, stream); CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); }
-    if (!st || !traces || (!chal && hash_kind == MDN_HASH_POSEIDON2)) fail(MDN_ERR_INVALID_ARG, "null argument");
+    if (!st || !traces || (!chal && !byte_hash())) fail(MDN_ERR_INVALID_ARG, "null argument");
     if (st->n_airs == 0 || st->n_airs > 256) fail(MDN_ERR_INVALID_ARG, "AIR count must be in 1..=256");
     if (params.log_folding_arity < 1 || params.log_folding_arity > 3) fail(MDN_ERR_INVALID_ARG, "invalid folding arity: log_arity %u (must be 1, 2, or 3)", params.log_folding_arity);
     u32 lb = params.log_blowup;
@@ -998,7 +1000,8 @@ void mdn_session::prove_begin(const mdn_statement* st, const mdn_matrix* traces,
 
     // challenger: caller's pre-bound state, then Statement::observe + observe_shape (mod.rs:290-291)
     Duplex& ch = tr.ch;
-    if (hash_kind != MDN_HASH_POSEIDON2) {
+    ch.perm = perm();
+    if (byte_hash()) {
         ch.hashed = true; ch.keccak = (hash_kind == MDN_HASH_KECCAK); ch.bin = hash_ch_in; ch.bout = hash_ch_out;      // mdn_session_set_hash_challenger
         if (ch.keccak && ch.bin.size() % 8) fail(MDN_ERR_INVALID_ARG, "Keccak hash challenger: the input buffer must be whole 64-bit words");
     } else {
@@ -1668,7 +1671,7 @@ void mdn_session::finish() {
             perms += (q * (la == 3 ? 2 : 1) + q - 1) / (in_sh ? shard_world : 1);
             if (hash_kind == MDN_HASH_BLAKE3) mk::launch_fri_leaf_hash_b3(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
             else if (hash_kind == MDN_HASH_KECCAK) mk::launch_fri_leaf_hash_kk(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
-            else mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream);
+            else mk::launch_fri_leaf_hash(fri_layers[r].p, q, la, dig, lb, ft0, fnt, stream, perm());
         }
         if (in_sh) shard_barrier();
         if (!split) {
@@ -2157,7 +2160,7 @@ int mdn_session_set_shard(mdn_session* s, uint32_t rank, uint32_t world, mdn_all
 
 int mdn_session_set_hash(mdn_session* s, mdn_hash_kind kind) {
     if (!s) return MDN_ERR_INVALID_ARG;
-    if (kind != MDN_HASH_POSEIDON2 && kind != MDN_HASH_BLAKE3 && kind != MDN_HASH_KECCAK) { s->error = "unknown hash configuration"; return MDN_ERR_UNSUPPORTED; }
+    if (kind < MDN_HASH_POSEIDON2 || kind > MDN_HASH_RPX) { s->error = "unknown hash configuration"; return MDN_ERR_UNSUPPORTED; }
     if (s->in_proof) { s->error = "mdn_session_set_hash called inside a proof"; return MDN_ERR_INVALID_ARG; }
     if (s->has_prep && kind != s->hash_kind) { s->error = "the preprocessed bundle was committed under the other hash: remove it first"; return MDN_ERR_INVALID_ARG; }
     s->hash_kind = kind;

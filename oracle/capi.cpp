@@ -182,15 +182,26 @@ void orc_lmcs_commit(const orc_matrix* mats, uint32_t n, uint64_t root[4], uint6
     }
 }
 
-// STARK hash configuration of every later call (0 = Poseidon2, the default; 1 = Blake3_256; 2 = Keccak) and, for the two byte-oriented ones, the
+// STARK hash configuration of every later call (0 = Poseidon2, the default; 1 = Blake3_256; 2 = Keccak; 3 = RPO; 4 = RPX) and, for the two byte-oriented ones, the
 // pre-bound challenger = the bytes its HashChallenger input buffer holds after `config.challenger()` +
 // `observe_protocol_params` (air/src/config.rs:299-307,188-198); the `orc_challenger*` argument is then ignored.
 static std::vector<uint8_t> g_hash_challenger_input;
 int orc_set_hash(int kind, const uint8_t* challenger_input, size_t n) {
-    if (kind < 0 || kind > 2) return -1;
-    hash_kind() = kind == 2 ? H_KECCAK : kind ? H_BLAKE3 : H_POSEIDON2;
+    if (kind < 0 || kind > 4) return -1;
+    hash_kind() = (HashKind)kind;
     g_hash_challenger_input.assign(challenger_input, challenger_input + (challenger_input ? n : 0));
     return 0;
+}
+// RPO / RPX: the permutation on 12 canonical felts (kind 3 / 4) and AlgebraicSponge::hash_elements (the reference's known answers)
+void orc_rescue_permute(int kind, uint64_t st[12]) {
+    RState s; for (int i = 0; i < 12; i++) s[i] = Fp(st[i]);
+    if (kind == 4) rpx_permute(s); else rpo_permute(s);
+    for (int i = 0; i < 12; i++) st[i] = s[i].v;
+}
+void orc_rescue_hash_elements(int kind, const uint64_t* e, size_t n, uint64_t out[4]) {
+    std::vector<Fp> v(n); for (size_t i = 0; i < n; i++) v[i] = Fp(e[i]);
+    auto d = kind == 4 ? rescue_hash_elements(v.data(), n, [](RState& s) { rpx_permute(s); }) : rescue_hash_elements(v.data(), n, [](RState& s) { rpo_permute(s); });
+    for (int i = 0; i < 4; i++) out[i] = d[i].v;
 }
 // Keccak-256 (pad = 1) / SHA3-256 (pad = 6) of a byte string, and the permutation on 25 lanes
 void orc_keccak256(const uint8_t* p, size_t n, uint8_t pad, uint8_t out[32]) { auto h = keccak::hash256(p, n, pad); memcpy(out, h.data(), 32); }
@@ -198,7 +209,7 @@ void orc_keccak_f(uint64_t st[25]) { std::array<u64, 25> a; memcpy(a.data(), st,
 void orc_blake3(const uint8_t* p, size_t n, uint8_t out[32]) { auto h = blake3::hash(p, n); memcpy(out, h.data(), 32); }
 
 static Challenger to_challenger(const orc_challenger* c) {
-    if (hash_kind() != H_POSEIDON2) return Challenger::from_bytes(g_hash_challenger_input.data(), g_hash_challenger_input.size());
+    if (byte_hash()) return Challenger::from_bytes(g_hash_challenger_input.data(), g_hash_challenger_input.size());
     Challenger ch;
     for (int i = 0; i < 12; i++) ch.st[i] = Fp(c->sponge_state[i]);
     for (uint32_t i = 0; i < c->input_len; i++) ch.in_buf[i] = Fp(c->input_buffer[i]);
@@ -213,7 +224,7 @@ void orc_challenger_script(orc_challenger* c, const uint32_t* ops, const uint64_
     for (int i = 0; i < 12; i++) ch.st[i] = Fp(c->sponge_state[i]);
     for (uint32_t i = 0; i < c->input_len; i++) ch.in_buf[i] = Fp(c->input_buffer[i]);
     ch.in_len = c->input_len; ch.out_len = c->output_len;
-    if (hash_kind() != H_POSEIDON2) ch = to_challenger(c);      // the hash challenger starts from the bytes given to orc_set_hash
+    if (byte_hash()) ch = to_challenger(c);      // the hash challenger starts from the bytes given to orc_set_hash
     for (size_t i = 0; i < n; i++) {
         switch (ops[i]) {
             case 0: ch.observe(Fp(args[i])); out[i] = 0; break;

@@ -8,6 +8,7 @@
 #include "field.hpp"
 #include "blake3.hpp"
 #include "keccak.hpp"
+#include "rescue.hpp"
 #include <array>
 #include <vector>
 
@@ -73,8 +74,17 @@ using Digest = std::array<Fp, 4>;
 //                lanes 0..8, one permutation, lanes 0..4), SerializingChallenger64<HashChallenger<u8, Keccak256Hash, 32>>
 //                (:309-353).  A digest is four u64 lanes, carried raw in a `Digest`.
 // One process-wide switch: the oracle is test infrastructure with a single client at a time.
-enum HashKind { H_POSEIDON2 = 0, H_BLAKE3 = 1, H_KECCAK = 2 };
+//   H_RPO, H_RPX: `rpo_config` / `rpx_config` (:225-248) -- everything of H_POSEIDON2 with the permutation replaced
+//                (`alg_config<P>` is generic in it, :255-273); oracle/rescue.hpp.
+enum HashKind { H_POSEIDON2 = 0, H_BLAKE3 = 1, H_KECCAK = 2, H_RPO = 3, H_RPX = 4 };
 inline HashKind& hash_kind() { static HashKind k = H_POSEIDON2; return k; }
+inline bool byte_hash() { return hash_kind() == H_BLAKE3 || hash_kind() == H_KECCAK; }      // hash challenger instead of the duplex one
+// the permutation of the algebraic configurations
+inline void algebraic_permute(State& s) {
+    if (hash_kind() == H_RPO) rpo_permute(s);
+    else if (hash_kind() == H_RPX) rpx_permute(s);
+    else poseidon2_permute(s);
+}
 inline size_t lmcs_alignment() { return hash_kind() == H_BLAKE3 ? 1 : hash_kind() == H_KECCAK ? 17 : 8; }
 // the 32-byte hash of the byte-oriented challengers
 inline std::array<uint8_t, 32> hash32(const uint8_t* p, size_t n) { return hash_kind() == H_KECCAK ? keccak::hash256(p, n) : blake3::hash(p, n); }
@@ -117,7 +127,7 @@ inline void sponge_absorb_generic(std::array<T, WIDTH>& st, const T* in, size_t 
 }
 inline void sponge_absorb(State& st, const Fp* in, size_t n) {
     if (hash_kind() == H_BLAKE3) { chaining_absorb_blake3(st.data(), in, n); return; }
-    sponge_absorb_generic<Fp, 12, 8>(st, in, n, [](State& s) { poseidon2_permute(s); });
+    sponge_absorb_generic<Fp, 12, 8>(st, in, n, [](State& s) { algebraic_permute(s); });
 }
 inline Digest sponge_squeeze(const State& st) { return Digest{st[0], st[1], st[2], st[3]}; }
 // the Keccak leaf sponge: 25 u64 lanes, rate 17, the row's felts as canonical u64
@@ -146,7 +156,7 @@ inline Digest compress2(const Digest& l, const Digest& r) {
     }
     State s;
     for (int i = 0; i < 4; i++) { s[i] = l[i]; s[4 + i] = r[i]; s[8 + i] = Fp(); }
-    poseidon2_permute(s);
+    algebraic_permute(s);
     return Digest{s[0], s[1], s[2], s[3]};
 }
 

@@ -64,27 +64,27 @@ struct Challenger {
             st[8] = st[8] + Fp::raw((u64)in_len);
             in_len = 0;
         }
-        poseidon2_permute(st);
+        algebraic_permute(st);
         out_len = 8;
     }
     void observe(Fp x) {
-        if (hash_kind() != H_POSEIDON2) { for (int k = 0; k < 8; k++) observe_byte((uint8_t)(x.v >> (8 * k))); return; }
+        if (byte_hash()) { for (int k = 0; k < 8; k++) observe_byte((uint8_t)(x.v >> (8 * k))); return; }
         out_len = 0;
         in_buf[in_len++] = x;
         if (in_len == 8) duplex();
     }
     void observe_digest(const Digest& d) {
-        if (hash_kind() != H_POSEIDON2) { uint8_t b[32]; digest_to_bytes(d.data(), b); for (int i = 0; i < 32; i++) observe_byte(b[i]); return; }
+        if (byte_hash()) { uint8_t b[32]; digest_to_bytes(d.data(), b); for (int i = 0; i < 32; i++) observe_byte(b[i]); return; }
         for (int i = 0; i < 4; i++) observe(d[i]);
     }
     Fp sample() {
-        if (hash_kind() != H_POSEIDON2) { for (;;) { u64 v = sample_u64_bytes(); if (v < P) return Fp::raw(v); } }
+        if (byte_hash()) { for (;;) { u64 v = sample_u64_bytes(); if (v < P) return Fp::raw(v); } }
         if (in_len > 0 || out_len == 0) duplex();
         return st[--out_len];
     }
     Ef sample_ext() { Fp a = sample(); Fp b = sample(); return Ef(a, b); }  // channel.rs:54-56
     u64 sample_bits(unsigned bits) {
-        if (hash_kind() != H_POSEIDON2) return sample_u64_bytes() & ((u64(1) << bits) - 1);
+        if (byte_hash()) return sample_u64_bytes() & ((u64(1) << bits) - 1);
         u64 v = sample().v;
         return v & ((u64(1) << bits) - 1);
     }

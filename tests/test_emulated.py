@@ -67,6 +67,16 @@ def test_keccak_configuration_on_the_emulator():
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
 
 
+def test_rpo_rpx_configurations_on_the_emulator():
+    """`rpo_config` / `rpx_config`: the Poseidon2 kernels instantiated with the Rescue permutations (leaf sponge, nodes, FRI
+    leaves, proof-of-work) and the duplex challenger with them: the -m gpu cases of tests/test_rescue.py on the emulator."""
+    lib = _build("")
+    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_rescue.py"), "-q", "-m", "gpu",
+                        "-p", "no:cacheprovider", "--timeout", "900"], env=env, capture_output=True, text=True, timeout=2400, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+
+
 @pytest.mark.parametrize("world,min_log", [(2, None), (4, 2), (8, None)])
 def test_one_proof_split_over_ranks_on_the_emulator(world, min_log):
     """ONE proof split over `world` ranks (mdn_session_set_shard: LDE cosets, leaf sponge, constraints, quotient chunks,
