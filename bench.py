@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "trace cells/sec proved"
 UNIT = "cells/s"
-HASH_IDS = {"poseidon2": 0, "blake3": 1, "keccak": 2}     # mdn_hash_kind / orc_set_hash
+HASH_IDS = {"poseidon2": 0, "blake3": 1, "keccak": 2, "rpo": 3, "rpx": 4}     # mdn_hash_kind / orc_set_hash
 
 
 def load_peaks():
@@ -97,7 +97,8 @@ class ClockSampler(threading.Thread):
 def workload_name(lh, hash_name="poseidon2"):
     """`config.workload` of BOTH arms (the driver compares the two lines' configs)."""
     h = {"poseidon2": "Poseidon2 LMCS + duplex challenger", "blake3": "Blake3_256 LMCS (chaining hasher) + hash challenger",
-         "keccak": "Keccak LMCS (stateful sponge, rate 17) + Keccak-256 hash challenger"}[hash_name]
+         "keccak": "Keccak LMCS (stateful sponge, rate 17) + Keccak-256 hash challenger",
+         "rpo": "RPO LMCS + duplex challenger", "rpx": "RPX LMCS + duplex challenger"}[hash_name]
     return (f"synthetic 2^{lh} x (51,22,16) Miden-shaped prove (DummyMidenAir degree-9 constraint, zero aux 4/3/1 EF cols), "
             f"96-bit params: blowup 8, FRI arity 4, final degree 2^7, 27 queries, PoW 4/12/16, {h}")
 
@@ -187,8 +188,8 @@ def main():
     ap.add_argument("--ref-log-height", type=int, default=0, help="CPU arm: 0 = the same height as --log-height")
     ap.add_argument("--cpu-log-height", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hash", choices=["poseidon2", "blake3", "keccak"], default="poseidon2",
-                    help="STARK hash configuration: poseidon2 (the metric's; default), blake3 (the CLI default hasher / blake3-bench, BASELINE config 3) or keccak")
+    ap.add_argument("--hash", choices=["poseidon2", "blake3", "keccak", "rpo", "rpx"], default="poseidon2",
+                    help="STARK hash configuration: poseidon2 (the metric's; default), blake3 (the CLI default hasher / blake3-bench, BASELINE config 3), keccak, rpo or rpx (functional coverage; use --no-cpu-baseline)")
     ap.add_argument("--sharding", choices=["coset", "proof"], default="coset",
                     help="N>1: 'coset' (default) = ONE proof split over the GPUs -- LDE cosets, leaf sponge, constraints, DEEP and FRI "
                          "folds per coset, Merkle sub-trees per leaf range, peer-memory stores over NVLink (strong scaling); "
@@ -240,7 +241,8 @@ def main():
     ch = W.initial_challenger(params, observe)
     if args.hash != "poseidon2":
         sess.set_hash(HASH_IDS[args.hash], W.initial_hash_challenger(params))
-        ch = None
+        if args.hash in ("blake3", "keccak"):
+            ch = None         # hash challenger installed with set_hash; rpo / rpx keep the duplex state (any pre-bound state is a valid statement)
 
     # device-resident copies (for `value`) and pinned host copies (for `e2e`)
     dev_t = [torch.from_numpy(t.view(np.int64)).cuda() for t in wl.traces]

@@ -152,6 +152,10 @@ pub enum HashKind {
     Poseidon2 = 0,
     Blake3 = 1,
     Keccak = 2,
+    /// `rpo_config`: the duplex challenger passed to `prove` must be built over `RpoPermutation256`
+    Rpo = 3,
+    /// `rpx_config`
+    Rpx = 4,
 }
 
 /// `mdn_hash_challenger`: p3 `HashChallenger<u8, H, 32>`'s two buffers.

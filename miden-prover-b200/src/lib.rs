@@ -85,14 +85,15 @@ impl GpuSession {
 
     /// Switch the session to another of the reference's STARK hash configurations (`miden_air::config`): `input_buffer` is
     /// the `HashChallenger`'s input buffer after `config.challenger()` + `observe_protocol_params` (32 bytes of relation
-    /// digest + 8 parameter felts as little-endian u64); ignored for [`HashKind::Poseidon2`], whose duplex challenger is
+    /// digest + 8 parameter felts as little-endian u64); ignored for the algebraic configurations ([`HashKind::Poseidon2`],
+    /// [`HashKind::Rpo`], [`HashKind::Rpx`]), whose duplex challenger -- built over the matching permutation -- is
     /// the argument of [`GpuStarkProver::prove`].
     pub fn set_hash(&mut self, kind: HashKind, input_buffer: &[u8]) -> Result<(), ExecutionError> {
         let rc = unsafe { mdn_session_set_hash(self.raw, kind as c_int) };
         if rc != MDN_OK {
             return Err(ExecutionError::ProvingError(last_error(self.raw)));
         }
-        if !matches!(kind, HashKind::Poseidon2) {
+        if matches!(kind, HashKind::Blake3 | HashKind::Keccak) {
             let hc = MdnHashChallenger { input_buffer: input_buffer.as_ptr(), input_len: input_buffer.len(), output_buffer: ptr::null(), output_len: 0 };
             let rc = unsafe { mdn_session_set_hash_challenger(self.raw, &hc) };
             if rc != MDN_OK {
