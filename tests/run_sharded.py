@@ -77,6 +77,10 @@ def main():
     cases.append(("keccak: miden-shape mixed heights", W.miden_pcs_params(), W.Workload([log_h - 1, log_h - 2, log_h - 3]), None, "keccak"))
     cases.append(("keccak: preprocessed columns", W.fast_pcs_params(), test_airs.preprocessed_workload((6, 8), (True, True)), None, "keccak"))
 
+    if os.environ.get("SHARD_SUBSET"):      # one case per feature: mixed heights, host aux, device LogUp, preprocessed, second shape, each hash
+        keep = ("miden-shape mixed heights", "fib + dummy", "LogUp aux", "preprocessed columns", "FRI arity 2^3", "second shape", "blake3: miden", "keccak: miden")
+        cases = [c for c in cases if c[0].startswith(keep)]
+
     sessions = {}     # params tuple -> (single, split): sessions are reused so that arena reuse across shapes is exercised
 
     def sess_for(params, hash_name="poseidon2"):

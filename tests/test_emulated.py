@@ -26,6 +26,29 @@ def _build(gen):
     return os.path.join(EMU, "libmiden_b200_emu.so")
 
 
+# The four single-process suites are started together by whichever of their tests runs first and collected by each test
+# (they are independent python processes; running them side by side keeps the CPU suite within a few minutes).
+_SUITES = {
+    "parity": ["test_gpu_parity.py", SKIP, "300"],
+    "blake3": ["test_blake3.py", "not 2_16", "600"],
+    "keccak": ["test_keccak.py", "not 2_16", "600"],
+    # every RPO case; RPX differs in the permutation only: one proof case and the hash-switch test (the B200 runs all of them)
+    "rescue": ["test_rescue.py", "rpo or two_heights or switch", "900"],
+}
+_jobs = {}
+
+
+def _suite(name):
+    if not _jobs:
+        lib = _build("")
+        env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
+        for key, (file, expr, tmo) in _SUITES.items():
+            _jobs[key] = subprocess.Popen([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", file), "-q", "-m", "gpu", "-k", expr,
+                                           "-p", "no:cacheprovider", "--timeout", tmo], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+    out, err = _jobs[name].communicate(timeout=2400)
+    assert _jobs[name].returncode == 0 and " passed" in out and "failed" not in out, out[-3000:] + err[-1000:]
+
+
 def test_binding_refuses_the_emulator_without_opt_in():
     lib = _build("")
     env = dict(os.environ, MDN_LIB_PATH=lib)
@@ -37,44 +60,27 @@ def test_binding_refuses_the_emulator_without_opt_in():
 
 
 def test_gpu_parity_suite_on_the_emulator():
-    lib = _build("")
-    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
-                        "-k", SKIP, "-p", "no:cacheprovider", "--timeout", "300"],
-                       env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
-    tail = r.stdout[-3000:] + r.stderr[-1000:]
-    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, tail
+    """tests/test_gpu_parity.py (-m gpu, the sizes fibers can run) on the emulator."""
+    _suite("parity")
 
 
 def test_blake3_configuration_on_the_emulator():
     """The Blake3_256 configuration (chaining-hasher LMCS, blake3 nodes, hash challenger, PoW through the hash challenger):
     the -m gpu cases of tests/test_blake3.py on the emulator, bit-exact against the oracle in Blake3 mode."""
-    lib = _build("")
-    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_blake3.py"), "-q", "-m", "gpu", "-k", "not 2_16",
-                        "-p", "no:cacheprovider", "--timeout", "600"], env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
-    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+    _suite("blake3")
 
 
 def test_keccak_configuration_on_the_emulator():
     """The Keccak configuration (stateful sponge with rate 17 / alignment 17 and 25 lanes of state between height groups,
     PaddingFreeSponge nodes, Keccak-256 hash challenger and proof-of-work): the -m gpu cases of tests/test_keccak.py on the
     emulator, bit-exact against the oracle in Keccak mode."""
-    lib = _build("")
-    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_keccak.py"), "-q", "-m", "gpu", "-k", "not 2_16",
-                        "-p", "no:cacheprovider", "--timeout", "600"], env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
-    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+    _suite("keccak")
 
 
 def test_rpo_rpx_configurations_on_the_emulator():
     """`rpo_config` / `rpx_config`: the Poseidon2 kernels instantiated with the Rescue permutations (leaf sponge, nodes, FRI
     leaves, proof-of-work) and the duplex challenger with them: the -m gpu cases of tests/test_rescue.py on the emulator."""
-    lib = _build("")
-    env = dict(os.environ, MDN_LIB_PATH=lib, MDN_ALLOW_EMULATOR="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_rescue.py"), "-q", "-m", "gpu",
-                        "-p", "no:cacheprovider", "--timeout", "900"], env=env, capture_output=True, text=True, timeout=2400, cwd=ROOT)
-    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+    _suite("rescue")
 
 
 @pytest.mark.parametrize("world,min_log", [(2, None), (4, 2), (8, None)])
@@ -91,6 +97,8 @@ def test_one_proof_split_over_ranks_on_the_emulator(world, min_log):
     env.pop("SHARD_BENCH", None)
     if min_log is not None:
         env.update(MDN_SHARD_MIN_LOG=str(min_log), SHARD_DEBUG_STAGES="1")
+    else:
+        env["SHARD_SUBSET"] = "1"      # the full case list runs at world 4 (and on the GPU box); worlds 2 and 8 run one case per feature
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(29711 + world),
                         os.path.join(ROOT, "tests", "run_sharded.py")],
