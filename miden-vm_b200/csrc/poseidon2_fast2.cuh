@@ -172,12 +172,34 @@ GL_HD u64 div2k(u64 x) {
     return (u64)(n << (32 - K)) * EPS + q;
 }
 
+// ---- 96-bit values as operands (the lazy internal rounds keep lanes 1..11 unreduced) -----------------
+// w << k for a wide w (k = 1, 2); the caller's bound keeps the result below 2^96
+GL_HD W wshl96(W w, int k) { W r; r.lo = w.lo << k; r.hi = (w.hi << k) | (u32)(w.lo >> (64 - k)); return r; }
+GL_HD W wshr96(W w, int k) { W r; r.lo = (w.lo >> k) | ((u64)w.hi << (64 - k)); r.hi = w.hi >> k; return r; }
+// w / 2 exactly: (w + (w odd) * p) >> 1
+GL_HD W whalf(W w) {
+    wadd(w, gl::P & (0ull - (w.lo & 1ull)));
+    return wshr96(w, 1);
+}
+// w / 2^K exactly (K = 2, 3): (w + n p) >> K with n = -w mod 2^K (p = 1 mod 2^32), n p = n 2^64 - n (2^32 - 1)
+template <int K>
+GL_HD W wdiv2k(W w) {
+    u32 n = (0u - (u32)w.lo) & ((1u << K) - 1u);
+    w.hi += n;
+    wsub(w, wide((u64)n * EPS));          // n > 0 put n 2^64 on top first, so the difference stays non-negative
+    return wshr96(w, K);
+}
+
 }  // namespace glf
 
 namespace p2f {
 using gl::u64;
 using gl::u32;
 using glf::W;
+
+#if !defined(__CUDA_ARCH__) && defined(P2F_TRACK_BOUNDS)
+static u32 p2f_max_hi = 0;      // host test instrumentation: largest high word a lazy lane ever held
+#endif
 
 GL_HD u64 sbox(u64 x) {
     u64 x2 = glf::mul(x, x), x3 = glf::mul(x2, x), x4 = glf::mul(x2, x2);
@@ -239,6 +261,71 @@ GL_HD void internal_layer(u64* s) {
     o = sum; glf::wadd(o, e11); s[11] = glf::wred(o);
 }
 
+// The 22 internal rounds with lanes 1..11 kept as UNREDUCED 96-bit values: only lane 0 enters an S-box, so only
+// lane 0 is reduced every round; the other lanes are reduced after every block of 8 rounds (8 + 8 + 6).  Bounds, with M_j the
+// bound of the lanes entering round j of a block (M_0 = 2^64): sum_j < 2^64 + 11 M_j, the subtracting lanes use
+// sum_j + OFF_j with OFF_j = ceil(4 M_j / p) p >= |d| lane, and M_(j+1) = sum_j + max(4 M_j, OFF_j) -- 2^68.1, 2^72.0, 2^75.9, 2^79.8,
+// 2^83.7, 2^87.6, 2^91.5, 2^95.5 < 2^96 (tests/cpp/test_arith_v2.cpp recomputes the table and tracks the largest value seen).
+// Per round this removes 11 of the 12 reductions (one IMAD.WIDE + five ALU instructions each) for one extra register per lane:
+// SASS per round 267 -> 251 instructions, IMAD.WIDE 35 -> 24 (the FMA-heavy pipe is the binding one), still 80 registers.
+// -DP2_EAGER_INTERNAL restores the round-by-round reduction.
+#define P2F_OFF_LO {0xfffffffb00000005ull, 0xffffffbb00000045ull, 0xfffffbfb00000405ull, 0xffffc3bb00003c45ull, \
+                    0xfffc77fb00038805ull, 0xffcb07bb0034f845ull, 0xfce573fb031a8c05ull, 0xd171cbbb2e8e3445ull}
+#define P2F_OFF_HI {0x4u, 0x44u, 0x404u, 0x3c44u, 0x38804u, 0x34f844u, 0x31a8c04u, 0x2e8e3444u}
+static const u64 H_OFF_LO[8] = P2F_OFF_LO;
+static const u32 H_OFF_HI[8] = P2F_OFF_HI;
+#ifdef __CUDACC__
+__constant__ u64 D_OFF_LO[8] = P2F_OFF_LO;
+__constant__ u32 D_OFF_HI[8] = P2F_OFF_HI;
+#endif
+
+GL_HD void internal_rounds_lazy(u64* s, const u64* rc) {
+#ifdef __CUDA_ARCH__
+    const u64* off_lo = D_OFF_LO; const u32* off_hi = D_OFF_HI;
+#else
+    const u64* off_lo = H_OFF_LO; const u32* off_hi = H_OFF_HI;
+#endif
+    W L[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++) L[i] = glf::wide(s[i + 1]);
+    u64 s0 = s[0];
+    int r = 0;
+#pragma unroll 1
+    for (int blk = 0; blk < 3; blk++) {
+        const int n = blk < 2 ? 8 : 6;
+#pragma unroll 1
+        for (int j = 0; j < n; j++, r++) {
+            s0 = sbox(glf::add_const(s0, rc[r]));
+            W sum = glf::wide(s0);
+#pragma unroll
+            for (int i = 0; i < 11; i++) glf::wadd(sum, L[i]);
+            W sump = sum;
+            { W off; off.lo = off_lo[j]; off.hi = off_hi[j]; glf::wadd(sump, off); }
+            W t;
+            t = sump; glf::wsub(t, glf::wshl(s0, 1)); s0 = glf::wred(t);                              // d0 = -2
+            glf::wadd(L[0], sum);                                                                     // 1
+            L[1] = glf::wshl96(L[1], 1); glf::wadd(L[1], sum);                                        // 2
+            L[2] = glf::whalf(L[2]); glf::wadd(L[2], sum);                                            // 1/2
+            t = glf::wshl96(L[3], 1); glf::wadd(t, L[3]); glf::wadd(t, sum); L[3] = t;                // 3
+            L[4] = glf::wshl96(L[4], 2); glf::wadd(L[4], sum);                                        // 4
+            t = sump; glf::wsub(t, glf::whalf(L[5])); L[5] = t;                                       // -1/2
+            { W t3 = glf::wshl96(L[6], 1); glf::wadd(t3, L[6]); t = sump; glf::wsub(t, t3); L[6] = t; }   // -3
+            t = sump; glf::wsub(t, glf::wshl96(L[7], 2)); L[7] = t;                                   // -4
+            L[8] = glf::wdiv2k<2>(L[8]); glf::wadd(L[8], sum);                                        // 1/4
+            t = sump; glf::wsub(t, glf::wdiv2k<2>(L[9])); L[9] = t;                                   // -1/4
+            L[10] = glf::wdiv2k<3>(L[10]); glf::wadd(L[10], sum);                                     // 1/8
+#if !defined(__CUDA_ARCH__) && defined(P2F_TRACK_BOUNDS)
+            for (int i = 0; i < 11; i++) if (L[i].hi > p2f_max_hi) p2f_max_hi = L[i].hi;
+#endif
+        }
+#pragma unroll
+        for (int i = 0; i < 11; i++) L[i] = glf::wide(glf::wred(L[i]));
+    }
+    s[0] = s0;
+#pragma unroll
+    for (int i = 0; i < 11; i++) s[i + 1] = L[i].lo;
+}
+
 #ifdef __CUDA_ARCH__
 #define P2F_RC_EXT_INITIAL p2::D_RC_EXT_INITIAL
 #define P2F_RC_EXT_TERMINAL p2::D_RC_EXT_TERMINAL
@@ -264,11 +351,15 @@ GL_HD void permute(u64* s) {
             external_layer(s);
         }
         if (phase == 0) {
+#ifndef P2_EAGER_INTERNAL      // B200, 2^20 proof: leaf sponge 89.06 -> 86.19 ms, nodes 17.26 -> 16.72 ms, identical proof bytes (profiles/r2_tuning.md)
+            internal_rounds_lazy(s, P2F_RC_INTERNAL);
+#else
 #pragma unroll 1
             for (int r = 0; r < 22; r++) {
                 s[0] = sbox(glf::add_const(s[0], P2F_RC_INTERNAL[r]));
                 internal_layer(s);
             }
+#endif
         }
     }
 }

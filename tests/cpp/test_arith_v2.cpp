@@ -60,6 +60,44 @@ int main() {
         p2f::permute(a); p2::permute(b);
         for (int k = 0; k < 12; k++) CHECK(cn(a[k]) == b[k], "permutation word %d", k);
     }
+#ifndef P2_EAGER_INTERNAL
+    // 96-bit helpers of the lazy internal rounds against 128-bit integer arithmetic
+    for (int i = 0; i < 400000; i++) {
+        glf::W w; w.lo = pick(i); w.hi = (unsigned)(rnd() >> (32 + (i % 29)));         // any high word up to 2^32 - 1 >> small shifts
+        unsigned __int128 v = ((unsigned __int128)w.hi << 64) | w.lo;
+        auto val = [](glf::W x) { return ((unsigned __int128)x.hi << 64) | x.lo; };
+        if (w.hi < (1u << 29)) {
+            CHECK(val(glf::wshl96(w, 1)) == v * 2 && val(glf::wshl96(w, 2)) == v * 4, "wshl96");
+            glf::W h = glf::whalf(w);
+            CHECK(val(h) * 2 % gl::P == v % gl::P && val(h) <= (v + gl::P) / 2, "whalf");
+            glf::W q = glf::wdiv2k<2>(w), e = glf::wdiv2k<3>(w);
+            CHECK(val(q) * 4 % gl::P == v % gl::P && val(q) <= v / 4 + gl::P, "wdiv4");
+            CHECK(val(e) * 8 % gl::P == v % gl::P && val(e) <= v / 8 + gl::P, "wdiv8");
+        }
+        CHECK(cn(glf::wred(w)) == (u64)(v % gl::P), "wred of a 96-bit value");
+    }
+    // the offset table: OFF_j = ceil(4 M_j / p) p, M_(j+1) = 2^64 + 11 M_j + max(4 M_j, OFF_j) < 2^96 for the 8 rounds of a block
+    {
+        unsigned __int128 M = (unsigned __int128)1 << 64, lim = (unsigned __int128)1 << 96;
+        for (int j = 0; j < 8; j++) {
+            unsigned __int128 C = (4 * M + gl::P - 1) / gl::P, OFF = C * gl::P, S = ((unsigned __int128)1 << 64) + 11 * M;
+            CHECK((u64)OFF == p2f::H_OFF_LO[j] && (unsigned)(OFF >> 64) == p2f::H_OFF_HI[j], "offset table entry %d", j);
+            CHECK(OFF >= 4 * M && S + OFF < lim && 4 * M + S < lim, "bound of round %d", j);
+            M = S + (OFF > 4 * M ? OFF : 4 * M);
+        }
+    }
+    // worst-case drivers for the bound: every lane at 2^64 - 1 and at p - 1 on entry
+    for (int it = 0; it < 2000; it++) {
+        u64 a[12], b[12];
+        for (int k = 0; k < 12; k++) { a[k] = (it & 1) ? 0xFFFFFFFFFFFFFFFFull : (it & 2) ? gl::P - 1 : pick(it + k) | 0xFFFFFFFF00000000ull; b[k] = cn(a[k]); }
+        a[0] = pick(it); b[0] = cn(a[0]);
+        p2f::permute(a); p2::permute(b);
+        for (int k = 0; k < 12; k++) CHECK(cn(a[k]) == b[k], "permutation (large lanes) word %d", k);
+    }
+#ifdef P2F_TRACK_BOUNDS
+    printf("lazy internal rounds: largest lane high word seen 2^%.2f (limit 2^32)\n", p2f::p2f_max_hi ? __builtin_log2((double)p2f::p2f_max_hi) : 0.0);
+#endif
+#endif
     // reference KAT: input 0..11 (test.rs:7-39)
     static const u64 KAT[12] = {0xf292ab67c0f14b03ull, 0x0a32f1b37656544cull, 0x053c61ab895498deull, 0x02ff92e55b196ffbull,
                                 0x58176e8f6f58cab2ull, 0xb0aa1206e7aec0f8ull, 0xe90c13f3dce83ca4ull, 0xf4da15333edf39c2ull,
