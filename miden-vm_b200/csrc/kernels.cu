@@ -1104,7 +1104,33 @@ void launch_pow_bitrev(E2 y, u32 n, u64* wvec, u64* scratch, size_t p0, size_t c
     COUNT_LAUNCH(); COUNT_LAUNCH();
 }
 
+// 160-bit accumulator of unreduced 64 x 64 -> 128-bit products
+struct Acc160 { u64 lo, mid; u32 hi; };
+__device__ __forceinline__ void acc_mul(Acc160& A, u64 x, u64 y) {
+    unsigned __int128 q = (unsigned __int128)x * y;
+    u64 ql = (u64)q, qh = (u64)(q >> 64);
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(A.lo), "+l"(A.mid), "+r"(A.hi) : "l"(ql), "l"(qh));
+#else
+    unsigned __int128 s0 = (unsigned __int128)A.lo + ql;
+    unsigned __int128 s1 = (unsigned __int128)A.mid + qh + (u64)(s0 >> 64);
+    A.lo = (u64)s0; A.mid = (u64)s1; A.hi += (u32)(s1 >> 64);
+#endif
+}
+// lo + mid * 2^64 + hi * 2^128 mod p, canonical.  2^64 = 2^32 - 1 and 2^96 = -1, so 2^128 = -2^32: the first two words go
+// through the ordinary 128-bit reduction, and hi * 2^32 (< p for every hi < 2^32) is subtracted.
+__device__ __forceinline__ u64 acc_reduce(const Acc160& A) {
+    u64 r = glf::canon_cc(glf::red128(A.lo, A.mid));
+    return glf::csub(r, (u64)A.hi << 32);
+}
+// Column dot products with the two weight vectors of an opening point pair: like k_deep, the 128-bit products are accumulated
+// unreduced (a thread adds chunk / 256 of them per accumulator) and reduced once; 4 columns x 4 weight coordinates per thread
+// (16 accumulators of five registers).  OOD_EAGER restores the reduce-every-product form with 8 columns per thread.
+#ifdef OOD_EAGER
 static constexpr int OOD_COLS = 8;
+#else
+static constexpr int OOD_COLS = 4;
+#endif
 __global__ void __launch_bounds__(256) k_ood_dot(const u64* __restrict__ coef, size_t col_stride, u32 n_cols, u32 n,
                                                  const u64* __restrict__ w0, const u64* __restrict__ w1,
                                                  u64* __restrict__ partial, u32 n_chunks) {
@@ -1113,11 +1139,12 @@ __global__ void __launch_bounds__(256) k_ood_dot(const u64* __restrict__ coef, s
     size_t chunk = N / n_chunks;
     size_t p0 = (size_t)blockIdx.x * chunk;
     u32 c0 = blockIdx.y * OOD_COLS;
-    u64 acc[OOD_COLS * 4];
-#pragma unroll
-    for (int i = 0; i < OOD_COLS * 4; i++) acc[i] = 0;
     const ulonglong2* W0 = reinterpret_cast<const ulonglong2*>(w0);
     const ulonglong2* W1 = reinterpret_cast<const ulonglong2*>(w1);
+    u64 acc[OOD_COLS * 4];
+#ifdef OOD_EAGER
+#pragma unroll
+    for (int i = 0; i < OOD_COLS * 4; i++) acc[i] = 0;
     for (size_t p = p0 + threadIdx.x; p < p0 + chunk; p += blockDim.x) {
         ulonglong2 a = W0[p], b = W1[p];
 #pragma unroll
@@ -1131,6 +1158,24 @@ __global__ void __launch_bounds__(256) k_ood_dot(const u64* __restrict__ coef, s
             }
         }
     }
+#else
+    Acc160 A[OOD_COLS * 4];
+#pragma unroll
+    for (int i = 0; i < OOD_COLS * 4; i++) A[i] = Acc160{0, 0, 0};
+    for (size_t p = p0 + threadIdx.x; p < p0 + chunk; p += blockDim.x) {
+        ulonglong2 a = W0[p], b = W1[p];
+        u64 v[OOD_COLS];
+#pragma unroll
+        for (int c = 0; c < OOD_COLS; c++) v[c] = (c0 + c < n_cols) ? coef[(size_t)(c0 + c) * col_stride + p] : 0ull;
+#pragma unroll
+        for (int c = 0; c < OOD_COLS; c++) {
+            acc_mul(A[4 * c + 0], a.x, v[c]); acc_mul(A[4 * c + 1], a.y, v[c]);
+            acc_mul(A[4 * c + 2], b.x, v[c]); acc_mul(A[4 * c + 3], b.y, v[c]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < OOD_COLS * 4; i++) acc[i] = acc_reduce(A[i]);
+#endif
 #pragma unroll
     for (int i = 0; i < OOD_COLS * 4; i++) {
         u64 v = acc[i];
@@ -1167,25 +1212,6 @@ void launch_ood_reduce(const u64* partial, u32 n_cols, u32 n_chunks, u64* out, c
 // =============================================================================================
 // DEEP quotient
 // =============================================================================================
-// 160-bit accumulator of unreduced 64 x 64 -> 128-bit products
-struct Acc160 { u64 lo, mid; u32 hi; };
-__device__ __forceinline__ void acc_mul(Acc160& A, u64 x, u64 y) {
-    unsigned __int128 q = (unsigned __int128)x * y;
-    u64 ql = (u64)q, qh = (u64)(q >> 64);
-#if defined(__CUDA_ARCH__)
-    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(A.lo), "+l"(A.mid), "+r"(A.hi) : "l"(ql), "l"(qh));
-#else
-    unsigned __int128 s0 = (unsigned __int128)A.lo + ql;
-    unsigned __int128 s1 = (unsigned __int128)A.mid + qh + (u64)(s0 >> 64);
-    A.lo = (u64)s0; A.mid = (u64)s1; A.hi += (u32)(s1 >> 64);
-#endif
-}
-// lo + mid * 2^64 + hi * 2^128 mod p, canonical.  2^64 = 2^32 - 1 and 2^96 = -1, so 2^128 = -2^32: the first two words go
-// through the ordinary 128-bit reduction, and hi * 2^32 (< p for every hi < 2^32) is subtracted.
-__device__ __forceinline__ u64 acc_reduce(const Acc160& A) {
-    u64 r = glf::canon_cc(glf::red128(A.lo, A.mid));
-    return glf::csub(r, (u64)A.hi << 32);
-}
 struct DeepKArgs {
     const DeepMat* m; int n_mats;
     u32 log_n, log_b;
@@ -1196,50 +1222,89 @@ struct DeepKArgs {
     u64 shift, w_l;
     u32 t0, nt;
 };
+// PTS points per thread: point k lies k/PTS of the rank's range further on, so every stream stays coalesced; PTS points multiply
+// the independent column loads in flight (4 columns x PTS points) and share ONE field inversion for their denominators
+// (z0 - x)(z1 - x) (Montgomery's trick) -- the inversion (a Fermat power, ~100 multiplications) is as much arithmetic as the
+// 121-column dot products of a point.  B200, 2^20 proof: PTS = 1 -> 2: 3.65 -> 2.64 ms (tools/ab_check.py timing).
+#ifndef DEEP_PTS
+#define DEEP_PTS 2
+#endif
+template <int PTS>
 __global__ void __launch_bounds__(256) k_deep(DeepKArgs a) {
     extern __shared__ u64 sm_apow[];
     for (u32 i = threadIdx.x; i < 2 * a.total_w; i += blockDim.x) sm_apow[i] = a.apow[i];
     __syncthreads();
-    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= ((size_t)a.nt << a.log_n)) return;
-    pos += (size_t)a.t0 << a.log_n;
-    u32 t = (u32)(pos >> a.log_n), r = (u32)(pos & (((size_t)1 << a.log_n) - 1));
+    const size_t per = ((size_t)a.nt << a.log_n) / PTS;          // launch_deep picks PTS so that it divides the range
+    size_t pos0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos0 >= per) return;
+    pos0 += (size_t)a.t0 << a.log_n;
     // f_red(x) = sum_i alpha^(W-1-i) col_i(x): two base-field dot products (one per extension coordinate of the alpha
     // powers).  The 128-bit products are accumulated UNREDUCED in 160-bit accumulators and reduced once at the end
     // (at most 2^32 terms fit; a proof has a few hundred columns): a column costs two wide multiplications and two
     // three-word additions instead of two modular multiplications and their reductions (ncu r2b: the kernel was bound by
     // the integer pipes at ~85 instructions per column, not by HBM).
-    Acc160 fa{0, 0, 0}, fb{0, 0, 0};
+    Acc160 fa[PTS], fb[PTS];
+    u32 t[PTS], r[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; k++) {
+        fa[k] = Acc160{0, 0, 0}; fb[k] = Acc160{0, 0, 0};
+        size_t pos = pos0 + (size_t)k * per;
+        t[k] = (u32)(pos >> a.log_n); r[k] = (u32)(pos & (((size_t)1 << a.log_n) - 1));
+    }
     for (int m = 0; m < a.n_mats; m++) {
         const DeepMat M = a.m[m];
         size_t Lm = (size_t)1 << (M.log_n + a.log_b);
-        size_t pm = ((size_t)t << M.log_n) + (r & ((1u << M.log_n) - 1));
-        const u64* base = M.base + pm;
+        const u64* base[PTS];
+#pragma unroll
+        for (int k = 0; k < PTS; k++) base[k] = M.base + ((size_t)t[k] << M.log_n) + (r[k] & ((1u << M.log_n) - 1));
         const u64* ap = sm_apow + 2 * M.alpha_off;
         u32 c = 0;
-        // four independent column loads in flight per thread (eight measured slower: 3.30 against 3.13 ms at 2^20)
+        // four independent column loads in flight per point (eight measured slower: 3.30 against 3.13 ms at 2^20)
         for (; c + 4 <= M.width; c += 4) {
-            u64 v0 = base[(size_t)c * Lm], v1 = base[(size_t)(c + 1) * Lm];
-            u64 v2 = base[(size_t)(c + 2) * Lm], v3 = base[(size_t)(c + 3) * Lm];
-            acc_mul(fa, ap[2 * c], v0); acc_mul(fb, ap[2 * c + 1], v0);
-            acc_mul(fa, ap[2 * c + 2], v1); acc_mul(fb, ap[2 * c + 3], v1);
-            acc_mul(fa, ap[2 * c + 4], v2); acc_mul(fb, ap[2 * c + 5], v2);
-            acc_mul(fa, ap[2 * c + 6], v3); acc_mul(fb, ap[2 * c + 7], v3);
+            u64 v[PTS][4];
+#pragma unroll
+            for (int k = 0; k < PTS; k++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[k][j] = base[k][(size_t)(c + j) * Lm];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                u64 pa = ap[2 * (c + j)], pb = ap[2 * (c + j) + 1];
+#pragma unroll
+                for (int k = 0; k < PTS; k++) { acc_mul(fa[k], pa, v[k][j]); acc_mul(fb[k], pb, v[k][j]); }
+            }
         }
         for (; c < M.width; c++) {
-            u64 v = base[(size_t)c * Lm];
-            acc_mul(fa, ap[2 * c], v); acc_mul(fb, ap[2 * c + 1], v);
+#pragma unroll
+            for (int k = 0; k < PTS; k++) {
+                u64 v = base[k][(size_t)c * Lm];
+                acc_mul(fa[k], ap[2 * c], v); acc_mul(fb[k], ap[2 * c + 1], v);
+            }
         }
     }
-    E2 fr = gl::e2(acc_reduce(fa), acc_reduce(fb));
-    u64 x = gl::mul(gl::mul(a.shift, gl::pow(a.w_l, t)), w_pow(a.w_hi, a.w_lo, a.lo_bits, r));
-    E2 d0 = gl::e2(gl::sub(a.z0.a, x), a.z0.b), d1 = gl::e2(gl::sub(a.z1.a, x), a.z1.b);
-    E2 inv = gl::e2_inv(gl::e2_mul(d0, d1));
-    E2 i0 = gl::e2_mul(inv, d1), i1 = gl::e2_mul(inv, d0);
-    E2 q = gl::e2_add(gl::e2_mul(i0, gl::e2_sub(a.fz0, fr)),
-                      gl::e2_mul(a.beta, gl::e2_mul(i1, gl::e2_sub(a.fz1, fr))));
-    size_t i = ((size_t)r << a.log_b) | t;
-    push_u2(a.out, i, i, make_ulonglong2(q.a, q.b));
+    E2 d0[PTS], d1[PTS], den[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; k++) {
+        u64 x = gl::mul(gl::mul(a.shift, gl::pow(a.w_l, t[k])), w_pow(a.w_hi, a.w_lo, a.lo_bits, r[k]));
+        d0[k] = gl::e2(gl::sub(a.z0.a, x), a.z0.b); d1[k] = gl::e2(gl::sub(a.z1.a, x), a.z1.b);
+        den[k] = gl::e2_mul(d0[k], d1[k]);
+    }
+    E2 inv[PTS], prefix[PTS];
+    prefix[0] = den[0];
+#pragma unroll
+    for (int k = 1; k < PTS; k++) prefix[k] = gl::e2_mul(prefix[k - 1], den[k]);
+    E2 run = gl::e2_inv(prefix[PTS - 1]);              // 1 / (den_0 ... den_(PTS-1)), peeled from the back
+#pragma unroll
+    for (int k = PTS - 1; k > 0; k--) { inv[k] = gl::e2_mul(run, prefix[k - 1]); run = gl::e2_mul(run, den[k]); }
+    inv[0] = run;
+#pragma unroll
+    for (int k = 0; k < PTS; k++) {
+        E2 fr = gl::e2(acc_reduce(fa[k]), acc_reduce(fb[k]));
+        E2 i0 = gl::e2_mul(inv[k], d1[k]), i1 = gl::e2_mul(inv[k], d0[k]);
+        E2 q = gl::e2_add(gl::e2_mul(i0, gl::e2_sub(a.fz0, fr)),
+                          gl::e2_mul(a.beta, gl::e2_mul(i1, gl::e2_sub(a.fz1, fr))));
+        size_t i = ((size_t)r[k] << a.log_b) | t[k];
+        push_u2(a.out, i, i, make_ulonglong2(q.a, q.b));
+    }
 }
 void launch_deep(const DeepArgs& a, cudaStream_t st) {
     DeepKArgs k;
@@ -1251,7 +1316,8 @@ void launch_deep(const DeepArgs& a, cudaStream_t st) {
     u32 B = 1u << a.log_blowup;
     k.t0 = a.nt ? a.t0 : 0; k.nt = a.nt ? a.nt : B;
     size_t cnt = (size_t)k.nt << a.log_n_max;
-    k_deep<<<(unsigned)((cnt + 255) / 256), 256, 2 * a.total_w * sizeof(u64), st>>>(k);
+    if (DEEP_PTS > 1 && cnt % (256 * DEEP_PTS) == 0) k_deep<DEEP_PTS><<<(unsigned)(cnt / (256 * DEEP_PTS)), 256, 2 * a.total_w * sizeof(u64), st>>>(k);
+    else k_deep<1><<<(unsigned)((cnt + 255) / 256), 256, 2 * a.total_w * sizeof(u64), st>>>(k);
     COUNT_LAUNCH();
 }
 

@@ -96,6 +96,9 @@ GL_HD u64 mul(u64 a, u64 b) {
     u128 q = (u128)a * b;
     return red128((u64)q, (u64)(q >> 64));
 }
+// a^2.  (Three partial products, a0^2 + a0 a1 2^33 + a1^2 2^64, were measured on the B200: leaf sponge 86.1 -> 93.0 ms --
+// the shifts and the extra carry chain cost more than the saved IMAD.WIDE; profiles/r2_tuning.md.)
+GL_HD u64 sqr(u64 a) { return mul(a, a); }
 
 // x + k for a canonical constant k (< p): a carry leaves r < k < p, so the fold fits.
 GL_HD u64 add_const(u64 x, u64 k) {
@@ -186,7 +189,7 @@ template <int K>
 GL_HD W wdiv2k(W w) {
     u32 n = (0u - (u32)w.lo) & ((1u << K) - 1u);
     w.hi += n;
-    wsub(w, wide((u64)n * EPS));          // n > 0 put n 2^64 on top first, so the difference stays non-negative
+    wsub(w, wide((u64)n * EPS));          // n > 0 put n 2^64 on top first, so the difference stays non-negative ((n << 32) - n on the ALU pipe: no difference)
     return wshr96(w, K);
 }
 
@@ -202,7 +205,7 @@ static u32 p2f_max_hi = 0;      // host test instrumentation: largest high word 
 #endif
 
 GL_HD u64 sbox(u64 x) {
-    u64 x2 = glf::mul(x, x), x3 = glf::mul(x2, x), x4 = glf::mul(x2, x2);
+    u64 x2 = glf::sqr(x), x3 = glf::mul(x2, x), x4 = glf::sqr(x2);
     return glf::mul(x3, x4);
 }
 

@@ -31,6 +31,7 @@ int main() {
         unsigned __int128 q = (unsigned __int128)a * b;
         u64 want = (u64)(q % gl::P);
         CHECK(cn(glf::mul(a, b)) == want, "mul %llx %llx", (unsigned long long)a, (unsigned long long)b);
+        CHECK(cn(glf::sqr(a)) == (u64)(((unsigned __int128)a * a) % gl::P), "sqr %llx", (unsigned long long)a);
         CHECK(glf::cmul(cn(a), cn(b)) == want, "cmul");
         CHECK(glf::cadd(cn(a), cn(b)) == (u64)(((unsigned __int128)cn(a) + cn(b)) % gl::P), "cadd");
         CHECK(glf::csub(cn(a), cn(b)) == (u64)(((unsigned __int128)cn(a) + gl::P - cn(b)) % gl::P), "csub");
