@@ -1124,13 +1124,10 @@ __device__ __forceinline__ u64 acc_reduce(const Acc160& A) {
     return glf::csub(r, (u64)A.hi << 32);
 }
 // Column dot products with the two weight vectors of an opening point pair: like k_deep, the 128-bit products are accumulated
-// unreduced (a thread adds chunk / 256 of them per accumulator) and reduced once; 4 columns x 4 weight coordinates per thread
-// (16 accumulators of five registers).  OOD_EAGER restores the reduce-every-product form with 8 columns per thread.
-#ifdef OOD_EAGER
-static constexpr int OOD_COLS = 8;
-#else
-static constexpr int OOD_COLS = 4;
-#endif
+// unreduced (a thread adds chunk / 256 of them per accumulator) and reduced once; 2 columns x 4 weight coordinates per thread
+// (8 accumulators of five registers, 74 registers).  B200, 2^20 proof, OOD phase: reducing every product (8 columns per
+// thread) 1.95 ms, unreduced with 4 columns 1.29 ms, with 2 columns 1.22 ms (profiles/r2_tuning.md).
+static constexpr int OOD_COLS = 2;
 __global__ void __launch_bounds__(256) k_ood_dot(const u64* __restrict__ coef, size_t col_stride, u32 n_cols, u32 n,
                                                  const u64* __restrict__ w0, const u64* __restrict__ w1,
                                                  u64* __restrict__ partial, u32 n_chunks) {
@@ -1142,23 +1139,6 @@ __global__ void __launch_bounds__(256) k_ood_dot(const u64* __restrict__ coef, s
     const ulonglong2* W0 = reinterpret_cast<const ulonglong2*>(w0);
     const ulonglong2* W1 = reinterpret_cast<const ulonglong2*>(w1);
     u64 acc[OOD_COLS * 4];
-#ifdef OOD_EAGER
-#pragma unroll
-    for (int i = 0; i < OOD_COLS * 4; i++) acc[i] = 0;
-    for (size_t p = p0 + threadIdx.x; p < p0 + chunk; p += blockDim.x) {
-        ulonglong2 a = W0[p], b = W1[p];
-#pragma unroll
-        for (int c = 0; c < OOD_COLS; c++) {
-            if (c0 + c < n_cols) {
-                u64 v = coef[(size_t)(c0 + c) * col_stride + p];
-                acc[4 * c + 0] = gl::add(acc[4 * c + 0], gl::mul(a.x, v));
-                acc[4 * c + 1] = gl::add(acc[4 * c + 1], gl::mul(a.y, v));
-                acc[4 * c + 2] = gl::add(acc[4 * c + 2], gl::mul(b.x, v));
-                acc[4 * c + 3] = gl::add(acc[4 * c + 3], gl::mul(b.y, v));
-            }
-        }
-    }
-#else
     Acc160 A[OOD_COLS * 4];
 #pragma unroll
     for (int i = 0; i < OOD_COLS * 4; i++) A[i] = Acc160{0, 0, 0};
@@ -1175,7 +1155,6 @@ __global__ void __launch_bounds__(256) k_ood_dot(const u64* __restrict__ coef, s
     }
 #pragma unroll
     for (int i = 0; i < OOD_COLS * 4; i++) acc[i] = acc_reduce(A[i]);
-#endif
 #pragma unroll
     for (int i = 0; i < OOD_COLS * 4; i++) {
         u64 v = acc[i];
@@ -1225,7 +1204,8 @@ struct DeepKArgs {
 // PTS points per thread: point k lies k/PTS of the rank's range further on, so every stream stays coalesced; PTS points multiply
 // the independent column loads in flight (4 columns x PTS points) and share ONE field inversion for their denominators
 // (z0 - x)(z1 - x) (Montgomery's trick) -- the inversion (a Fermat power, ~100 multiplications) is as much arithmetic as the
-// 121-column dot products of a point.  B200, 2^20 proof: PTS = 1 -> 2: 3.65 -> 2.64 ms (tools/ab_check.py timing).
+// 121-column dot products of a point.  B200, 2^20 proof (tools/ab_check.py timing): PTS = 1: 3.65 ms, 2: 2.64 ms, 4: 4.12 ms
+// (164 registers).
 #ifndef DEEP_PTS
 #define DEEP_PTS 2
 #endif
