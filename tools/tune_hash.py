@@ -7,9 +7,12 @@ tools/ab_check.py on each (KAT, bit-exact small proofs, 2^20 proof verified by t
     python tools/tune_hash.py run                        # on the GPU box: one line per variant + gpurun_out/tune_*.json
 
 Remaining switches: -DHASH_MIN_BLOCKS=k (default 6: 80 registers), -DP2_LINEAR_FOLD_IMAD, -DP2_FOLD_IMAD (both folds back on the FMA
-pipe), -DMDN_GL_SLOW (branchy gl:: arithmetic), -DMDN_GEN1 (first generation).  Every other knob of round 1 was timed in
-round 2 and removed (profiles/r2_tuning.md): hash block sizes 64/256, NTT resident-block bounds, internal rounds unrolled by
-two and x2*(2^32-1) on the ALU pipe all lost or made no difference; MDN_GL_FAST and the ALU-pipe fold won and are defaults.
+pipe), -DP2_EAGER_INTERNAL (reduce every lane in every internal round), -DDEEP_PTS=k (points per thread of k_deep, default 2),
+-DMDN_GL_SLOW (branchy gl:: arithmetic), -DMDN_GEN1 (first generation).  Every other knob was timed in round 2 and removed
+(profiles/r2_tuning.md): hash block sizes 64/256, NTT resident-block bounds, internal rounds unrolled by two, x2*(2^32-1) on the
+ALU pipe, three-product squarings, the ALU form of the exact divisions and the reduce-every-product OOD kernel all lost or made
+no difference; MDN_GL_FAST, the ALU-pipe fold, the lazy internal rounds, the two-point DEEP kernel and the unreduced OOD
+accumulation won and are defaults.
 Round-1 results: profiles/r1_summary.md "r1l" (HASH_MIN_BLOCKS 1..8, linear-layer folds)."""
 import json
 import os
@@ -19,7 +22,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "miden-vm_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_tune")
-DEFAULT = ["base=", "foldimad=-DP2_FOLD_IMAD", "linimad=-DP2_LINEAR_FOLD_IMAD", "glslow=-DMDN_GL_SLOW", "mb5=-DHASH_MIN_BLOCKS=5", "mb7=-DHASH_MIN_BLOCKS=7"]
+DEFAULT = ["base=", "eager=-DP2_EAGER_INTERNAL", "foldimad=-DP2_FOLD_IMAD", "glslow=-DMDN_GL_SLOW", "mb5=-DHASH_MIN_BLOCKS=5", "deep1=-DDEEP_PTS=1"]
 
 
 def build(specs):
