@@ -348,7 +348,7 @@ def main():
         try:
             ipp2 = (tj.get("thread_instructions_per_permutation") if os.path.exists(tf) else None) or 13673
             instr_per_perm = {1: (15960, "ncu inst_executed of the first-generation kernel (round-1 capture r1i)"),
-                              2: (round(ipp2), "ncu smsp__inst_executed x 32 / permutations of the k_leaf_hash capture of the shipped second-generation kernel (profiles/leaf_sponge_traffic.json, profiles/r2m_kernels.json)")}[build[0]]
+                              2: (round(ipp2), "ncu smsp__inst_executed x 32 / permutations of the k_leaf_hash capture of the shipped second-generation kernel (profiles/leaf_sponge_traffic.json, profiles/r2r_kernels.json)")}[build[0]]
             clk = sampler.summary()
             sm_mhz = clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965
             perms_per_s = tim_v.permutations / ((km[2] + km[3]) * 1e-3) if km[2] + km[3] > 0 else None
