@@ -77,6 +77,9 @@ def main():
     cases.append(("keccak: miden-shape mixed heights", W.miden_pcs_params(), W.Workload([log_h - 1, log_h - 2, log_h - 3]), None, "keccak"))
     cases.append(("keccak: preprocessed columns", W.fast_pcs_params(), test_airs.preprocessed_workload((6, 8), (True, True)), None, "keccak"))
 
+    # RPO: the Poseidon2 kernels instantiated with the Rescue permutation, through the same partition
+    cases.append(("rpo: two heights", W.fast_pcs_params(), W.Workload([7, 6], widths=(9, 12), aux_widths=(1, 2)), None, "rpo"))
+
     if os.environ.get("SHARD_SUBSET"):      # one case per feature: mixed heights, host aux, device LogUp, preprocessed, second shape, each hash
         keep = ("miden-shape mixed heights", "fib + dummy", "LogUp aux", "preprocessed columns", "FRI arity 2^3", "second shape", "blake3: miden", "keccak: miden")
         cases = [c for c in cases if c[0].startswith(keep)]
@@ -90,7 +93,7 @@ def main():
             split = B.Session(params, local)
             if hash_name != "poseidon2":
                 for s_ in (single, split):
-                    s_.set_hash({"blake3": B.HASH_BLAKE3, "keccak": B.HASH_KECCAK}[hash_name], W.initial_hash_challenger(params))
+                    s_.set_hash({"blake3": B.HASH_BLAKE3, "keccak": B.HASH_KECCAK, "rpo": B.HASH_RPO}[hash_name], W.initial_hash_challenger(params))
             split.set_shard(rank, world, allgather)
             for s_ in (single, split):
                 lib.mdn_set_debug(s_.handle, 1 if os.environ.get("SHARD_DEBUG_STAGES") else 0)
@@ -101,7 +104,7 @@ def main():
         name, params, wl, aux = case[:4]
         hash_name = case[4] if len(case) > 4 else "poseidon2"
         cb = B.AUX_BUILDER(aux) if aux is not None else None
-        ch = W.initial_challenger(params, observe) if hash_name == "poseidon2" else None
+        ch = W.initial_challenger(params, observe) if hash_name in ("poseidon2", "rpo") else None      # any pre-bound duplex state is a valid statement
         single, split = sess_for(params, hash_name)
         if getattr(wl, "preprocessed", None) is not None:
             single.set_preprocessed(wl.statement, wl.preprocessed_matrices)
