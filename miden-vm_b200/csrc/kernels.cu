@@ -837,6 +837,59 @@ void launch_grind_kk(const u64* d_input_words, u32 n_words, u32 bits, u64 start,
 }
 
 // =============================================================================================
+// The small layers of a Merkle (sub-)tree in ONE block: layers d_from-1 ... lg of the sub-tree of `rank` (2^(d - lg) nodes of
+// layer d, starting at node rank << (d - lg); the whole tree with lg = 0, rank = 0).  A layer with fewer nodes than the GPU has
+// threads costs one permutation latency plus a launch when it is its own kernel; here consecutive layers are separated by a
+// block barrier only (the block's own global stores are visible to it after __syncthreads()).  HK = mdn_hash_kind.
+// =============================================================================================
+template <int HK>
+__device__ __forceinline__ void compress_pair(const u64* l, const u64* r, u64* o) {
+    if constexpr (HK == 1) b3::compress2(l, r, o);
+    else if constexpr (HK == 2) kk::compress2(l, r, o);
+    else {
+        u64 s[12] = {l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], 0, 0, 0, 0};
+        alg_permute<HK>(s);
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = glf::canon(s[k]);
+    }
+}
+template <int HK>
+__global__ void __launch_bounds__(256) k_compress_top(u64* tree, u32 d_from, u32 lg, u32 rank) {
+    for (u32 d = d_from; d-- > lg;) {
+        const u32 cnt = 1u << (d - lg);
+        const size_t start = (size_t)rank << (d - lg);
+        const u64* child = tree + (((size_t)2 << d) - 1) * 4;      // layer d + 1
+        u64* par = tree + (((size_t)1 << d) - 1) * 4;
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const size_t node = start + i;
+            const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + node * 8);
+            ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2], b1 = c[3];
+            u64 l[4] = {a0.x, a0.y, a1.x, a1.y}, r[4] = {b0.x, b0.y, b1.x, b1.y}, o[4];
+            compress_pair<HK>(l, r, o);
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(par + node * 4);
+            dst[0] = make_ulonglong2(o[0], o[1]);
+            dst[1] = make_ulonglong2(o[2], o[3]);
+        }
+        __syncthreads();
+    }
+}
+template <int HK>
+static void launch_compress_top_t(u64* tree, u32 d_from, u32 lg, u32 rank, cudaStream_t st) {
+    k_compress_top<HK><<<1, 256, 0, st>>>(tree, d_from, lg, rank);
+    COUNT_LAUNCH();
+}
+void launch_compress_top(u64* tree, u32 d_from, u32 lg, u32 rank, int hash_kind, cudaStream_t st) {
+    if (d_from <= lg) return;
+    switch (hash_kind) {
+        case 1: launch_compress_top_t<1>(tree, d_from, lg, rank, st); break;
+        case 2: launch_compress_top_t<2>(tree, d_from, lg, rank, st); break;
+        case 3: launch_compress_top_t<3>(tree, d_from, lg, rank, st); break;
+        case 4: launch_compress_top_t<4>(tree, d_from, lg, rank, st); break;
+        default: launch_compress_top_t<0>(tree, d_from, lg, rank, st); break;
+    }
+}
+
+// =============================================================================================
 // Constraint evaluation (op-list interpreter) + quotient accumulation
 // =============================================================================================
 struct ConstraintKArgs {

@@ -107,6 +107,8 @@ void launch_compress_layer(const u64* children, u64* parents, size_t n_parents, 
 void launch_fri_leaf_hash(const u64* evals /* EF interleaved */, size_t rows, u32 log_arity, const PushDst& digests,
                           u32 log_b, u32 t0, u32 nt, cudaStream_t st, int perm = 0);
 void launch_poseidon2_batch(u64* states, size_t n, cudaStream_t st);
+// layers d_from-1 ... lg of the sub-tree of `rank` (heap-ordered tree, 4 u64 per node) in one block; hash_kind = mdn_hash_kind
+void launch_compress_top(u64* tree, u32 d_from, u32 lg, u32 rank, int hash_kind, cudaStream_t st);
 // The same three tree kernels and the proof-of-work search for the Blake3_256 configuration (air/src/config.rs:276-307):
 // chaining leaf hasher (4-lane SoA states), blake3(left || right) nodes, hash-challenger PoW over the challenger's input
 // buffer (d_input_words, whole 32-bit words).

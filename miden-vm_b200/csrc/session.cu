@@ -208,6 +208,20 @@ struct mdn_session {
     u32 align() const { return hash_kind == MDN_HASH_BLAKE3 ? 1u : hash_kind == MDN_HASH_KECCAK ? 17u : 8u; }
     bool byte_hash() const { return hash_kind == MDN_HASH_BLAKE3 || hash_kind == MDN_HASH_KECCAK; }     // hash challenger, not the duplex one
     int perm() const { return byte_hash() ? 0 : hash_kind; }                                             // rescue.cuh permutations share the Poseidon2 kernels
+    // Compression layers d_from-1 ... lg of the sub-tree of `rank` (the whole tree: lg = 0, rank = 0): one launch per layer while a
+    // layer has more than 512 nodes, then ONE single-block launch for the rest (mk::launch_compress_top).  Returns the permutations.
+    size_t compress_subtree(Tree& t, u32 d_from, u32 lg, u32 rank) {
+        static constexpr u32 TOP = 10;
+        size_t n_perm = 0;
+        u32 d = d_from;
+        for (; d > lg && d - 1 - lg >= TOP; d--) {
+            size_t cnt = (size_t)1 << (d - 1 - lg), start = (size_t)rank << (d - 1 - lg);
+            n_perm += cnt;
+            compress_layer(t.layer(d) + 2 * start * 4, t.layer(d - 1) + start * 4, cnt);
+        }
+        if (d > lg) { n_perm += ((size_t)1 << (d - lg)) - 1; mk::launch_compress_top(t.nodes.p, d, lg, rank, hash_kind, stream); }
+        return n_perm;
+    }
     u32 state_words() const { return hash_kind == MDN_HASH_KECCAK ? 25u : 12u; }      // leaf state handed on between height groups
     std::vector<uint8_t> hash_ch_in, hash_ch_out;          // pre-bound HashChallenger state (mdn_session_set_hash_challenger)
     void hash_leaves(const mk::LeafArgs& a, u32 ln, u32 lb, const u64* prev, u32 prev_log, u64* states_out, const mk::PushDst* dig, u32 tb, u32 tn) {
@@ -627,22 +641,17 @@ void mdn_session::build_tree(Committed& c) {
     shard_barrier();   // every digest of this rank's leaf range (or of the whole replicated tree) has arrived
     if (!split) {
         ProfScope ps(prof, PC_COMPRESS);
-        perms += L - 1;
-        for (u32 d = depth; d-- > 0;) compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d);
+        perms += compress_subtree(c.tree, depth, 0, 0);
     } else {
         {
             ProfScope ps(prof, PC_COMPRESS);
-            for (u32 d = depth; d-- > lg;) {
-                size_t cnt = (size_t)1 << (d - lg), start = (size_t)shard_rank << (d - lg);
-                perms += cnt;
-                compress_layer(c.tree.layer(d + 1) + 2 * start * 4, c.tree.layer(d) + start * 4, cnt);
-            }
+            perms += compress_subtree(c.tree, depth, lg, shard_rank);
         }
         u64* mine = c.tree.layer(lg) + (size_t)shard_rank * 4;
         mk::launch_push(mine, peers_of(mine), shard_rank, shard_world, 4, stream);
         shard_barrier();
         ProfScope ps(prof, PC_COMPRESS);
-        for (u32 d = lg; d-- > 0;) compress_layer(c.tree.layer(d + 1), c.tree.layer(d), (size_t)1 << d);
+        compress_subtree(c.tree, lg, 0, 0);
     }
     CUDA_OK(cudaMemcpyAsync(c.root, c.tree.layer(0), 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -1676,21 +1685,18 @@ void mdn_session::finish() {
         if (in_sh) shard_barrier();
         if (!split) {
             ProfScope ps(prof, PC_FRI);
-            for (u32 d = t.depth; d-- > 0;) compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d);
+            compress_subtree(t, t.depth, 0, 0);
         } else {
             const u32 lg = shard_log_g;
             {
                 ProfScope ps(prof, PC_FRI);
-                for (u32 d = t.depth; d-- > lg;) {
-                    size_t cnt = (size_t)1 << (d - lg), start = (size_t)shard_rank << (d - lg);
-                    compress_layer(t.layer(d + 1) + 2 * start * 4, t.layer(d) + start * 4, cnt);
-                }
+                compress_subtree(t, t.depth, lg, shard_rank);
             }
             u64* mine = t.layer(lg) + (size_t)shard_rank * 4;
             mk::launch_push(mine, peers_of(mine), shard_rank, shard_world, 4, stream);
             shard_barrier();
             ProfScope ps(prof, PC_FRI);
-            for (u32 d = lg; d-- > 0;) compress_layer(t.layer(d + 1), t.layer(d), (size_t)1 << d);
+            compress_subtree(t, lg, 0, 0);
         }
         u64 root[4];
         CUDA_OK(cudaMemcpyAsync(root, t.layer(0), sizeof root, cudaMemcpyDeviceToHost, stream));
