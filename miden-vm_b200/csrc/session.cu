@@ -240,6 +240,11 @@ struct mdn_session {
     void shard_teardown();
     void shard_barrier();
     void shard_check(const char* where);
+    // the same check folded into a stream synchronisation the caller performs anyway: enqueue the copy of the barrier
+    // flag before that synchronisation, evaluate it after (one host round trip less per commitment of a split proof)
+    u32 shard_flag_host = 0;
+    void shard_check_enqueue();
+    void shard_check_finish(const char* where);
     mk::PeerPtrs peers_of(const u64* p) const;
     mk::PushDst push_dst(u64* p, u32 mode, u32 owner_shift = 0) const;
     std::map<u32, std::unique_ptr<NttPlan>> ntt_plans;
@@ -474,6 +479,15 @@ void mdn_session::shard_check(const char* where) {
     if (flag & 8) { CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); fail(MDN_ERR_CUDA, "cross-GPU barrier timed out (%s): a peer rank stopped or proves a different statement", where); }
 }
 
+void mdn_session::shard_check_enqueue() {
+    shard_flag_host = 0;
+    if (sharded()) CUDA_OK(cudaMemcpyAsync(&shard_flag_host, d_flag.p, sizeof shard_flag_host, cudaMemcpyDeviceToHost, stream));
+}
+void mdn_session::shard_check_finish(const char* where) {
+    if (!sharded()) return;
+    if (shard_flag_host & 8) { CUDA_OK(cudaMemsetAsync(d_flag.p, 0, 8, stream)); fail(MDN_ERR_CUDA, "cross-GPU barrier timed out (%s): a peer rank stopped or proves a different statement", where); }
+}
+
 void mdn_session::check_input_flag(const char* what) {
     u32 flag = 0;
     CUDA_OK(cudaMemcpyAsync(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, stream));
@@ -654,8 +668,9 @@ void mdn_session::build_tree(Committed& c) {
         compress_subtree(c.tree, lg, 0, 0);
     }
     CUDA_OK(cudaMemcpyAsync(c.root, c.tree.layer(0), 4 * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    shard_check_enqueue();
     CUDA_OK(cudaStreamSynchronize(stream));
-    shard_check("commitment");
+    shard_check_finish("commitment");
 }
 
 // GrindingChallenger::grind on the device: smallest witness (sequential p3 order), then the
@@ -1715,7 +1730,7 @@ void mdn_session::finish() {
         }
         log_dom -= la;
     }
-    shard_check("FRI commit phase");
+    shard_check_enqueue();        // evaluated after the synchronisation of the final-layer copy below
     // final polynomial (fri/prover.rs:228-239): values on the size-final_deg subgroup are the
     // final-layer entries at natural indices i*B; iDFT on the host, sent in descending order.
     {
@@ -1723,6 +1738,7 @@ void mdn_session::finish() {
         std::vector<u64> lay(2 * dom);
         CUDA_OK(cudaMemcpyAsync(lay.data(), fri_layers[rounds].p, 2 * dom * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
+        shard_check_finish("FRI commit phase");
         size_t stride = dom / final_deg;
         u32 lf = 0; while (((size_t)1 << lf) < final_deg) lf++;
         u64 wi = gl::inv(gl::two_adic_generator(lf)), ninv = gl::inv((u64)final_deg);
@@ -1813,8 +1829,9 @@ void mdn_session::finish() {
         }
         std::vector<u64> vals(ptrs.size());
         CUDA_OK(cudaMemcpyAsync(vals.data(), d_vals.p, vals.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        shard_check_enqueue();
         CUDA_OK(cudaStreamSynchronize(stream));
-        shard_check("query openings");
+        shard_check_finish("query openings");
         size_t o = 0;
         for (auto& e : plan) {
             if (e.kind == 0) { for (size_t i = 0; i < e.count; i++) tr.hint_field(vals[o++]); for (size_t i = 0; i < e.pad; i++) tr.hint_field(0); }
