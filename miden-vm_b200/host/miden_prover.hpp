@@ -15,6 +15,8 @@
 //   ProverInstance::prove(challenger) -> StarkOutput              ProverInstance::prove(challenger) -> StarkOutput
 //   StarkProofData { log_trace_heights, transcript }              miden::StarkProofData
 //   ProverError::{Instance, Domain, ..}  prover/mod.rs:582-596    miden::ProverError { kind, what() }
+//   HashFunction::{Blake3_256, Keccak, Rpo256, Poseidon2, Rpx256} -> the config constructor (prover/src/lib.rs:245-301)
+//                                                                 miden::HashFunction + StarkConfig::with_hash
 //
 // Header-only; link with -lmiden_b200.  There is no CPU fallback: constructing a StarkConfig without a usable
 // CUDA device throws ProverError{NoDevice}.
@@ -35,7 +37,7 @@ using QuadFelt = std::array<Felt, 2>;        // (c0, c1) of F[u]/(u^2 - 7)
 using Commitment = std::array<Felt, 4>;      // Hash<Felt, Felt, 4>
 
 struct ProverError : std::runtime_error {
-    enum Kind { Instance, Domain, Cuda, Unsupported, AuxBuilder, NoDevice } kind;
+    enum Kind { Instance, Domain, Cuda, Unsupported, AuxBuilder, NoDevice, ExternalAssertion } kind;
     ProverError(Kind k, const std::string& m) : std::runtime_error(m), kind(k) {}
     static Kind from_status(int rc) {
         switch (rc) {
@@ -44,6 +46,7 @@ struct ProverError : std::runtime_error {
             case MDN_ERR_UNSUPPORTED: return Unsupported;
             case MDN_ERR_AUX_BUILDER: return AuxBuilder;
             case MDN_ERR_NO_DEVICE: return NoDevice;
+            case MDN_ERR_EXTERNAL_ASSERTION: return ExternalAssertion;
             default: return Instance;
         }
     }
@@ -54,6 +57,9 @@ struct PcsParams {
     uint32_t folding_pow_bits = 4, deep_pow_bits = 12, num_queries = 27, query_pow_bits = 16;   // air/src/config.rs:55-67
     mdn_pcs_params raw() const { return {log_blowup, log_folding_arity, log_final_degree, folding_pow_bits, deep_pow_bits, num_queries, query_pow_bits}; }
 };
+
+// `HashFunction` of miden_prover::prove_stark's match (prover/src/lib.rs:245-301) = which miden_air::config constructor applies
+enum class HashFunction { Poseidon2 = MDN_HASH_POSEIDON2, Blake3_256 = MDN_HASH_BLAKE3, Keccak = MDN_HASH_KECCAK, Rpo256 = MDN_HASH_RPO, Rpx256 = MDN_HASH_RPX };
 
 // p3 DuplexChallenger<Felt, Poseidon2, 12, 8> state (air/src/config.rs:223,264-271)
 struct Challenger {
@@ -156,11 +162,29 @@ public:
         if (rc != MDN_OK) throw ProverError(ProverError::from_status(rc), mdn_last_error(nullptr));
         session_.reset(s, mdn_session_destroy);
     }
+    // blake3_256_config / keccak_config / rpo_config / rpx_config instead of poseidon2_config.  For the two byte-oriented
+    // configurations `hash_challenger_input` is the HashChallenger's input buffer after config.challenger() +
+    // observe_protocol_params (relation digest + 8 parameter felts, little-endian u64) and the Challenger prototype is unused;
+    // for RPO / RPX the prototype must be the duplex state built over that permutation.
+    StarkConfig& with_hash(HashFunction h, const std::vector<uint8_t>& hash_challenger_input = {}) {
+        int rc = mdn_session_set_hash(session_.get(), (mdn_hash_kind)h);
+        if (rc != MDN_OK) throw ProverError(ProverError::from_status(rc), mdn_last_error(session_.get()));
+        if (h == HashFunction::Blake3_256 || h == HashFunction::Keccak) {
+            mdn_hash_challenger hc{hash_challenger_input.data(), hash_challenger_input.size(), nullptr, 0};
+            rc = mdn_session_set_hash_challenger(session_.get(), &hc);
+            if (rc != MDN_OK) throw ProverError(ProverError::from_status(rc), mdn_last_error(session_.get()));
+        }
+        hash_ = h;
+        return *this;
+    }
+    HashFunction hash() const { return hash_; }
+    bool hash_challenger() const { return hash_ == HashFunction::Blake3_256 || hash_ == HashFunction::Keccak; }
     const PcsParams& pcs() const { return params_; }
     Challenger challenger() const { return proto_; }
     mdn_session* session() const { return session_.get(); }
 private:
     PcsParams params_; Challenger proto_;
+    HashFunction hash_ = HashFunction::Poseidon2;
     std::shared_ptr<mdn_session> session_;
 };
 
@@ -234,7 +258,7 @@ public:
         std::vector<mdn_matrix> mats;
         for (const RowMajorMatrix& t : ps_.traces) mats.push_back(t.raw());
         mdn_proof proof{};
-        int rc = mdn_prove(config_.session(), &low.st, mats.data(), &challenger.raw, aux_ ? &ProverInstance::trampoline : nullptr,
+        int rc = mdn_prove(config_.session(), &low.st, mats.data(), config_.hash_challenger() ? nullptr : &challenger.raw, aux_ ? &ProverInstance::trampoline : nullptr,
                            (void*)this, 0, &proof);
         detail::check(config_, rc);
         StarkOutput out;

@@ -11,6 +11,7 @@ extern "C" {
 int orc_verify(const void* params, const void* st, const void* proof, const void* challenger);
 int orc_verify_pp(const void* params, const void* st, const void* proof, const void* challenger, const uint64_t* prep_commitment);
 const char* orc_last_error();
+int orc_set_hash(int kind, const uint8_t* challenger_input, size_t n);
 }
 
 using namespace miden;
@@ -143,6 +144,37 @@ int main() {
         CHECK(verify(st, params, out.proof, proto, &wrong) != 0);
         Statement plain = Statement::with_default_observe({dummy_miden_air(9, 1)}, {});
         CHECK(Preprocessed::build(plain, *config) == nullptr);
+    }
+    // 4. the other HashFunctions of prove_stark: the same statement under Blake3_256, Keccak, Rpo256, Rpx256; every proof is
+    //    accepted by the oracle verifier in that mode only, and the config returns to Poseidon2
+    {
+        config.reset(new StarkConfig(params, proto, 0));      // a fresh session: the one above still holds section 3's preprocessed bundle
+        Statement st = Statement::with_default_observe({dummy_miden_air(18, 2), dummy_miden_air(9, 1)}, {});
+        ProverStatement ps(st, {synthetic_trace(0, 6, 18), synthetic_trace(1, 5, 9)});
+        StarkOutput p2 = ProverInstance(*config, ps, nullptr).prove(config->challenger());
+        std::vector<uint8_t> init;                       // relation digest + parameter felts as little-endian bytes
+        {
+            static const Felt RELATION_DIGEST[4] = {837197885082815666ULL, 17812429367884914ULL, 12945170128166309606ULL, 6547471563106428306ULL};
+            std::vector<Felt> f(RELATION_DIGEST, RELATION_DIGEST + 4);
+            for (Felt v : {Felt(params.num_queries), Felt(params.query_pow_bits), Felt(params.deep_pow_bits), Felt(params.folding_pow_bits),
+                           Felt(params.log_blowup), Felt(params.log_final_degree), Felt(1) << params.log_folding_arity, Felt(0)}) f.push_back(v);
+            for (Felt v : f) for (int k = 0; k < 8; k++) init.push_back((uint8_t)(v >> (8 * k)));
+        }
+        const HashFunction kinds[4] = {HashFunction::Blake3_256, HashFunction::Keccak, HashFunction::Rpo256, HashFunction::Rpx256};
+        for (HashFunction h : kinds) {
+            config->with_hash(h, init);
+            StarkOutput out = ProverInstance(*config, ps, nullptr).prove(config->challenger());
+            CHECK(out.proof.transcript.commitments[0] != p2.proof.transcript.commitments[0]);
+            CHECK(orc_set_hash((int)h, init.data(), init.size()) == 0);
+            CHECK(verify(st, params, out.proof, proto) == 0);
+            StarkProofData bad = out.proof; bad.transcript.fields[bad.transcript.fields.size() / 3] ^= 1;
+            CHECK(verify(st, params, bad, proto) != 0);
+            CHECK(orc_set_hash(0, nullptr, 0) == 0);
+            CHECK(verify(st, params, out.proof, proto) != 0);          // the Poseidon2 verifier rejects it
+        }
+        config->with_hash(HashFunction::Poseidon2);
+        StarkOutput back = ProverInstance(*config, ps, nullptr).prove(config->challenger());
+        CHECK(back.proof.transcript.fields == p2.proof.transcript.fields && back.proof.transcript.commitments == p2.proof.transcript.commitments);
     }
     printf("HOST_API_OK\n");
     return 0;
