@@ -182,6 +182,7 @@ public:
     const PcsParams& pcs() const { return params_; }
     Challenger challenger() const { return proto_; }
     mdn_session* session() const { return session_.get(); }
+    const std::shared_ptr<mdn_session>& shared_session() const { return session_; }
 private:
     PcsParams params_; Challenger proto_;
     HashFunction hash_ = HashFunction::Poseidon2;
@@ -237,11 +238,18 @@ public:
         for (const Air& a : s.airs) mats.push_back(a.preprocessed_width ? a.preprocessed_trace.raw() : mdn_matrix{nullptr, 0, 0});
         auto p = std::unique_ptr<Preprocessed>(new Preprocessed());
         detail::check(config, mdn_session_set_preprocessed(config.session(), &low.st, mats.data(), p->commitment_.data()));
+        p->session_ = config.shared_session();
         return p;
     }
+    // the bundle lives in the session while this object does (the reference lends `&Preprocessed` to each ProverInstance)
+    ~Preprocessed() { if (session_) mdn_session_set_preprocessed(session_.get(), nullptr, nullptr, nullptr); }
+    Preprocessed(const Preprocessed&) = delete;
+    Preprocessed& operator=(const Preprocessed&) = delete;
     const Commitment& commitment() const { return commitment_; }
 private:
+    Preprocessed() {}
     Commitment commitment_{};
+    std::shared_ptr<mdn_session> session_;
 };
 
 class ProverInstance {

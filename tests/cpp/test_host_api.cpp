@@ -148,7 +148,6 @@ int main() {
     // 4. the other HashFunctions of prove_stark: the same statement under Blake3_256, Keccak, Rpo256, Rpx256; every proof is
     //    accepted by the oracle verifier in that mode only, and the config returns to Poseidon2
     {
-        config.reset(new StarkConfig(params, proto, 0));      // a fresh session: the one above still holds section 3's preprocessed bundle
         Statement st = Statement::with_default_observe({dummy_miden_air(18, 2), dummy_miden_air(9, 1)}, {});
         ProverStatement ps(st, {synthetic_trace(0, 6, 18), synthetic_trace(1, 5, 9)});
         StarkOutput p2 = ProverInstance(*config, ps, nullptr).prove(config->challenger());
